@@ -1,0 +1,199 @@
+"""ctypes mirror of include/biceps_b200.h and the loader of the CUDA library.
+
+There is no CPU fallback: if lib/libbiceps_b200.so is missing or fails to load, every
+entry point of the package raises.  Build it with `python __graft_entry__.py build`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbiceps_b200.so")
+
+BCP_KIND_SCALAR, BCP_KIND_GAMMA, BCP_KIND_PFGRID = 0, 1, 2
+BCP_MAX_RESTRAINTS = 8
+BCP_PF_NGRID = 6
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+c_uint8_p = C.POINTER(C.c_uint8)
+
+
+class bcp_restraint(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_sigma", C.c_int32), ("n_gamma", C.c_int32),
+                ("has_ref", C.c_int32), ("cnorm", C.c_double),
+                ("nlsig", c_double_p), ("two_sig2", c_double_p), ("sse", c_double_p),
+                ("refsum", c_double_p),
+                ("pf_n", C.c_int32 * BCP_PF_NGRID), ("pf_n_obs", C.c_int32),
+                ("pf_ref_kind", C.c_int32),
+                ("pf_grid", c_double_p), ("pf_Nc", c_double_p), ("pf_Nh", c_double_p),
+                ("pf_exp", c_double_p), ("pf_weight", c_double_p), ("pf_prior", c_double_p)]
+
+
+class bcp_tables(C.Structure):
+    _fields_ = [("n_states", C.c_int32), ("n_lambda", C.c_int32), ("n_restraints", C.c_int32),
+                ("reserved", C.c_int32), ("energy", c_double_p), ("logZ", c_double_p),
+                ("restraints", C.POINTER(bcp_restraint))]
+
+
+class bcp_chain_cfg(C.Structure):
+    _fields_ = [("n_chains", C.c_int64), ("seed", C.c_uint64), ("chain_id0", C.c_uint64),
+                ("n_groups", C.c_int32), ("reserved", C.c_int32),
+                ("chain_lambda", c_int32_p), ("chain_group", c_int32_p), ("init_state", c_int32_p)]
+
+
+class bcp_sample_cfg(C.Structure):
+    _fields_ = [("n_steps", C.c_int64), ("burn", C.c_int64), ("traj_every", C.c_int64),
+                ("record_state_trace", C.c_int32), ("reserved", C.c_int32)]
+
+
+class bcp_sample_out(C.Structure):
+    _fields_ = [("state_counts", c_int64_p), ("param_counts", c_int64_p),
+                ("accepted", c_int64_p), ("total", c_int64_p), ("sep_accepted", c_int64_p),
+                ("state", c_int32_p), ("indices", c_int32_p), ("energy", c_double_p),
+                ("traj_energy", c_double_p), ("traj_state", c_int32_p),
+                ("traj_accept", c_uint8_p), ("traj_indices", c_int32_p),
+                ("state_trace", c_int32_p)]
+
+
+def _ptr(a, ctype):
+    if a is None:
+        return C.cast(None, C.POINTER(ctype))
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def dptr(a):
+    return _ptr(a, C.c_double)
+
+
+def i32ptr(a):
+    return _ptr(a, C.c_int32)
+
+
+def i64ptr(a):
+    return _ptr(a, C.c_int64)
+
+
+def u8ptr(a):
+    return _ptr(a, C.c_uint8)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class PackedTables(object):
+    """Owns contiguous numpy copies of a `tables` dict (see flatten.py) and exposes the
+    bcp_tables struct that points into them.  `tables["energy"]` may be [S] or [K][S]."""
+
+    def __init__(self, tables):
+        self._keep = []
+        energy = np.atleast_2d(f64(tables["energy"]))
+        logZ = np.atleast_1d(f64(tables["logZ"]))
+        K, S = energy.shape
+        if logZ.shape[0] != K:
+            raise ValueError("logZ must have one entry per lambda (got %d for %d)" % (logZ.shape[0], K))
+        rs = tables["restraints"]
+        if not (1 <= len(rs) <= BCP_MAX_RESTRAINTS):
+            raise ValueError("number of restraints must be in 1..%d" % BCP_MAX_RESTRAINTS)
+        arr = (bcp_restraint * len(rs))()
+        for q, rt in enumerate(rs):
+            r = arr[q]
+            kind = {"scalar": BCP_KIND_SCALAR, "gamma": BCP_KIND_GAMMA, "pfgrid": BCP_KIND_PFGRID}[rt["kind"]]
+            r.kind = kind
+            nlsig, two = f64(rt["nlsig"]), f64(rt["two_sig2"])
+            r.n_sigma = nlsig.shape[0]
+            r.cnorm = float(rt["cnorm"])
+            r.nlsig, r.two_sig2 = dptr(nlsig), dptr(two)
+            self._keep += [nlsig, two]
+            r.n_gamma = 1
+            if kind != BCP_KIND_PFGRID:
+                sse = f64(rt["sse"])
+                if kind == BCP_KIND_GAMMA:
+                    if sse.ndim != 2 or sse.shape[0] != S:
+                        raise ValueError("restraint %d: sse must be [S][G]" % q)
+                    r.n_gamma = sse.shape[1]
+                elif sse.shape != (S,):
+                    raise ValueError("restraint %d: sse must be [S]" % q)
+                r.sse = dptr(sse)
+                self._keep.append(sse)
+                if rt.get("refsum") is not None:
+                    ref = f64(rt["refsum"])
+                    if ref.shape != (S,):
+                        raise ValueError("restraint %d: refsum must be [S]" % q)
+                    r.has_ref, r.refsum = 1, dptr(ref)
+                    self._keep.append(ref)
+            else:
+                pf = rt["pf"]
+                grids = [f64(g) for g in rt["grids"]]
+                for k in range(BCP_PF_NGRID):
+                    r.pf_n[k] = grids[k].shape[0]
+                gcat = f64(np.concatenate(grids))
+                Nc, Nh = f64(pf["Nc"]), f64(pf["Nh"])
+                ex, w = f64(pf["exp"]), f64(pf["weight"])
+                r.pf_n_obs = ex.shape[0]
+                r.pf_ref_kind = 1 if rt.get("ref") == "exponential" else 0
+                r.pf_grid, r.pf_Nc, r.pf_Nh, r.pf_exp, r.pf_weight = dptr(gcat), dptr(Nc), dptr(Nh), dptr(ex), dptr(w)
+                self._keep += [gcat, Nc, Nh, ex, w]
+                if rt.get("prior") is not None:
+                    pr = f64(rt["prior"])
+                    r.pf_prior = dptr(pr)
+                    self._keep.append(pr)
+        self._keep += [energy, logZ, arr]
+        self.struct = bcp_tables(S, K, len(rs), 0, dptr(energy), dptr(logZ), arr)
+        self.n_states, self.n_lambda, self.n_restraints = S, K, len(rs)
+
+
+_SIGS = {
+    "bcp_abi_version": (C.c_int, []),
+    "bcp_last_error": (C.c_char_p, []),
+    "bcp_kernel_launches": (C.c_uint64, []),
+    "bcp_create": (C.c_int, [C.POINTER(bcp_tables), C.c_int, C.POINTER(C.c_void_p)]),
+    "bcp_destroy": (None, [C.c_void_p]),
+    "bcp_n_params": (C.c_int, [C.c_void_p]),
+    "bcp_param_bins": (C.c_int, [C.c_void_p]),
+    "bcp_param_layout": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p]),
+    "bcp_chains_create": (C.c_int, [C.c_void_p, C.POINTER(bcp_chain_cfg), C.POINTER(C.c_void_p)]),
+    "bcp_chains_destroy": (None, [C.c_void_p]),
+    "bcp_sample": (C.c_int, [C.c_void_p, C.POINTER(bcp_sample_cfg), C.POINTER(bcp_sample_out)]),
+    "bcp_sample_launch": (C.c_int, [C.c_void_p, C.POINTER(bcp_sample_cfg), C.c_void_p]),
+    "bcp_chains_sync": (C.c_int, [C.c_void_p]),
+    "bcp_chains_fetch": (C.c_int, [C.c_void_p, C.POINTER(bcp_sample_out)]),
+    "bcp_chains_device_hist": (C.c_int, [C.c_void_p, C.POINTER(c_int64_p), C.POINTER(c_int64_p)]),
+    "bcp_chains_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), c_int32_p]),
+    "bcp_neglogp": (C.c_int, [C.c_void_p, C.c_int64, c_int32_p, c_int32_p, c_int32_p, c_double_p]),
+}
+
+_lib = None
+
+
+def declare(lib, sigs):
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+def lib():
+    """The loaded CUDA library; raises if it has not been built (no CPU fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("biceps_b200: %s is missing -- build it with "
+                               "`python __graft_entry__.py build`; there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        declare(L, _SIGS)
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().bcp_last_error()
+        raise RuntimeError("biceps_b200 %s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))

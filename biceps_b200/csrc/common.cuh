@@ -1,0 +1,64 @@
+// Shared host-side helpers for the biceps_b200 C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/biceps_b200.h"
+
+namespace bcp {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_kernel_launches;
+
+#define BCP_CUDA(call)                                                                    \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            bcp::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                           cudaGetErrorString(e__));                                      \
+            return BCP_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+#define BCP_REQUIRE(cond, ...)                                                            \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            bcp::set_error(__VA_ARGS__);                                                  \
+            return BCP_ERR_INVALID;                                                       \
+        }                                                                                 \
+    } while (0)
+
+#define BCP_LAUNCHED(n) bcp::g_kernel_launches.fetch_add((n), std::memory_order_relaxed)
+
+// RAII device-selection guard: every entry point runs on the handle's device and restores
+// the caller's current device afterwards.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+static inline cudaError_t dev_alloc(T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) return cudaSuccess;
+    return cudaMalloc((void**)p, n * sizeof(T));
+}
+
+static inline int num_sms(int device) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    return n;
+}
+
+}  // namespace bcp

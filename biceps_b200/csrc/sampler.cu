@@ -1,0 +1,756 @@
+// K5: many independent Metropolis chains over (state, sigma index, gamma index).
+//
+// Replaces PosteriorSampler.sample / neglogP and Restraint_*.compute_neglogP
+// (/root/reference/biceps/PosteriorSampler.py:233-374, Restraint.py:356-383, 457-477,
+// 572-592).  One thread = one chain, one warp = a batch of 32 chains.  Per step a chain
+//   1. generates its Philox4x32-10 block for (chain id, step)          [philox.cuh]
+//   2. proposes either a uniform random state or a +-1 move of all parameters of one
+//      restraint (periodic wrap)                                       [:298-307]
+//   3. re-evaluates only the restraint terms the move touches, in the reference's exact
+//      fp64 order: t = ((nlsig[s] + sse/two_sig2[s]) + cnorm) - refsum,
+//      E = (energy_i + logZ) + t_0 + t_1 + ...                         [:233-248]
+//   4. Metropolis test                                                  [:322-326]
+//   5. bookkeeping: acceptance counters, state / parameter histograms (run-length
+//      compressed: a counter is flushed only when the state or index changes), thinned
+//      snapshots and the optional state trace                          [:329-358]
+// The sigma-dependent vectors of all restraints (a few KB) are staged once per CTA into
+// shared memory with a 1-D TMA bulk copy; the state-dependent words are gathered from L2.
+#include "common.cuh"
+#include "exp_det.cuh"
+#include "philox.cuh"
+
+#include <vector>
+
+namespace bcp {
+
+constexpr int MAXR = BCP_MAX_RESTRAINTS;
+
+struct RestraintDev {
+    const double* sse;      // [S][G]
+    const double* refsum;   // [S] or nullptr
+    double cnorm;
+    int sig_off;            // doubles into the staged sigma table: nlsig, then two_sig2
+    int n_sigma;
+    int n_gamma;            // 1 if the restraint has no gamma
+    int hist_sigma;         // bin offset of this restraint's sigma histogram
+    int hist_gamma;         // bin offset of its gamma histogram (if has_gamma)
+    int has_gamma;          // Restraint_noe: gamma moves together with sigma
+};
+
+struct SamplerTables {
+    RestraintDev r[MAXR];
+    const double* energy;   // [K][S]
+    const double* logZ;     // [K]
+    const double* sig_tab;  // staged table in global memory (16 B aligned, padded)
+    int sig_bytes;          // multiple of 16
+    int R, S, K, P, HB;
+    uint32_t nuis_thresh;   // floor(R * 2^32 / (R+1))
+};
+
+struct ChainBuffers {
+    long long n_chains;
+    unsigned long long seed, chain_id0;
+    const int* lam;         // [n]
+    const int* group;       // [n]
+    int* state;             // [n]
+    int* isg;               // [R][n]
+    int* igm;               // [R][n]
+    double* E;              // [n]
+    unsigned long long* accepted;     // [n]
+    unsigned long long* sep;          // [R+1][n]  (this sample() call)
+    unsigned long long* state_counts; // [groups][S]
+    unsigned long long* param_counts; // [groups][HB]
+};
+
+struct LaunchArgs {
+    unsigned long long step0;   // Philox step counter of local step 0
+    long long s_begin, s_end;   // local step range of this launch
+    long long burn;
+    long long traj_every;       // 0 = none
+    long long n_snap;
+    double* traj_E;             // [n_snap][n]
+    int* traj_state;            // [n_snap][n]
+    unsigned char* traj_accept; // [n_snap][n]
+    int* traj_idx;              // [n_snap][P][n]
+    int* state_trace;           // [n_steps][n] or nullptr
+};
+
+// number of recorded steps in [a, b): those with local step >= burn
+__device__ __forceinline__ long long recorded(long long a, long long b, long long burn) {
+    const long long lo = a > burn ? a : burn;
+    return b > lo ? b - lo : 0;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// 1-D TMA bulk copy global -> shared with mbarrier completion (SASS: UBLKCP).
+__device__ __forceinline__ void stage_sigma_table(double* s_sig, const double* g_sig, int bytes,
+                                                  uint64_t* mbar) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)),
+                     "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(smem_u32(s_sig)), "l"(g_sig), "r"(bytes), "r"(smem_u32(mbar))
+            : "memory");
+    }
+    // every thread waits for phase 0
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(mbar))
+        : "memory");
+}
+
+template <int R>
+__device__ __forceinline__ double restraint_term(const SamplerTables& T, const double* s_sig, int q,
+                                                 int state, int sg, int gm) {
+    const RestraintDev& rd = T.r[q];
+    const double sse = __ldg(rd.sse + (size_t)state * rd.n_gamma + gm);
+    const double a = s_sig[rd.sig_off + sg];
+    const double d = s_sig[rd.sig_off + rd.n_sigma + sg];
+    double t = __dadd_rn(a, __ddiv_rn(sse, d));
+    t = __dadd_rn(t, rd.cnorm);
+    if (rd.refsum) t = __dsub_rn(t, __ldg(rd.refsum + state));
+    return t;
+}
+
+template <int R>
+__global__ void __launch_bounds__(256)
+mcmc_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
+            const __grid_constant__ LaunchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_sig = reinterpret_cast<double*>(smem_raw);
+    __shared__ __align__(8) uint64_t mbar;
+    stage_sigma_table(s_sig, T.sig_tab, T.sig_bytes, &mbar);
+
+    const long long n = C.n_chains;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+
+    const int lam = C.lam[c];
+    const int grp = C.group[c];
+    const unsigned long long chain_id = C.chain_id0 + (unsigned long long)c;
+    const double* energy = T.energy + (size_t)lam * T.S;
+    const double logZ = T.logZ[lam];
+    unsigned long long* g_state_counts = C.state_counts + (size_t)grp * T.S;
+    unsigned long long* g_param_counts = C.param_counts + (size_t)grp * T.HB;
+
+    int state = C.state[c];
+    double E = C.E[c];
+    int isg[R], igm[R];
+    double t[R];
+    long long since_sg[R], since_gm[R];
+    unsigned int acc_r[R];
+    unsigned int acc_state = 0, acc_total = 0;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        isg[q] = C.isg[(size_t)q * n + c];
+        igm[q] = C.igm[(size_t)q * n + c];
+        t[q] = restraint_term<R>(T, s_sig, q, state, isg[q], igm[q]);
+        since_sg[q] = A.s_begin;
+        since_gm[q] = A.s_begin;
+        acc_r[q] = 0;
+    }
+    double Cst = __dadd_rn(__ldg(energy + state), logZ);
+    long long since_state = A.s_begin;
+
+    long long next_snap = -1, snap_idx = 0;
+    if (A.traj_every > 0) {
+        // first snapshot step >= s_begin on the lattice burn + m * traj_every
+        long long m = A.s_begin <= A.burn ? 0 : (A.s_begin - A.burn + A.traj_every - 1) / A.traj_every;
+        snap_idx = m;
+        next_snap = A.burn + m * A.traj_every;
+    }
+
+    for (long long s = A.s_begin; s < A.s_end; ++s) {
+        const Philox4 w = step_block(C.seed, chain_id, A.step0 + (unsigned long long)s);
+        const bool nuis = w.w0 < T.nuis_thresh;
+        const uint64_t pr = (uint64_t)w.w1 * (uint32_t)(nuis ? R : T.S);
+        const int hi = (int)(pr >> 32);
+        uint32_t f = (uint32_t)pr;
+        const int pick = nuis ? hi : -1;
+        const int nstate = nuis ? state : hi;
+
+        // proposal: indices and the terms that change
+        int nsg = 0, ngm = 0;
+        double tn[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            tn[q] = t[q];
+            if (!nuis) {
+                tn[q] = restraint_term<R>(T, s_sig, q, nstate, isg[q], igm[q]);
+            } else if (q == pick) {
+                uint64_t z = (uint64_t)f * 3u;
+                int v = isg[q] + (int)(z >> 32) - 1;
+                f = (uint32_t)z;
+                const int ns = T.r[q].n_sigma;
+                v = v < 0 ? v + ns : (v >= ns ? v - ns : v);
+                nsg = v;
+                ngm = igm[q];
+                if (T.r[q].has_gamma) {
+                    const int ng = T.r[q].n_gamma;
+                    z = (uint64_t)f * 3u;
+                    int g2 = igm[q] + (int)(z >> 32) - 1;
+                    f = (uint32_t)z;
+                    g2 = g2 < 0 ? g2 + ng : (g2 >= ng ? g2 - ng : g2);
+                    ngm = g2;
+                }
+                tn[q] = restraint_term<R>(T, s_sig, q, state, nsg, ngm);
+            }
+        }
+        const double Cn = nuis ? Cst : __dadd_rn(__ldg(energy + nstate), logZ);
+        double En = Cn;
+#pragma unroll
+        for (int q = 0; q < R; ++q) En = __dadd_rn(En, tn[q]);
+
+        bool acc;
+        if (En < E) {
+            acc = true;
+        } else {
+            acc = metropolis_accept(__dsub_rn(E, En), u2_from_words(w.w2, w.w3));
+        }
+
+        if (acc) {
+            E = En;
+            if (!nuis) {
+                if (nstate != state) {
+                    const long long cnt = recorded(since_state, s, A.burn);
+                    if (cnt) atomicAdd(g_state_counts + state, (unsigned long long)cnt);
+                    since_state = s;
+                    state = nstate;
+                }
+                Cst = Cn;
+                ++acc_state;
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                t[q] = tn[q];
+                if (nuis && q == pick) {
+                    ++acc_r[q];
+                    if (nsg != isg[q]) {
+                        const long long cnt = recorded(since_sg[q], s, A.burn);
+                        if (cnt) atomicAdd(g_param_counts + T.r[q].hist_sigma + isg[q], (unsigned long long)cnt);
+                        since_sg[q] = s;
+                        isg[q] = nsg;
+                    }
+                    if (ngm != igm[q]) {
+                        const long long cnt = recorded(since_gm[q], s, A.burn);
+                        if (cnt) atomicAdd(g_param_counts + T.r[q].hist_gamma + igm[q], (unsigned long long)cnt);
+                        since_gm[q] = s;
+                        igm[q] = ngm;
+                    }
+                }
+            }
+            ++acc_total;
+        }
+
+        if (s >= A.burn) {
+            if (A.state_trace) A.state_trace[(size_t)(s - A.burn) * n + c] = state;
+            if (s == next_snap) {
+                const size_t o = (size_t)snap_idx * n + c;
+                A.traj_E[o] = E;
+                A.traj_state[o] = state;
+                A.traj_accept[o] = acc ? 1 : 0;
+                int p = 0;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    A.traj_idx[((size_t)snap_idx * T.P + p) * n + c] = isg[q];
+                    ++p;
+                    if (T.r[q].has_gamma) {
+                        A.traj_idx[((size_t)snap_idx * T.P + p) * n + c] = igm[q];
+                        ++p;
+                    }
+                }
+                ++snap_idx;
+                next_snap += A.traj_every;
+            }
+        }
+    }
+
+    // flush run-length counters and persist the chain
+    {
+        const long long cnt = recorded(since_state, A.s_end, A.burn);
+        if (cnt) atomicAdd(g_state_counts + state, (unsigned long long)cnt);
+    }
+    C.state[c] = state;
+    C.E[c] = E;
+    C.accepted[c] += acc_total;
+    C.sep[(size_t)R * n + c] += acc_state;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        long long cnt = recorded(since_sg[q], A.s_end, A.burn);
+        if (cnt) atomicAdd(g_param_counts + T.r[q].hist_sigma + isg[q], (unsigned long long)cnt);
+        if (T.r[q].has_gamma) {
+            cnt = recorded(since_gm[q], A.s_end, A.burn);
+            if (cnt) atomicAdd(g_param_counts + T.r[q].hist_gamma + igm[q], (unsigned long long)cnt);
+        }
+        C.isg[(size_t)q * n + c] = isg[q];
+        C.igm[(size_t)q * n + c] = igm[q];
+        C.sep[(size_t)q * n + c] += acc_r[q];
+    }
+}
+
+// initial state of every chain from the Philox block at step 2^64-1 (oracle/philox.py)
+__global__ void init_chains_kernel(long long n, unsigned long long seed, unsigned long long chain_id0,
+                                   int S, int R, const int* init_state, int* state, double* E,
+                                   int* isg, int* igm, SamplerTables T) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    int s0;
+    if (init_state) {
+        s0 = init_state[c];
+    } else {
+        const Philox4 w = step_block(seed, chain_id0 + (unsigned long long)c, BCP_INIT_STEP);
+        s0 = (int)(((uint64_t)w.w1 * (uint32_t)S) >> 32);
+    }
+    state[c] = s0;
+    E[c] = 1.0e99;
+    for (int q = 0; q < R; ++q) {
+        isg[(size_t)q * n + c] = T.r[q].n_sigma / 2;
+        igm[(size_t)q * n + c] = T.r[q].has_gamma ? T.r[q].n_gamma / 2 : 0;
+    }
+}
+
+// -log P of explicit configurations (PosteriorSampler.neglogP, PosteriorSampler.py:233-248)
+__global__ void neglogp_kernel(const SamplerTables T, long long n, const int* lam, const int* state,
+                               const int* indices, double* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int st = state[i];
+    const int l = lam ? lam[i] : 0;
+    double E = __dadd_rn(T.energy[(size_t)l * T.S + st], T.logZ[l]);
+    int p = 0;
+    for (int q = 0; q < T.R; ++q) {
+        const RestraintDev& rd = T.r[q];
+        const int sg = indices[(size_t)i * T.P + p++];
+        const int gm = rd.has_gamma ? indices[(size_t)i * T.P + p++] : 0;
+        const double sse = rd.sse[(size_t)st * rd.n_gamma + gm];
+        const double* sig = T.sig_tab + rd.sig_off;
+        double t = __dadd_rn(sig[sg], __ddiv_rn(sse, sig[rd.n_sigma + sg]));
+        t = __dadd_rn(t, rd.cnorm);
+        if (rd.refsum) t = __dsub_rn(t, rd.refsum[st]);
+        E = __dadd_rn(E, t);
+    }
+    out[i] = E;
+}
+
+}  // namespace bcp
+
+using namespace bcp;
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct bcp_handle {
+    int device = 0;
+    SamplerTables T{};
+    std::vector<void*> allocs;
+    int32_t rest_index[2 * MAXR];
+    int32_t grid_len[2 * MAXR];
+};
+
+struct bcp_chains {
+    bcp_handle* h = nullptr;
+    ChainBuffers C{};
+    int n_groups = 0;
+    unsigned long long steps_done = 0;   // Philox step counter == reference's `total`
+    int* d_lam = nullptr;
+    int* d_group = nullptr;
+    // outputs of the last sample() call
+    long long n_snap = 0, n_trace = 0;
+    double* d_traj_E = nullptr;
+    int* d_traj_state = nullptr;
+    unsigned char* d_traj_accept = nullptr;
+    int* d_traj_idx = nullptr;
+    int* d_trace = nullptr;
+    size_t cap_snap = 0, cap_trace = 0;
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_launches = 0;
+    bool sampled = false;
+};
+
+template <typename T>
+static int upload(bcp_handle* h, const T* host, size_t n, const T** dev) {
+    T* d = nullptr;
+    if (n == 0) { *dev = nullptr; return BCP_OK; }
+    BCP_CUDA(cudaMalloc((void**)&d, n * sizeof(T)));
+    h->allocs.push_back(d);
+    BCP_CUDA(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = d;
+    return BCP_OK;
+}
+
+extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
+    BCP_REQUIRE(t && out, "bcp_create: NULL argument");
+    *out = nullptr;
+    BCP_REQUIRE(t->n_states > 0 && t->n_lambda > 0, "bcp_create: n_states and n_lambda must be > 0");
+    BCP_REQUIRE(t->n_restraints > 0 && t->n_restraints <= MAXR,
+                "bcp_create: n_restraints must be in 1..%d", MAXR);
+    BCP_REQUIRE(t->energy && t->logZ && t->restraints, "bcp_create: NULL table pointer");
+    int ndev = 0;
+    BCP_CUDA(cudaGetDeviceCount(&ndev));
+    BCP_REQUIRE(device >= 0 && device < ndev, "bcp_create: device %d out of range (%d visible)", device, ndev);
+    DeviceGuard guard(device);
+
+    bcp_handle* h = new bcp_handle();
+    h->device = device;
+    SamplerTables& T = h->T;
+    T.R = t->n_restraints; T.S = t->n_states; T.K = t->n_lambda;
+    T.nuis_thresh = (uint32_t)(((uint64_t)T.R << 32) / (uint64_t)(T.R + 1));
+    int rc = BCP_OK;
+    auto fail = [&](int code) { bcp_destroy(h); return code; };
+
+    // sigma-dependent vectors of all restraints, contiguous, padded to 16 B for the bulk copy
+    std::vector<double> sig;
+    int P = 0, HB = 0;
+    for (int q = 0; q < T.R; ++q) {
+        const bcp_restraint& r = t->restraints[q];
+        if (r.kind == BCP_KIND_PFGRID) {
+            set_error("bcp_create: restraint %d: BCP_KIND_PFGRID is not supported by this build", q);
+            return fail(BCP_ERR_INVALID);
+        }
+        if (!(r.kind == BCP_KIND_SCALAR || r.kind == BCP_KIND_GAMMA) || r.n_sigma <= 0 || !r.nlsig ||
+            !r.two_sig2 || !r.sse || (r.kind == BCP_KIND_GAMMA && r.n_gamma <= 0)) {
+            set_error("bcp_create: restraint %d: bad kind/size/pointer", q);
+            return fail(BCP_ERR_INVALID);
+        }
+        RestraintDev& rd = T.r[q];
+        rd.n_sigma = r.n_sigma;
+        rd.n_gamma = r.kind == BCP_KIND_GAMMA ? r.n_gamma : 1;
+        rd.cnorm = r.cnorm;
+        rd.sig_off = (int)sig.size();
+        sig.insert(sig.end(), r.nlsig, r.nlsig + r.n_sigma);
+        sig.insert(sig.end(), r.two_sig2, r.two_sig2 + r.n_sigma);
+        rd.hist_sigma = HB; HB += rd.n_sigma;
+        h->rest_index[P] = q; h->grid_len[P] = rd.n_sigma; ++P;
+        rd.has_gamma = r.kind == BCP_KIND_GAMMA;
+        if (rd.has_gamma) {
+            rd.hist_gamma = HB; HB += rd.n_gamma;
+            h->rest_index[P] = q; h->grid_len[P] = rd.n_gamma; ++P;
+        }
+        if ((rc = upload(h, r.sse, (size_t)T.S * rd.n_gamma, &rd.sse)) != BCP_OK) return fail(rc);
+        rd.refsum = nullptr;
+        if (r.has_ref) {
+            if (!r.refsum) { set_error("bcp_create: restraint %d: has_ref but refsum is NULL", q); return fail(BCP_ERR_INVALID); }
+            if ((rc = upload(h, r.refsum, (size_t)T.S, &rd.refsum)) != BCP_OK) return fail(rc);
+        }
+    }
+    while (sig.size() % 2) sig.push_back(0.0);
+    T.P = P; T.HB = HB;
+    T.sig_bytes = (int)(sig.size() * sizeof(double));
+    if (T.sig_bytes > 200 * 1024) {
+        set_error("bcp_create: sigma grids need %d B of shared memory (limit 200 KB)", T.sig_bytes);
+        return fail(BCP_ERR_INVALID);
+    }
+    if ((rc = upload(h, sig.data(), sig.size(), &T.sig_tab)) != BCP_OK) return fail(rc);
+    if ((rc = upload(h, t->energy, (size_t)T.K * T.S, &T.energy)) != BCP_OK) return fail(rc);
+    if ((rc = upload(h, t->logZ, (size_t)T.K, &T.logZ)) != BCP_OK) return fail(rc);
+    *out = h;
+    return BCP_OK;
+}
+
+extern "C" void bcp_destroy(bcp_handle* h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+extern "C" int bcp_n_params(const bcp_handle* h) { return h ? h->T.P : BCP_ERR_INVALID; }
+extern "C" int bcp_param_bins(const bcp_handle* h) { return h ? h->T.HB : BCP_ERR_INVALID; }
+extern "C" int bcp_param_layout(const bcp_handle* h, int32_t* rest_index, int32_t* grid_len) {
+    BCP_REQUIRE(h, "bcp_param_layout: NULL handle");
+    for (int p = 0; p < h->T.P; ++p) {
+        if (rest_index) rest_index[p] = h->rest_index[p];
+        if (grid_len) grid_len[p] = h->grid_len[p];
+    }
+    return BCP_OK;
+}
+
+extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_chains** out) {
+    BCP_REQUIRE(h && cfg && out, "bcp_chains_create: NULL argument");
+    *out = nullptr;
+    BCP_REQUIRE(cfg->n_chains > 0, "bcp_chains_create: n_chains must be > 0");
+    DeviceGuard guard(h->device);
+    const SamplerTables& T = h->T;
+    const long long n = cfg->n_chains;
+    const int n_groups = cfg->n_groups > 0 ? cfg->n_groups : T.K;
+    std::vector<int> lam(n, 0), grp(n, 0);
+    for (long long i = 0; i < n; ++i) {
+        if (cfg->chain_lambda) lam[i] = cfg->chain_lambda[i];
+        BCP_REQUIRE(lam[i] >= 0 && lam[i] < T.K, "bcp_chains_create: chain_lambda[%lld]=%d out of range", i, lam[i]);
+        grp[i] = cfg->chain_group ? cfg->chain_group[i] : lam[i];
+        BCP_REQUIRE(grp[i] >= 0 && grp[i] < n_groups, "bcp_chains_create: chain_group[%lld]=%d out of range", i, grp[i]);
+        if (cfg->init_state)
+            BCP_REQUIRE(cfg->init_state[i] >= 0 && cfg->init_state[i] < T.S,
+                        "bcp_chains_create: init_state[%lld]=%d out of range", i, cfg->init_state[i]);
+    }
+    bcp_chains* c = new bcp_chains();
+    c->h = h;
+    c->n_groups = n_groups;
+    ChainBuffers& C = c->C;
+    C.n_chains = n; C.seed = cfg->seed; C.chain_id0 = cfg->chain_id0;
+    auto fail = [&](int code) { bcp_chains_destroy(c); return code; };
+#define TRY_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(e_)); return fail(BCP_ERR_CUDA); } } while (0)
+    TRY_CUDA(dev_alloc(&c->d_lam, n));
+    TRY_CUDA(dev_alloc(&c->d_group, n));
+    TRY_CUDA(cudaMemcpy(c->d_lam, lam.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    TRY_CUDA(cudaMemcpy(c->d_group, grp.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    C.lam = c->d_lam; C.group = c->d_group;
+    TRY_CUDA(dev_alloc(&C.state, n));
+    TRY_CUDA(dev_alloc(&C.isg, (size_t)T.R * n));
+    TRY_CUDA(dev_alloc(&C.igm, (size_t)T.R * n));
+    TRY_CUDA(dev_alloc(&C.E, n));
+    TRY_CUDA(dev_alloc(&C.accepted, n));
+    TRY_CUDA(dev_alloc(&C.sep, (size_t)(T.R + 1) * n));
+    TRY_CUDA(dev_alloc(&C.state_counts, (size_t)n_groups * T.S));
+    TRY_CUDA(dev_alloc(&C.param_counts, (size_t)n_groups * T.HB));
+    TRY_CUDA(cudaMemset(C.accepted, 0, n * sizeof(unsigned long long)));
+    TRY_CUDA(cudaMemset(C.sep, 0, (size_t)(T.R + 1) * n * sizeof(unsigned long long)));
+    TRY_CUDA(cudaMemset(C.state_counts, 0, (size_t)n_groups * T.S * sizeof(unsigned long long)));
+    TRY_CUDA(cudaMemset(C.param_counts, 0, (size_t)n_groups * T.HB * sizeof(unsigned long long)));
+    int* d_init = nullptr;
+    if (cfg->init_state) {
+        TRY_CUDA(dev_alloc(&d_init, n));
+        TRY_CUDA(cudaMemcpy(d_init, cfg->init_state, n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    const int tpb = 256;
+    init_chains_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb>>>(n, C.seed, C.chain_id0, T.S, T.R, d_init,
+                                                                 C.state, C.E, C.isg, C.igm, T);
+    BCP_LAUNCHED(1);
+    TRY_CUDA(cudaGetLastError());
+    TRY_CUDA(cudaDeviceSynchronize());
+    if (d_init) cudaFree(d_init);
+    TRY_CUDA(cudaEventCreate(&c->ev0));
+    TRY_CUDA(cudaEventCreate(&c->ev1));
+#undef TRY_CUDA
+    *out = c;
+    return BCP_OK;
+}
+
+extern "C" void bcp_chains_destroy(bcp_chains* c) {
+    if (!c) return;
+    DeviceGuard guard(c->h->device);
+    cudaFree(c->d_lam); cudaFree(c->d_group);
+    cudaFree(c->C.state); cudaFree(c->C.isg); cudaFree(c->C.igm); cudaFree(c->C.E);
+    cudaFree(c->C.accepted); cudaFree(c->C.sep); cudaFree(c->C.state_counts); cudaFree(c->C.param_counts);
+    cudaFree(c->d_traj_E); cudaFree(c->d_traj_state); cudaFree(c->d_traj_accept); cudaFree(c->d_traj_idx);
+    cudaFree(c->d_trace);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+}
+
+template <int R>
+static cudaError_t launch_mcmc(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, int grid,
+                               int block, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(mcmc_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.sig_bytes);
+    if (e != cudaSuccess) return e;
+    mcmc_kernel<R><<<grid, block, T.sig_bytes, st>>>(T, C, A);
+    return cudaGetLastError();
+}
+
+// steps per kernel launch: bounds a launch to a few hundred ms and keeps 32-bit per-launch
+// counters far from overflow
+static const long long kMaxStepsPerLaunch = 1ll << 22;
+
+extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void* stream) {
+    BCP_REQUIRE(c && cfg, "bcp_sample_launch: NULL argument");
+    BCP_REQUIRE(cfg->n_steps > 0 && cfg->burn >= 0 && cfg->traj_every >= 0,
+                "bcp_sample_launch: n_steps must be > 0, burn and traj_every >= 0");
+    bcp_handle* h = c->h;
+    DeviceGuard guard(h->device);
+    const SamplerTables& T = h->T;
+    const long long n = c->C.n_chains;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    const long long n_snap = cfg->traj_every > 0 ? (cfg->n_steps + cfg->traj_every - 1) / cfg->traj_every : 0;
+    if ((size_t)n_snap * n > c->cap_snap) {
+        cudaFree(c->d_traj_E); cudaFree(c->d_traj_state); cudaFree(c->d_traj_accept); cudaFree(c->d_traj_idx);
+        c->d_traj_E = nullptr; c->d_traj_state = nullptr; c->d_traj_accept = nullptr; c->d_traj_idx = nullptr;
+        c->cap_snap = 0;
+        BCP_CUDA(dev_alloc(&c->d_traj_E, (size_t)n_snap * n));
+        BCP_CUDA(dev_alloc(&c->d_traj_state, (size_t)n_snap * n));
+        BCP_CUDA(dev_alloc(&c->d_traj_accept, (size_t)n_snap * n));
+        BCP_CUDA(dev_alloc(&c->d_traj_idx, (size_t)n_snap * n * T.P));
+        c->cap_snap = (size_t)n_snap * n;
+    }
+    const long long n_trace = cfg->record_state_trace ? cfg->n_steps : 0;
+    if ((size_t)n_trace * n > c->cap_trace) {
+        cudaFree(c->d_trace); c->d_trace = nullptr; c->cap_trace = 0;
+        BCP_CUDA(dev_alloc(&c->d_trace, (size_t)n_trace * n));
+        c->cap_trace = (size_t)n_trace * n;
+    }
+    c->n_snap = n_snap; c->n_trace = n_trace;
+    // sep_accepted is per sample() call (PosteriorSampler.py:287)
+    BCP_CUDA(cudaMemsetAsync(c->C.sep, 0, (size_t)(T.R + 1) * n * sizeof(unsigned long long), st));
+
+    // grid: spread warps over all SMs first, then grow the CTA
+    const long long n_warps = (n + 31) / 32;
+    const int sms = num_sms(h->device);
+    int wpb = (int)((n_warps + sms - 1) / sms);
+    wpb = wpb < 1 ? 1 : (wpb > 8 ? 8 : wpb);
+    const int block = wpb * 32;
+    const int grid = (int)((n + block - 1) / block);
+
+    LaunchArgs A{};
+    A.step0 = c->steps_done;
+    A.burn = cfg->burn; A.traj_every = cfg->traj_every; A.n_snap = n_snap;
+    A.traj_E = c->d_traj_E; A.traj_state = c->d_traj_state; A.traj_accept = c->d_traj_accept;
+    A.traj_idx = c->d_traj_idx; A.state_trace = n_trace ? c->d_trace : nullptr;
+    const long long total = cfg->n_steps + cfg->burn;
+    BCP_CUDA(cudaEventRecord(c->ev0, st));
+    int launches = 0;
+    for (long long s0 = 0; s0 < total; s0 += kMaxStepsPerLaunch) {
+        A.s_begin = s0;
+        A.s_end = s0 + kMaxStepsPerLaunch < total ? s0 + kMaxStepsPerLaunch : total;
+        cudaError_t e;
+        switch (T.R) {
+            case 1: e = launch_mcmc<1>(T, c->C, A, grid, block, st); break;
+            case 2: e = launch_mcmc<2>(T, c->C, A, grid, block, st); break;
+            case 3: e = launch_mcmc<3>(T, c->C, A, grid, block, st); break;
+            case 4: e = launch_mcmc<4>(T, c->C, A, grid, block, st); break;
+            case 5: e = launch_mcmc<5>(T, c->C, A, grid, block, st); break;
+            case 6: e = launch_mcmc<6>(T, c->C, A, grid, block, st); break;
+            case 7: e = launch_mcmc<7>(T, c->C, A, grid, block, st); break;
+            default: e = launch_mcmc<8>(T, c->C, A, grid, block, st); break;
+        }
+        if (e != cudaSuccess) { set_error("mcmc_kernel launch failed: %s", cudaGetErrorString(e)); return BCP_ERR_CUDA; }
+        ++launches;
+    }
+    BCP_LAUNCHED(launches);
+    BCP_CUDA(cudaEventRecord(c->ev1, st));
+    c->steps_done += (unsigned long long)total;
+    c->last_stream = st;
+    c->last_launches = launches;
+    c->sampled = true;
+    return BCP_OK;
+}
+
+extern "C" int bcp_chains_sync(bcp_chains* c) {
+    BCP_REQUIRE(c, "bcp_chains_sync: NULL argument");
+    DeviceGuard guard(c->h->device);
+    BCP_CUDA(cudaStreamSynchronize(c->last_stream));
+    return BCP_OK;
+}
+
+extern "C" int bcp_chains_last_kernel_ms(bcp_chains* c, float* ms, int32_t* n_launches) {
+    BCP_REQUIRE(c && ms, "bcp_chains_last_kernel_ms: NULL argument");
+    if (!c->sampled) { set_error("bcp_chains_last_kernel_ms: no sample launched yet"); return BCP_ERR_STATE; }
+    DeviceGuard guard(c->h->device);
+    BCP_CUDA(cudaEventSynchronize(c->ev1));
+    BCP_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    if (n_launches) *n_launches = c->last_launches;
+    return BCP_OK;
+}
+
+extern "C" int bcp_chains_device_hist(bcp_chains* c, int64_t** d_state_counts, int64_t** d_param_counts) {
+    BCP_REQUIRE(c, "bcp_chains_device_hist: NULL argument");
+    if (d_state_counts) *d_state_counts = (int64_t*)c->C.state_counts;
+    if (d_param_counts) *d_param_counts = (int64_t*)c->C.param_counts;
+    return BCP_OK;
+}
+
+extern "C" int bcp_chains_fetch(bcp_chains* c, bcp_sample_out* o) {
+    BCP_REQUIRE(c && o, "bcp_chains_fetch: NULL argument");
+    bcp_handle* h = c->h;
+    DeviceGuard guard(h->device);
+    const SamplerTables& T = h->T;
+    const size_t n = (size_t)c->C.n_chains;
+    BCP_CUDA(cudaStreamSynchronize(c->last_stream));
+#define D2H(dst, src, count) do { if (dst) BCP_CUDA(cudaMemcpy(dst, src, (count), cudaMemcpyDeviceToHost)); } while (0)
+    D2H(o->state_counts, c->C.state_counts, (size_t)c->n_groups * T.S * 8);
+    D2H(o->param_counts, c->C.param_counts, (size_t)c->n_groups * T.HB * 8);
+    D2H(o->accepted, c->C.accepted, n * 8);
+    if (o->total) for (size_t i = 0; i < n; ++i) o->total[i] = (int64_t)c->steps_done;
+    D2H(o->state, c->C.state, n * 4);
+    D2H(o->energy, c->C.E, n * 8);
+    if (o->indices || o->sep_accepted) {
+        std::vector<int> isg((size_t)T.R * n), igm((size_t)T.R * n);
+        std::vector<unsigned long long> sep((size_t)(T.R + 1) * n);
+        BCP_CUDA(cudaMemcpy(isg.data(), c->C.isg, isg.size() * 4, cudaMemcpyDeviceToHost));
+        BCP_CUDA(cudaMemcpy(igm.data(), c->C.igm, igm.size() * 4, cudaMemcpyDeviceToHost));
+        BCP_CUDA(cudaMemcpy(sep.data(), c->C.sep, sep.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) {
+            int p = 0;
+            for (int q = 0; q < T.R; ++q) {
+                const bool has_gamma = (p + 1 < T.P) && h->rest_index[p + 1] == q;
+                if (o->indices) o->indices[i * T.P + p] = isg[(size_t)q * n + i];
+                if (o->sep_accepted) o->sep_accepted[i * (T.P + 1) + p] = (int64_t)sep[(size_t)q * n + i];
+                ++p;
+                if (has_gamma) {
+                    if (o->indices) o->indices[i * T.P + p] = igm[(size_t)q * n + i];
+                    if (o->sep_accepted) o->sep_accepted[i * (T.P + 1) + p] = (int64_t)sep[(size_t)q * n + i];
+                    ++p;
+                }
+            }
+            if (o->sep_accepted) o->sep_accepted[i * (T.P + 1) + T.P] = (int64_t)sep[(size_t)T.R * n + i];
+        }
+    }
+    if (c->sampled) {
+        D2H(o->traj_energy, c->d_traj_E, (size_t)c->n_snap * n * 8);
+        D2H(o->traj_state, c->d_traj_state, (size_t)c->n_snap * n * 4);
+        D2H(o->traj_accept, c->d_traj_accept, (size_t)c->n_snap * n);
+        D2H(o->traj_indices, c->d_traj_idx, (size_t)c->n_snap * n * T.P * 4);
+        if (o->state_trace) {
+            if (!c->n_trace) { set_error("bcp_chains_fetch: state_trace requested but not recorded"); return BCP_ERR_STATE; }
+            D2H(o->state_trace, c->d_trace, (size_t)c->n_trace * n * 4);
+        }
+    }
+#undef D2H
+    return BCP_OK;
+}
+
+extern "C" int bcp_sample(bcp_chains* c, const bcp_sample_cfg* cfg, bcp_sample_out* out) {
+    int rc = bcp_sample_launch(c, cfg, nullptr);
+    if (rc != BCP_OK) return rc;
+    if (out) return bcp_chains_fetch(c, out);
+    return bcp_chains_sync(c);
+}
+
+extern "C" int bcp_neglogp(bcp_handle* h, int64_t n, const int32_t* lam, const int32_t* state,
+                           const int32_t* indices, double* energy_out) {
+    BCP_REQUIRE(h && state && indices && energy_out, "bcp_neglogp: NULL argument");
+    if (n <= 0) return BCP_OK;
+    DeviceGuard guard(h->device);
+    const SamplerTables& T = h->T;
+    for (int64_t i = 0; i < n; ++i) {
+        BCP_REQUIRE(state[i] >= 0 && state[i] < T.S, "bcp_neglogp: state[%lld] out of range", (long long)i);
+        BCP_REQUIRE(!lam || (lam[i] >= 0 && lam[i] < T.K), "bcp_neglogp: lam[%lld] out of range", (long long)i);
+        for (int p = 0; p < T.P; ++p)
+            BCP_REQUIRE(indices[i * T.P + p] >= 0 && indices[i * T.P + p] < h->grid_len[p],
+                        "bcp_neglogp: indices[%lld][%d] out of range", (long long)i, p);
+    }
+    int *d_lam = nullptr, *d_state = nullptr, *d_idx = nullptr;
+    double* d_out = nullptr;
+    int rc = BCP_OK;
+    do {
+#define STEP(x) if ((x) != cudaSuccess) { set_error("bcp_neglogp: %s: %s", #x, cudaGetErrorString(cudaGetLastError())); rc = BCP_ERR_CUDA; break; }
+        if (lam) { STEP(dev_alloc(&d_lam, (size_t)n)); STEP(cudaMemcpy(d_lam, lam, n * 4, cudaMemcpyHostToDevice)); }
+        STEP(dev_alloc(&d_state, (size_t)n)); STEP(cudaMemcpy(d_state, state, n * 4, cudaMemcpyHostToDevice));
+        STEP(dev_alloc(&d_idx, (size_t)n * T.P)); STEP(cudaMemcpy(d_idx, indices, (size_t)n * T.P * 4, cudaMemcpyHostToDevice));
+        STEP(dev_alloc(&d_out, (size_t)n));
+        neglogp_kernel<<<(unsigned)((n + 255) / 256), 256>>>(T, n, d_lam, d_state, d_idx, d_out);
+        BCP_LAUNCHED(1);
+        STEP(cudaGetLastError());
+        STEP(cudaMemcpy(energy_out, d_out, n * 8, cudaMemcpyDeviceToHost));
+#undef STEP
+    } while (0);
+    cudaFree(d_lam); cudaFree(d_state); cudaFree(d_idx); cudaFree(d_out);
+    return rc;
+}

@@ -1,0 +1,146 @@
+"""Host-side engine over the C ABI: DeviceTables (an ensemble resident in HBM) and ChainBlock
+(a block of independent Metropolis chains).  This is the layer PosteriorSampler / Analysis
+sit on; it deals only in flat numpy arrays."""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi as A
+
+
+def n_snapshots(n_steps, traj_every):
+    return (n_steps + traj_every - 1) // traj_every if traj_every > 0 else 0
+
+
+def alloc_outputs(n_chains, n_groups, S, P, HB, n_steps, traj_every, record_state_trace):
+    """numpy buffers + the bcp_sample_out struct pointing at them."""
+    ns = n_snapshots(n_steps, traj_every)
+    o = dict(state_counts=np.zeros((n_groups, S), np.int64), param_counts=np.zeros((n_groups, HB), np.int64),
+             accepted=np.zeros(n_chains, np.int64), total=np.zeros(n_chains, np.int64),
+             sep_accepted=np.zeros((n_chains, P + 1), np.int64),
+             state=np.zeros(n_chains, np.int32), indices=np.zeros((n_chains, P), np.int32),
+             energy=np.zeros(n_chains, np.float64),
+             traj_energy=np.zeros((ns, n_chains), np.float64), traj_state=np.zeros((ns, n_chains), np.int32),
+             traj_accept=np.zeros((ns, n_chains), np.uint8), traj_indices=np.zeros((ns, P, n_chains), np.int32),
+             state_trace=np.zeros((n_steps if record_state_trace else 0, n_chains), np.int32))
+    s = A.bcp_sample_out(A.i64ptr(o["state_counts"]), A.i64ptr(o["param_counts"]), A.i64ptr(o["accepted"]),
+                         A.i64ptr(o["total"]), A.i64ptr(o["sep_accepted"]), A.i32ptr(o["state"]),
+                         A.i32ptr(o["indices"]), A.dptr(o["energy"]),
+                         A.dptr(o["traj_energy"]) if ns else None, A.i32ptr(o["traj_state"]) if ns else None,
+                         A.u8ptr(o["traj_accept"]) if ns else None, A.i32ptr(o["traj_indices"]) if ns else None,
+                         A.i32ptr(o["state_trace"]) if record_state_trace else None)
+    return o, s
+
+
+def chain_cfg(n_chains, seed, chain_id0=0, chain_lambda=None, chain_group=None, n_groups=0, init_state=None):
+    keep = [None if a is None else A.i32(a) for a in (chain_lambda, chain_group, init_state)]
+    for a in keep:
+        if a is not None and a.shape != (n_chains,):
+            raise ValueError("per-chain arrays must have shape (n_chains,)")
+    cfg = A.bcp_chain_cfg(int(n_chains), int(seed) & (2 ** 64 - 1), int(chain_id0), int(n_groups), 0,
+                          A.i32ptr(keep[0]), A.i32ptr(keep[1]), A.i32ptr(keep[2]))
+    return cfg, keep
+
+
+class DeviceTables(object):
+    """bcp_handle: the flattened ensemble (all lambdas) resident on one GPU."""
+
+    def __init__(self, tables, device=0):
+        self._lib = A.lib()
+        self.packed = tables if isinstance(tables, A.PackedTables) else A.PackedTables(tables)
+        h = C.c_void_p()
+        A.check(self._lib.bcp_create(C.byref(self.packed.struct), int(device), C.byref(h)), "bcp_create")
+        self._h = h
+        self.device = int(device)
+        self.n_states, self.n_lambda = self.packed.n_states, self.packed.n_lambda
+        self.n_params = self._lib.bcp_n_params(h)
+        self.param_bins = self._lib.bcp_param_bins(h)
+        ri = np.zeros(self.n_params, np.int32); gl = np.zeros(self.n_params, np.int32)
+        A.check(self._lib.bcp_param_layout(h, A.i32ptr(ri), A.i32ptr(gl)), "bcp_param_layout")
+        self.rest_index, self.grid_len = ri, gl
+        self.hist_offsets = np.concatenate([[0], np.cumsum(gl)[:-1]]).astype(np.int64)
+
+    def neglogp(self, state, indices, lam=None):
+        state = A.i32(np.atleast_1d(state))
+        n = state.shape[0]
+        indices = A.i32(np.asarray(indices).reshape(n, self.n_params))
+        lam_a = None if lam is None else A.i32(np.broadcast_to(np.asarray(lam), (n,)))
+        out = np.zeros(n, np.float64)
+        A.check(self._lib.bcp_neglogp(self._h, n, A.i32ptr(lam_a), A.i32ptr(state), A.i32ptr(indices),
+                                      A.dptr(out)), "bcp_neglogp")
+        return out
+
+    def chains(self, n_chains, seed, **kw):
+        return ChainBlock(self, n_chains, seed, **kw)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bcp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ChainBlock(object):
+    """bcp_chains: n independent chains on one DeviceTables."""
+
+    def __init__(self, tables, n_chains, seed, chain_id0=0, chain_lambda=None, chain_group=None,
+                 n_groups=0, init_state=None):
+        self._lib = A.lib()
+        self.tables = tables
+        self.n_chains = int(n_chains)
+        self.n_groups = int(n_groups) if n_groups else tables.n_lambda
+        cfg, keep = chain_cfg(n_chains, seed, chain_id0, chain_lambda, chain_group, n_groups, init_state)
+        c = C.c_void_p()
+        A.check(self._lib.bcp_chains_create(tables._h, C.byref(cfg), C.byref(c)), "bcp_chains_create")
+        self._c = c
+
+    def sample(self, n_steps, burn=0, traj_every=0, record_state_trace=False):
+        """Synchronous bcp_sample with host output buffers; returns a dict of numpy arrays."""
+        T = self.tables
+        o, s = alloc_outputs(self.n_chains, self.n_groups, T.n_states, T.n_params, T.param_bins, int(n_steps),
+                             int(traj_every), bool(record_state_trace))
+        cfg = A.bcp_sample_cfg(int(n_steps), int(burn), int(traj_every), int(bool(record_state_trace)), 0)
+        A.check(self._lib.bcp_sample(self._c, C.byref(cfg), C.byref(s)), "bcp_sample")
+        return o
+
+    def launch(self, n_steps, burn=0, traj_every=0, record_state_trace=False, stream=None):
+        cfg = A.bcp_sample_cfg(int(n_steps), int(burn), int(traj_every), int(bool(record_state_trace)), 0)
+        self._last = (int(n_steps), int(traj_every), bool(record_state_trace))
+        A.check(self._lib.bcp_sample_launch(self._c, C.byref(cfg), C.c_void_p(stream or 0)), "bcp_sample_launch")
+
+    def sync(self):
+        A.check(self._lib.bcp_chains_sync(self._c), "bcp_chains_sync")
+
+    def fetch(self):
+        T = self.tables
+        n_steps, traj_every, rec = getattr(self, "_last", (0, 0, False))
+        o, s = alloc_outputs(self.n_chains, self.n_groups, T.n_states, T.n_params, T.param_bins, n_steps,
+                             traj_every, rec)
+        A.check(self._lib.bcp_chains_fetch(self._c, C.byref(s)), "bcp_chains_fetch")
+        return o
+
+    def last_kernel_ms(self):
+        ms = C.c_float(); nl = C.c_int32()
+        A.check(self._lib.bcp_chains_last_kernel_ms(self._c, C.byref(ms), C.byref(nl)), "bcp_chains_last_kernel_ms")
+        return float(ms.value), int(nl.value)
+
+    def device_hist_ptrs(self):
+        a = A.c_int64_p(); b = A.c_int64_p()
+        A.check(self._lib.bcp_chains_device_hist(self._c, C.byref(a), C.byref(b)), "bcp_chains_device_hist")
+        return C.cast(a, C.c_void_p).value, C.cast(b, C.c_void_p).value
+
+    def close(self):
+        if getattr(self, "_c", None):
+            self._lib.bcp_chains_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

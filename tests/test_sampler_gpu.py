@@ -1,0 +1,128 @@
+"""GPU: the CUDA Metropolis kernel (through the C ABI) against the C oracle on identical tables
+and the same Philox streams -- every output must agree bit for bit."""
+import numpy as np
+import pytest
+
+from helpers import cineromycin_tables, stack_lambdas, assert_outputs_equal, load_npz, tables_from_npz
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cin():
+    z, t0, t1 = cineromycin_tables()
+    return stack_lambdas([t0, t1])
+
+
+def run_both(tabs, n_chains, seed, n_steps, **kw):
+    from biceps_b200 import engine
+    from oracle import cbind
+    T = engine.DeviceTables(tabs, device=0)
+    ck = {k: kw[k] for k in ("chain_id0", "chain_lambda", "chain_group", "n_groups", "init_state") if k in kw}
+    sk = {k: kw[k] for k in ("burn", "traj_every", "record_state_trace") if k in kw}
+    got = T.chains(n_chains, seed, **ck).sample(n_steps, **sk)
+    want = cbind.sample(tabs, n_chains, seed, n_steps, n_threads=8, **ck, **sk)
+    return got, want
+
+
+def test_cineromycin_two_lambdas_bit_exact(cin):
+    n = 96
+    lam = (np.arange(n) % 2).astype(np.int32)
+    got, want = run_both(cin, n, 12345, 5000, burn=123, traj_every=100, record_state_trace=True, chain_lambda=lam)
+    assert_outputs_equal(got, want)
+    assert got["accepted"].min() > 0 and got["state_counts"].sum() == n * 5000
+
+
+def test_single_chain_per_group_like_the_reference(cin):
+    """One chain per histogram group == one reference sampler per chain."""
+    n = 7
+    got, want = run_both(cin, n, 1, 3000, traj_every=1, record_state_trace=True,
+                         chain_lambda=np.ones(n, np.int32), chain_group=np.arange(n, dtype=np.int32), n_groups=n,
+                         chain_id0=1000)
+    assert_outputs_equal(got, want)
+    assert np.array_equal(got["state_counts"].sum(axis=1), np.full(n, 3000))
+
+
+def test_given_initial_states_and_ragged_chain_count(cin):
+    n = 33                                     # not a multiple of the warp size
+    init = (np.arange(n) * 3 % 100).astype(np.int32)
+    got, want = run_both(cin, n, 77, 1000, burn=0, traj_every=7, init_state=init)
+    assert_outputs_equal(got, want)
+
+
+def test_no_snapshots_no_trace(cin):
+    got, want = run_both(cin, 64, 5, 2000)
+    assert_outputs_equal(got, want)
+    assert got["traj_energy"].shape[0] == 0
+
+
+def test_repeated_sample_calls_continue_the_chain(cin):
+    from biceps_b200 import engine
+    from oracle import cbind
+    T = engine.DeviceTables(cin, device=0)
+    blk = T.chains(40, 9)
+    a = blk.sample(700, traj_every=10)
+    b = blk.sample(1300, burn=50, traj_every=10)
+    wa = cbind.sample(cin, 40, 9, 700, traj_every=10)
+    wb = cbind.sample(cin, 40, 9, 1300, burn=50, traj_every=10, step0=700, resume=wa)
+    assert_outputs_equal(a, wa)
+    assert_outputs_equal(b, wb)
+    one = cbind.sample(cin, 40, 9, 2050)
+    assert np.array_equal(b["state"], one["state"]) and np.array_equal(b["energy"], one["energy"])
+
+
+def test_three_scalar_restraints_with_reference_potentials():
+    g = load_npz("apomyoglobin_tables.npz")
+    tabs = tables_from_npz(g, "t_")
+    got, want = run_both(tabs, 50, 31, 4000, traj_every=20, record_state_trace=True)
+    assert_outputs_equal(got, want)
+
+
+def test_neglogp_matches_oracle(cin):
+    from biceps_b200 import engine
+    from oracle import sampler_oracle as O
+    z, t0, t1 = cineromycin_tables()
+    T = engine.DeviceTables(cin, device=0)
+    rng = np.random.default_rng(0)
+    n = 500
+    st = rng.integers(0, 100, n)
+    lam = rng.integers(0, 2, n)
+    idx = np.stack([rng.integers(0, g, n) for g in T.grid_len], axis=1)
+    e = T.neglogp(st, idx, lam)
+    want = np.array([O.neglogP(t1 if lam[i] else t0, int(st[i]), [int(x) for x in idx[i]]) for i in range(n)])
+    assert np.array_equal(e, want)
+
+
+def test_synthetic_c2_five_restraints_eight_lambdas():
+    from biceps_b200 import synthetic
+    from oracle import precompute_oracle as PO
+    ens = synthetic.make_ensemble("C2", seed=1, n_states=300)
+    tabs = PO.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], exact_pow=False)
+    n = 8 * 24
+    lam = (np.arange(n) % 8).astype(np.int32)
+    got, want = run_both(tabs, n, 2, 3000, burn=10, traj_every=50, chain_lambda=lam)
+    assert_outputs_equal(got, want)
+
+
+def test_statistical_agreement_of_independent_streams(cin):
+    """Posterior populations from two independent seeds agree (KL < 1e-3, north_star tolerance)."""
+    from biceps_b200 import engine
+    T = engine.DeviceTables(cin, device=0)
+    pops = []
+    for seed in (101, 202):
+        o = T.chains(4096, seed, chain_lambda=np.ones(4096, np.int32)).sample(20000, burn=2000)
+        c = o["state_counts"][1].astype(np.float64) + 1.0
+        pops.append(c / c.sum())
+    kl = float(np.sum(pops[0] * np.log(pops[0] / pops[1])))
+    assert kl < 1e-3
+
+
+def test_errors_are_reported_not_crashed(cin):
+    from biceps_b200 import engine
+    T = engine.DeviceTables(cin, device=0)
+    with pytest.raises(RuntimeError):
+        T.chains(4, 0, chain_lambda=np.array([0, 1, 2, 0], np.int32))     # lambda index out of range
+    with pytest.raises(RuntimeError):
+        T.chains(4, 0).sample(0)
+    with pytest.raises(RuntimeError):
+        T.neglogp([100], [[0, 0, 0]])                                     # state out of range
