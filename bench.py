@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- chain-steps/sec of the BICePs posterior-sampling hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], "C3"): synthetic ensemble of 10 000 states x 1 000 observables
+(cs_H 200 + cs_Ca 100 + J 300 + NOE 400, reference restraint order), 8 lambda values, 4096 chains
+per GPU (512 per lambda).  One bench "step" = one PosteriorSampler.sample(n_mcmc) pass of every
+chain of the block = n_chains * n_mcmc chain-steps.  Weak scaling: every GPU runs its own 4096
+chains (distinct global chain ids) on a replica of the tables; the only exchange is the NCCL
+all-reduce of the per-lambda state / parameter histograms after each pass.
+
+Prints ONE JSON line (rank 0).  `value` = chain-steps/s with the tables resident in HBM
+(CUDA events around the launches); `e2e` = the same through the host-buffer C ABI
+(bcp_create -> bcp_chains_create -> bcp_sample -> destroy) with the table upload and the result
+download inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_LAMBDA = 8
+CHAINS_PER_GPU = 4096
+N_MCMC = 20000              # MCMC steps per chain per bench step (ours)
+N_MCMC_E2E = 20000
+SEED = 20251019
+
+
+def workload_dict(n_gpus, n_mcmc):
+    return {"workload": "C3 synthetic: 10000 states x 1000 observables (cs_H 200, cs_Ca 100, J 300, NOE 400), "
+                        "R=4 restraints, P=5 nuisance parameters, 8 lambdas",
+            "n_states": 10000, "n_observables": 1000, "n_lambda": N_LAMBDA,
+            "chains_per_gpu": CHAINS_PER_GPU, "chains_total": CHAINS_PER_GPU * n_gpus,
+            "mcmc_steps_per_chain_per_bench_step": n_mcmc,
+            "chain_steps_per_bench_step": CHAINS_PER_GPU * n_gpus * n_mcmc,
+            "parallelism": "chains sharded over %d GPU(s), tables replicated" % n_gpus,
+            "l2": "tables (14 MB) are L2-resident by construction; a 256 MiB memset flushes L2 between timed steps"}
+
+
+def bytes_per_chain_step(tables):
+    """table words touched per step, averaged over the move types."""
+    R = len(tables["restraints"])
+    g = sum(1 for rt in tables["restraints"] if rt["kind"] == "gamma")
+    return 8.0 * ((1 + R) + (2 * R + g)) / (R + 1)
+
+
+def start_clock_sampler(gpu_index):
+    f = tempfile.NamedTemporaryFile(prefix="bcp_clocks_", suffix=".csv", delete=False)
+    f.close()
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                              "-lms", "100"], stdout=open(f.name, "w"), stderr=subprocess.DEVNULL)
+    except OSError:
+        return None, f.name
+    return p, f.name
+
+
+def stop_clock_sampler(p, path):
+    if p is not None:
+        p.terminate()
+        try:
+            p.wait(timeout=5)
+        except Exception:
+            p.kill()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    try:
+        for line in open(path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(path)
+    except OSError:
+        pass
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def table_bytes(tables):
+    n = tables["energy"].nbytes + np.asarray(tables["logZ"]).nbytes
+    for rt in tables["restraints"]:
+        n += rt["sse"].nbytes + rt["nlsig"].nbytes + rt["two_sig2"].nbytes
+        if rt.get("refsum") is not None:
+            n += rt["refsum"].nbytes
+    return n
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's CPU algorithm for the path, timed on the host cores.  The reference is pure
+    Python (no compiled sources to build into oracle/_ref), so this arm runs the plain-C oracle port
+    (oracle/biceps_oracle.c) on all host threads; tables come from the numpy oracle -- none of the
+    product's kernels are on this path."""
+    if rank != 0:
+        return
+    from biceps_b200 import synthetic
+    from oracle import cbind, precompute_oracle as PO, sampler_oracle as O, philox as PX
+    cbind.build()
+    ens = synthetic.make_ensemble("C3", seed=0, n_lambda=N_LAMBDA)
+    tabs = PO.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], exact_pow=False)
+    cores = os.cpu_count() or 1
+    n_chains = CHAINS_PER_GPU * args.gpus
+    lam = (np.arange(n_chains) % N_LAMBDA).astype(np.int32)
+    # size a step to ~3 s of CPU work from a short calibration
+    t0 = time.perf_counter()
+    cbind.sample(tabs, n_chains, SEED, 50, chain_lambda=lam, n_threads=cores)
+    rate = n_chains * 50 / (time.perf_counter() - t0)
+    n_mcmc = max(50, int(3.0 * rate / n_chains))
+    for _ in range(args.warmup):
+        cbind.sample(tabs, n_chains, SEED, max(10, n_mcmc // 10), chain_lambda=lam, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cbind.sample(tabs, n_chains, SEED, n_mcmc, chain_lambda=lam, n_threads=cores)
+    dt = time.perf_counter() - t0
+    value = n_chains * n_mcmc * args.steps / dt
+    # the Python restatement (interpreter-bound like the reference itself), one chain, for orientation
+    one = dict(tabs); one["energy"] = tabs["energy"][-1]; one["logZ"] = float(tabs["logZ"][-1])
+    t1 = time.perf_counter()
+    O.run_chain(one, PX.PhiloxStepRNG(SEED, 0), 5000, accept_fn=O.accept_bcp, record_state_trace=False)
+    py_rate = 5000 / (time.perf_counter() - t1)
+    sample = ("C oracle port of PosteriorSampler.sample, %d chains x %d steps per bench step, %d pthreads; "
+              "python restatement (reference-like interpreter loop) %.3g steps/s on 1 core" % (n_chains, n_mcmc, cores, py_rate))
+    cfg = workload_dict(args.gpus, n_mcmc)
+    line = {"impl": "reference", "metric": "MCMC chain-steps/sec", "value": value, "unit": "chain-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+class _DevArray(object):
+    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from biceps_b200 import _cabi, engine, precompute, synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    lib = _cabi.lib()
+
+    # inputs -> tables through the product's own precompute kernels (K1/K2/K4)
+    ens = synthetic.make_ensemble("C3", seed=0, n_lambda=N_LAMBDA)
+    tabs = precompute.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], device=dev)
+    packed = _cabi.PackedTables(tabs)
+    T = engine.DeviceTables(packed, device=dev)
+    n = CHAINS_PER_GPU
+    lam = (np.arange(n) % N_LAMBDA).astype(np.int32)
+    blk = T.chains(n, SEED, chain_id0=rank * n, chain_lambda=lam)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    hist_views = None
+    if world > 1:
+        p_sc, p_pc = blk.device_hist_ptrs()
+        sc = torch.as_tensor(_DevArray(p_sc, (N_LAMBDA, T.n_states), "<i8"), device="cuda")
+        pc = torch.as_tensor(_DevArray(p_pc, (N_LAMBDA, T.param_bins), "<i8"), device="cuda")
+        hist_views = (sc, pc)
+        red = (torch.empty_like(sc), torch.empty_like(pc))
+
+    def one_step():
+        blk.launch(N_MCMC, stream=stream)
+        if hist_views is not None:             # per-lambda histograms summed over all GPUs' chains
+            for src, dst in zip(hist_views, red):
+                dst.copy_(src)
+                dist.all_reduce(dst, op=dist.ReduceOp.SUM)
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk_p, clk_f = start_clock_sampler(local_rank)
+    launches0 = lib.bcp_kernel_launches()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    torch.cuda.synchronize()
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        one_step()
+        b.record()
+        b.synchronize()
+        kern_ms.append(blk.last_kernel_ms()[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = int(lib.bcp_kernel_launches() - launches0)
+    clocks = stop_clock_sampler(clk_p, clk_f)
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * n * N_MCMC / (ms_per_step * 1e-3)
+
+    # ---- e2e through the host-buffer C ABI: upload tables, sample, download results, every step ----
+    def e2e_step(n_mcmc):
+        T2 = engine.DeviceTables(packed, device=dev)
+        b2 = T2.chains(n, SEED + 1, chain_id0=rank * n, chain_lambda=lam)
+        o = b2.sample(n_mcmc, burn=0, traj_every=100)
+        b2.close(); T2.close()
+        return o
+    o = e2e_step(2000)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o = e2e_step(N_MCMC_E2E)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * n * N_MCMC_E2E * args.steps / e2e_s
+    h2d = table_bytes(tabs) + 2 * lam.nbytes
+    d2h = sum(int(v.nbytes) for v in o.values())
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (mcmc_kernel) ----
+    bps = bytes_per_chain_step(tabs)
+    k_ms = float(np.mean(kern_ms))
+    peak, peak_src = measured_peak_hbm()
+    achieved = bps * n * N_MCMC / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "mcmc_kernel_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "bcp::mcmc_kernel", "kernel_ms_per_launch": k_ms,
+                "algorithmic_bytes_per_chain_step": bps, "peak_source": peak_src,
+                "note": "latency/issue-bound by construction (SURVEY 8d): the useful table words are L2-resident "
+                        "gathers; the HBM fraction is reported as required, the meaningful ceiling is instruction issue"}
+
+    # ---- CPU baseline beside it: the C oracle port on the host cores, bounded sample ----
+    from oracle import cbind
+    cbind.build()
+    cores = os.cpu_count() or 1
+    nb = 25000 // 10
+    t0 = time.perf_counter()
+    cbind.sample(tabs, n, SEED, 200, chain_lambda=lam, n_threads=cores)
+    rate = n * 200 / (time.perf_counter() - t0)
+    nb = max(200, int(12.0 * rate / n))
+    t0 = time.perf_counter()
+    cbind.sample(tabs, n, SEED, nb, chain_lambda=lam, n_threads=cores)
+    cpu_value = n * nb / (time.perf_counter() - t0)
+    cpu = {"value": cpu_value, "unit": "chain-steps/s", "cores": cores, "kind": "port",
+           "sample": "oracle/biceps_oracle.c (C port of PosteriorSampler.sample, Philox RNG), same C3 tables, "
+                     "%d chains x %d steps, %d pthreads" % (n, nb, cores)}
+
+    line = {"metric": "MCMC chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_dict(world, N_MCMC), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "mcmc_steps_per_chain": N_MCMC_E2E, "traj_every": 100},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

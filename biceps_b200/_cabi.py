@@ -58,6 +58,12 @@ class bcp_sample_out(C.Structure):
                 ("state_trace", c_int32_p)]
 
 
+class bcp_obs(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_obs", C.c_int32), ("ref_kind", C.c_int32),
+                ("log_normal", C.c_int32), ("use_global_ref_sigma", C.c_int32), ("n_gamma", C.c_int32),
+                ("model", c_double_p), ("exp", c_double_p), ("weight", c_double_p), ("gamma", c_double_p)]
+
+
 def _ptr(a, ctype):
     if a is None:
         return C.cast(None, C.POINTER(ctype))
@@ -168,6 +174,19 @@ _SIGS = {
     "bcp_chains_device_hist": (C.c_int, [C.c_void_p, C.POINTER(c_int64_p), C.POINTER(c_int64_p)]),
     "bcp_chains_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), c_int32_p]),
     "bcp_neglogp": (C.c_int, [C.c_void_p, C.c_int64, c_int32_p, c_int32_p, c_int32_p, c_double_p]),
+    "bcp_precompute": (C.c_int, [C.POINTER(bcp_obs), C.c_int32, C.c_int, c_double_p, c_double_p, c_double_p,
+                                 c_double_p]),
+    "bcp_precompute_dev": (C.c_int, [C.POINTER(bcp_obs), C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "bcp_logz": (C.c_int, [c_double_p, C.c_int32, C.c_int32, C.c_int, c_double_p]),
+    "bcp_ukn": (C.c_int, [C.c_void_p, C.c_int64, c_int32_p, c_int32_p, c_double_p]),
+    "bcp_ukn_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bcp_mbar": (C.c_int, [c_double_p, c_int64_p, C.c_int32, C.c_int64, c_int32_p, C.c_int32, C.c_int, C.c_double,
+                           C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
+    "bcp_mbar_dev": (C.c_int, [C.c_void_p, c_int64_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int, C.c_void_p,
+                               C.c_double, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
+    "bcp_mbar_pass_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, c_int64_p, c_double_p, C.c_int32, C.c_int,
+                                    C.c_void_p, c_double_p, c_double_p]),
 }
 
 _lib = None

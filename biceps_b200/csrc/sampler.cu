@@ -18,34 +18,11 @@
 #include "common.cuh"
 #include "exp_det.cuh"
 #include "philox.cuh"
+#include "tables.cuh"
 
 #include <vector>
 
 namespace bcp {
-
-constexpr int MAXR = BCP_MAX_RESTRAINTS;
-
-struct RestraintDev {
-    const double* sse;      // [S][G]
-    const double* refsum;   // [S] or nullptr
-    double cnorm;
-    int sig_off;            // doubles into the staged sigma table: nlsig, then two_sig2
-    int n_sigma;
-    int n_gamma;            // 1 if the restraint has no gamma
-    int hist_sigma;         // bin offset of this restraint's sigma histogram
-    int hist_gamma;         // bin offset of its gamma histogram (if has_gamma)
-    int has_gamma;          // Restraint_noe: gamma moves together with sigma
-};
-
-struct SamplerTables {
-    RestraintDev r[MAXR];
-    const double* energy;   // [K][S]
-    const double* logZ;     // [K]
-    const double* sig_tab;  // staged table in global memory (16 B aligned, padded)
-    int sig_bytes;          // multiple of 16
-    int R, S, K, P, HB;
-    uint32_t nuis_thresh;   // floor(R * 2^32 / (R+1))
-};
 
 struct ChainBuffers {
     long long n_chains;
@@ -470,6 +447,11 @@ extern "C" void bcp_destroy(bcp_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     delete h;
 }
+
+namespace bcp {
+const SamplerTables& handle_tables(const bcp_handle* h) { return h->T; }
+int handle_device(const bcp_handle* h) { return h->device; }
+}  // namespace bcp
 
 extern "C" int bcp_n_params(const bcp_handle* h) { return h ? h->T.P : BCP_ERR_INVALID; }
 extern "C" int bcp_param_bins(const bcp_handle* h) { return h ? h->T.HB : BCP_ERR_INVALID; }

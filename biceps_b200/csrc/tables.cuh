@@ -1,0 +1,37 @@
+// Device-side view of a flattened ensemble (bcp_handle), shared by the sampler and the
+// analysis kernels.
+#pragma once
+#include "common.cuh"
+
+struct bcp_handle;
+
+namespace bcp {
+
+constexpr int MAXR = BCP_MAX_RESTRAINTS;
+
+struct RestraintDev {
+    const double* sse;      // [S][G]
+    const double* refsum;   // [S] or nullptr
+    double cnorm;
+    int sig_off;            // doubles into the staged sigma table: nlsig, then two_sig2
+    int n_sigma;
+    int n_gamma;            // 1 if the restraint has no gamma
+    int hist_sigma;         // bin offset of this restraint's sigma histogram
+    int hist_gamma;         // bin offset of its gamma histogram (if has_gamma)
+    int has_gamma;          // Restraint_noe: gamma moves together with sigma
+};
+
+struct SamplerTables {
+    RestraintDev r[MAXR];
+    const double* energy;   // [K][S]
+    const double* logZ;     // [K]
+    const double* sig_tab;  // staged table in global memory (16 B aligned, padded)
+    int sig_bytes;          // multiple of 16
+    int R, S, K, P, HB;
+    uint32_t nuis_thresh;   // floor(R * 2^32 / (R+1))
+};
+
+const SamplerTables& handle_tables(const bcp_handle* h);
+int handle_device(const bcp_handle* h);
+
+}  // namespace bcp

@@ -39,14 +39,15 @@ def _restraint(rng, S, J, flavour):
 def make_ensemble(config="C3", seed=0, n_states=None, n_lambda=None):
     """Raw observables of a named configuration.
 
-    C3: S=10k, R=4: 400 NOE + 300 J + 200 cs_H + 100 cs_Ca = 1000 observables (BASELINE configs[2])
+    C3: S=10k, R=4 in the reference's file-extension order: cs_H 200, cs_Ca 100, J 300, NOE 400
+        = 1000 observables (BASELINE configs[2])
     C2: S=1k,  R=5 in the reference's fixed order cs_H, cs_Ca, cs_N, J, noe      (BASELINE configs[1])
     C1s: a cineromycin-B-shaped synthetic stand-in, S=100, J 10 + NOE 33          (BASELINE configs[0])
     """
     rng = np.random.default_rng(seed)
     if config == "C3":
         S, K = n_states or 10000, n_lambda or 1
-        layout = [("noe", 400), ("J", 300), ("cs_H", 200), ("cs_Ca", 100)]
+        layout = [("cs_H", 200), ("cs_Ca", 100), ("J", 300), ("noe", 400)]
     elif config == "C2":
         S, K = n_states or 1000, n_lambda or 8
         layout = [("cs_H", 60), ("cs_Ca", 60), ("cs_N", 60), ("J", 40), ("noe", 120)]

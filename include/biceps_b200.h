@@ -168,6 +168,65 @@ int bcp_chains_last_kernel_ms(bcp_chains* c, float* ms, int32_t* n_launches);
 int bcp_neglogp(bcp_handle* h, int64_t n, const int32_t* lam, const int32_t* state,
                 const int32_t* indices, double* energy_out);
 
+/* ---------------------------------------------------------------------------------------
+ * Restraint-energy precompute.
+ * Raw observables of ONE restraint type over all states.                                 */
+typedef struct bcp_obs {
+    int32_t kind;                   /* BCP_KIND_SCALAR or BCP_KIND_GAMMA */
+    int32_t n_obs;                  /* J */
+    int32_t ref_kind;               /* 0 uniform, 1 exponential, 2 gaussian */
+    int32_t log_normal;             /* GAMMA: err = ln(model/(gamma*exp))      Restraint.py:561-562 */
+    int32_t use_global_ref_sigma;   /* gaussian ref: one sigma for all j       PosteriorSampler.py:139-143 */
+    int32_t n_gamma;                /* GAMMA: G */
+    const double* model;            /* [S][J] forward-model observables r_j(X_i) */
+    const double* exp;              /* [J] experimental values */
+    const double* weight;           /* [J] 1/n per equivalency group           Restraint.py:435-442 */
+    const double* gamma;            /* [G] */
+} bcp_obs;
+
+/* sse[S] (SCALAR: Restraint.py:344-353, 445-454, 736-741) or sse[S][G] (GAMMA: :552-569), and,
+ * if ref_kind != 0, refsum[S] = sum_j w_j * (-ln P_ref) with its per-observable parameters:
+ *   exponential: ref_par0 = beta_j            PosteriorSampler.py:74-104, Restraint.py:275-286
+ *   gaussian   : ref_par0 = mean_j, ref_par1 = sigma_j   PosteriorSampler.py:107-150, Restraint.py:288-298
+ * Host pointers in, host pointers out (copies included).  Results agree with the reference to
+ * ~1e-13 relative (reduction order and the gamma moment expansion differ), tolerance 1e-6.  */
+int bcp_precompute(const bcp_obs* obs, int32_t n_states, int device, double* sse, double* refsum,
+                   double* ref_par0, double* ref_par1);
+/* same with every pointer (inside obs too) a device pointer; asynchronous kernels on `stream`,
+ * returns after the stream has drained */
+int bcp_precompute_dev(const bcp_obs* obs, int32_t n_states, int device, void* stream, double* d_sse,
+                       double* d_refsum, double* d_ref_par0, double* d_ref_par1);
+/* logZ[k] = ln sum_i exp(-energy[k][i])   (PosteriorSampler.py:64-71); host pointers */
+int bcp_logz(const double* energy, int32_t n_lambda, int32_t n_states, int device, double* logZ);
+
+/* ---------------------------------------------------------------------------------------
+ * Analysis: rescoring and MBAR.
+ * u_kn[l][n] = -log P of snapshot n (state, indices) under lambda ensemble l of the handle,
+ * i.e. sampler[l].neglogP(...) of Analysis.py:165-183 for every l; layout [K][n].            */
+int bcp_ukn(bcp_handle* h, int64_t n, const int32_t* state, const int32_t* indices, double* u_kn);
+int bcp_ukn_dev(bcp_handle* h, int64_t n, const int32_t* d_state, const int32_t* d_indices, double* d_u_kn,
+                void* stream);
+
+/* MBAR(u_kn, N_k) + compute_free_energy_differences + compute_expectations of state indicators
+ * (pymbar calls at Analysis.py:192, 201, 217-223; uncertainty_method='approximate').
+ *   u_kn  [K][N]  reduced potentials, samples of run 0 first, then run 1, ... (kln_to_kn order)
+ *   N_k   [K]     samples per run (sum = N)
+ *   state_n [N]   conformational state of each sample (or NULL: no populations), S states
+ * Outputs: f_k [K] (f_0 = 0; BICePs score of lambda_l is f_l - f_0), theta [K][K] = W^T W
+ * (dDelta_f_ij = sqrt(theta_ii + theta_jj - 2 theta_ij)), pops / dpops [S][K], iteration count.
+ * tol <= 0 -> 1e-12 (max |delta f| relative to max(1, |f|)); max_iter <= 0 -> 10000.          */
+int bcp_mbar(const double* u_kn, const int64_t* N_k, int32_t K, int64_t N, const int32_t* state_n, int32_t S,
+             int device, double tol, int32_t max_iter, double* f_k, double* theta, double* pops, double* dpops,
+             int32_t* iters);
+/* same with u_kn / state_n resident in HBM (N_k and the outputs stay host pointers) */
+int bcp_mbar_dev(const double* d_u_kn, const int64_t* N_k, int32_t K, int64_t N, const int32_t* d_state_n, int32_t S,
+                 int device, void* stream, double tol, int32_t max_iter, double* f_k, double* theta, double* pops,
+                 double* dpops, int32_t* iters);
+/* One streaming reduction over a local shard of samples (multi-GPU MBAR: the caller all-reduces
+ * s and M across ranks between passes): s[K] = sum_n W_nk, M[K][K] = sum_n W_nk W_nl.        */
+int bcp_mbar_pass_dev(const double* d_u_kn, int64_t n_local, int32_t K, const int64_t* N_k_global,
+                      const double* f_k, int32_t want_hess, int device, void* stream, double* s_out, double* M_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,9 @@ Fixtures (all small .npz, committed):
                            np.random.seed(seed) for (lambda, seed) in [(1.0, 0), (0.0, 7)]:
                            snapshots (step, E, accept, state, indices), state_trace, state_counts,
                            sampled_parameters, accepted, sep_accept
+  tutorial_mbar.npz        the reference's stored tutorial results (2 lambdas x 1000 snapshots, tables
+                           from its pickled samplers, BS.dat and populations.dat written by its own
+                           Analysis with the real pymbar) -- the golden for u_kn + MBAR
   apomyoglobin_tables.npz  13 states, cs_H / cs_Ca / cs_N (gaussian / exponential / uniform refs)
                            and their MT-seeded reference trajectory (exercises Restraint_cs and
                            both reference potentials on three restraints)
@@ -126,10 +129,31 @@ def make_apomyoglobin(biceps):
     np.savez_compressed(os.path.join(HERE, "apomyoglobin_tables.npz"), **out)
 
 
+def make_tutorial_mbar(biceps):
+    """The one self-consistent stored result set of the reference:
+    docs/examples/Tutorials/Prep_Rest_Post_Ana/results -- trajectories + pickled samplers for
+    lambda = 0 and 1, and the BS.dat / populations.dat its own Analysis (with real pymbar) wrote."""
+    import pickle
+    D = os.path.join(H.REFERENCE_ROOT, "docs/examples/Tutorials/Prep_Rest_Post_Ana/results/")
+    out = {"BS": np.loadtxt(D + "BS.dat"), "populations": np.loadtxt(D + "populations.dat")}
+    for k, lam in enumerate(["0.00", "1.00"]):
+        traj = np.load(D + "traj_lambda%s.npz" % lam, allow_pickle=True)["arr_0"].item()
+        with open(D + "traj_lambda%s.pkl" % lam, "rb") as f:
+            sampler = pickle.load(f)
+        pack_tables("k%d_" % k, H.extract_tables(sampler), out)
+        tr = traj["trajectory"]
+        out["k%d_traj_E" % k] = np.array([t[1] for t in tr], np.float64)
+        out["k%d_traj_state" % k] = np.array([int(t[3][0]) for t in tr], np.int64)
+        out["k%d_traj_indices" % k] = np.array([np.concatenate(t[4]) for t in tr], np.int64)
+        out["k%d_state_counts" % k] = np.bincount(np.array(traj["state_trace"], np.int64), minlength=100)
+    np.savez_compressed(os.path.join(HERE, "tutorial_mbar.npz"), **out)
+
+
 if __name__ == "__main__":
     biceps = H.import_reference()
     make_cineromycin(biceps)
     make_apomyoglobin(biceps)
+    make_tutorial_mbar(biceps)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,65 @@
+"""GPU: u_kn rescoring (K6) and the streaming MBAR solver (K7) against the numpy oracle and the
+reference's stored tutorial results."""
+import numpy as np
+import pytest
+
+from helpers import load_npz, tables_from_npz, stack_lambdas
+from oracle import mbar_oracle as M
+
+pytestmark = pytest.mark.gpu
+
+
+def tutorial():
+    z = load_npz("tutorial_mbar.npz")
+    tabs = [tables_from_npz(z, "k%d_" % k) for k in range(2)]
+    trajs = [dict(E=z["k%d_traj_E" % k], state=z["k%d_traj_state" % k], indices=z["k%d_traj_indices" % k])
+             for k in range(2)]
+    return z, tabs, trajs
+
+
+def test_ukn_bitwise_and_tutorial_score():
+    from biceps_b200 import engine, mbar
+    z, tabs, trajs = tutorial()
+    want = M.analysis(tabs, trajs, 100)
+    T = engine.DeviceTables(stack_lambdas(tabs))
+    state = np.concatenate([t["state"] for t in trajs])
+    idx = np.concatenate([t["indices"] for t in trajs])
+    u = mbar.ukn(T, state, idx)
+    assert np.array_equal(u, want["u_kn"])                              # same fp64 op order -> same bits
+    r = mbar.mbar(u, want["N_k"], state, 100)
+    assert np.allclose(r["f"], want["f"], atol=1e-10)
+    assert abs(r["Delta_f"][0, 1] - z["BS"][1, 0]) < 1e-8 and abs(r["dDelta_f"][0, 1] - z["BS"][1, 1]) < 1e-8
+    sp = z["populations"]
+    assert np.max(np.abs(sp[:, :2] - r["P"])) < 1e-12
+    ok = ~np.isnan(sp[:, 2:])
+    assert np.array_equal(np.isnan(sp[:, 2:]), np.isnan(r["dP"]))
+    assert np.max(np.abs(sp[:, 2:][ok] - r["dP"][ok]) / sp[:, 2:][ok]) < 1e-9
+
+
+@pytest.mark.parametrize("K,n", [(1, 500), (3, 1000), (11, 20000), (40, 3000)])
+def test_mbar_against_oracle(K, n):
+    from biceps_b200 import mbar
+    rng = np.random.default_rng(K)
+    kspring = np.linspace(1.0, 4.0, K)
+    N_k = np.array([n + 17 * k for k in range(K)])                      # ragged sample counts
+    x = np.concatenate([rng.normal(0.1 * k, 1 / np.sqrt(ks), m) for k, (ks, m) in enumerate(zip(kspring, N_k))])
+    u_kn = 0.5 * kspring[:, None] * (x[None, :] - 0.1 * np.arange(K)[:, None]) ** 2
+    states = (np.abs(x) * 3).astype(np.int64) % 12
+    f, W, it = M.mbar_solve(u_kn, N_k)
+    Df, dDf, theta = M.free_energy_differences(f, W)
+    P, dP = M.populations(W, theta, states, 12)
+    r = mbar.mbar(u_kn, N_k, states, 12)
+    assert np.allclose(r["f"], f, atol=1e-9)
+    assert np.allclose(r["theta"], theta, rtol=1e-9, atol=1e-14)
+    assert np.allclose(r["dDelta_f"], dDf, rtol=1e-7, atol=1e-12)
+    assert np.allclose(r["P"], P, rtol=1e-9, atol=1e-14)
+    ok = ~np.isnan(dP)
+    assert np.allclose(r["dP"][ok], dP[ok], rtol=1e-7)
+
+
+def test_mbar_rejects_bad_input():
+    from biceps_b200 import mbar
+    with pytest.raises(RuntimeError):
+        mbar.mbar(np.zeros((2, 10)), [5, 4])            # sum(N_k) != N
+    with pytest.raises(RuntimeError):
+        mbar.mbar(np.zeros((2, 10)), [5, 5], np.full(10, 3), 3)   # state out of range
