@@ -19,78 +19,12 @@
 #include "exp_det.cuh"
 #include "philox.cuh"
 #include "tables.cuh"
+#include "sampler_common.cuh"
 
+#include <stdlib.h>
 #include <vector>
 
 namespace bcp {
-
-struct ChainBuffers {
-    long long n_chains;
-    unsigned long long seed, chain_id0;
-    const int* lam;         // [n]
-    const int* group;       // [n]
-    int* state;             // [n]
-    int* isg;               // [R][n]
-    int* igm;               // [R][n]
-    double* E;              // [n]
-    unsigned long long* accepted;     // [n]
-    unsigned long long* sep;          // [R+1][n]  (this sample() call)
-    unsigned long long* state_counts; // [groups][S]
-    unsigned long long* param_counts; // [groups][HB]
-};
-
-struct LaunchArgs {
-    unsigned long long step0;   // Philox step counter of local step 0
-    long long s_begin, s_end;   // local step range of this launch
-    long long burn;
-    long long traj_every;       // 0 = none
-    long long n_snap;
-    double* traj_E;             // [n_snap][n]
-    int* traj_state;            // [n_snap][n]
-    unsigned char* traj_accept; // [n_snap][n]
-    int* traj_idx;              // [n_snap][P][n]
-    int* state_trace;           // [n_steps][n] or nullptr
-};
-
-// number of recorded steps in [a, b): those with local step >= burn
-__device__ __forceinline__ long long recorded(long long a, long long b, long long burn) {
-    const long long lo = a > burn ? a : burn;
-    return b > lo ? b - lo : 0;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-// 1-D TMA bulk copy global -> shared with mbarrier completion (SASS: UBLKCP).
-__device__ __forceinline__ void stage_sigma_table(double* s_sig, const double* g_sig, int bytes,
-                                                  uint64_t* mbar) {
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)),
-                     "r"(bytes)
-                     : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-            ::"r"(smem_u32(s_sig)), "l"(g_sig), "r"(bytes), "r"(smem_u32(mbar))
-            : "memory");
-    }
-    // every thread waits for phase 0
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(mbar))
-        : "memory");
-}
 
 template <int R>
 __device__ __forceinline__ double restraint_term(const SamplerTables& T, const double* s_sig, int q,
@@ -435,6 +369,23 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
         return fail(BCP_ERR_INVALID);
     }
     if ((rc = upload(h, sig.data(), sig.size(), &T.sig_tab)) != BCP_OK) return fail(rc);
+    // packed per-state records for the specialised kernel (tables.cuh)
+    T.canonical = 1;
+    for (int q = 0; q < T.R; ++q)
+        if (T.r[q].has_gamma && q != T.R - 1) T.canonical = 0;
+    T.rec_stride = 2 * T.R;
+    T.rec = nullptr;
+    if (T.canonical) {
+        std::vector<double> rec((size_t)T.S * T.rec_stride, 0.0);
+        for (int q = 0; q < T.R; ++q) {
+            const bcp_restraint& r = t->restraints[q];
+            for (int i = 0; i < T.S; ++i) {
+                rec[(size_t)i * T.rec_stride + 2 * q] = T.r[q].has_gamma ? 0.0 : r.sse[i];
+                rec[(size_t)i * T.rec_stride + 2 * q + 1] = r.has_ref ? r.refsum[i] : 0.0;
+            }
+        }
+        if ((rc = upload(h, rec.data(), rec.size(), &T.rec)) != BCP_OK) return fail(rc);
+    }
     if ((rc = upload(h, t->energy, (size_t)T.K * T.S, &T.energy)) != BCP_OK) return fail(rc);
     if ((rc = upload(h, t->logZ, (size_t)T.K, &T.logZ)) != BCP_OK) return fail(rc);
     *out = h;
@@ -596,13 +547,24 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
     A.traj_E = c->d_traj_E; A.traj_state = c->d_traj_state; A.traj_accept = c->d_traj_accept;
     A.traj_idx = c->d_traj_idx; A.state_trace = n_trace ? c->d_trace : nullptr;
     const long long total = cfg->n_steps + cfg->burn;
+    // the specialised kernel covers the canonical layout; BCP_FORCE_GENERIC=1 selects the generic one
+    const char* force = getenv("BCP_FORCE_GENERIC");
+    const bool fast = T.canonical && !(force && force[0] == '1');
+    int fgrid = grid, fblock = block;
+    if (fast) {
+        int w = (int)((n_warps + sms - 1) / sms);
+        w = w < 1 ? 1 : (w > 4 ? 4 : w);
+        fblock = w * 32;
+        fgrid = (int)((n + fblock - 1) / fblock);
+    }
     BCP_CUDA(cudaEventRecord(c->ev0, st));
     int launches = 0;
     for (long long s0 = 0; s0 < total; s0 += kMaxStepsPerLaunch) {
         A.s_begin = s0;
         A.s_end = s0 + kMaxStepsPerLaunch < total ? s0 + kMaxStepsPerLaunch : total;
         cudaError_t e;
-        switch (T.R) {
+        if (fast) e = launch_mcmc_fast(T, c->C, A, fgrid, fblock, st);
+        else switch (T.R) {
             case 1: e = launch_mcmc<1>(T, c->C, A, grid, block, st); break;
             case 2: e = launch_mcmc<2>(T, c->C, A, grid, block, st); break;
             case 3: e = launch_mcmc<3>(T, c->C, A, grid, block, st); break;

@@ -1,0 +1,82 @@
+// Structures and device helpers shared by the generic and the specialised Metropolis kernels.
+#pragma once
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace bcp {
+
+struct ChainBuffers {
+    long long n_chains;
+    unsigned long long seed, chain_id0;
+    const int* lam;         // [n]
+    const int* group;       // [n]
+    int* state;             // [n]
+    int* isg;               // [R][n]
+    int* igm;               // [R][n]
+    double* E;              // [n]
+    unsigned long long* accepted;     // [n]
+    unsigned long long* sep;          // [R+1][n]  (this sample() call)
+    unsigned long long* state_counts; // [groups][S]
+    unsigned long long* param_counts; // [groups][HB]
+};
+
+struct LaunchArgs {
+    unsigned long long step0;   // Philox step counter of local step 0
+    long long s_begin, s_end;   // local step range of this launch
+    long long burn;
+    long long traj_every;       // 0 = none
+    long long n_snap;
+    double* traj_E;             // [n_snap][n]
+    int* traj_state;            // [n_snap][n]
+    unsigned char* traj_accept; // [n_snap][n]
+    int* traj_idx;              // [n_snap][P][n]
+    int* state_trace;           // [n_steps][n] or nullptr
+};
+
+// number of recorded steps in [a, b): those with local step >= burn
+__device__ __forceinline__ long long recorded(long long a, long long b, long long burn) {
+    const long long lo = a > burn ? a : burn;
+    return b > lo ? b - lo : 0;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// 1-D TMA bulk copy global -> shared with mbarrier completion (SASS: UBLKCP).
+__device__ __forceinline__ void stage_sigma_table(double* s_sig, const double* g_sig, int bytes,
+                                                  uint64_t* mbar) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)),
+                     "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(smem_u32(s_sig)), "l"(g_sig), "r"(bytes), "r"(smem_u32(mbar))
+            : "memory");
+    }
+    // every thread waits for phase 0
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(mbar))
+        : "memory");
+}
+
+
+// launches the specialised kernel (sampler_fast.cu); returns cudaErrorNotSupported if the table
+// layout is not the canonical one (at most one gamma restraint, and it is the last)
+cudaError_t launch_mcmc_fast(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, int grid, int block,
+                             cudaStream_t st);
+
+}  // namespace bcp

@@ -29,6 +29,14 @@ struct SamplerTables {
     int sig_bytes;          // multiple of 16
     int R, S, K, P, HB;
     uint32_t nuis_thresh;   // floor(R * 2^32 / (R+1))
+    // canonical layout (reference file-extension order: cs, J, noe): every restraint is SCALAR
+    // except, optionally, the last one.  rec[i] packs the state-dependent words of state i so
+    // that a state move touches one or two sectors: {sse_q, ref_q} for every scalar restraint,
+    // then {ref_g, 0} of the gamma restraint (ref = +0.0 where there is no reference potential;
+    // t - 0.0 == t bit for bit).
+    const double* rec;      // [S][rec_stride]
+    int rec_stride;         // 2 * R doubles
+    int canonical;          // 1 if the specialised kernel applies
 };
 
 const SamplerTables& handle_tables(const bcp_handle* h);

@@ -78,6 +78,50 @@ def test_three_scalar_restraints_with_reference_potentials():
     assert_outputs_equal(got, want)
 
 
+def test_generic_kernel_is_bit_exact_too(cin, monkeypatch):
+    """The canonical layout runs the specialised kernel; BCP_FORCE_GENERIC=1 and non-canonical layouts
+    (gamma restraint not last) run the generic one.  Both must match the oracle."""
+    monkeypatch.setenv("BCP_FORCE_GENERIC", "1")
+    lam = (np.arange(70) % 2).astype(np.int32)
+    got, want = run_both(cin, 70, 4, 2500, burn=11, traj_every=13, record_state_trace=True, chain_lambda=lam)
+    assert_outputs_equal(got, want)
+    monkeypatch.delenv("BCP_FORCE_GENERIC")
+    swapped = dict(cin)
+    swapped["restraints"] = [cin["restraints"][1], cin["restraints"][0]]      # noe first: non-canonical
+    got, want = run_both(swapped, 70, 4, 2500, burn=11, traj_every=13, record_state_trace=True, chain_lambda=lam)
+    assert_outputs_equal(got, want)
+
+
+def test_long_run_spans_several_launches(cin):
+    """> 2^22 steps are split over kernel launches; the chain must not notice."""
+    from biceps_b200 import engine
+    from oracle import cbind
+    T = engine.DeviceTables(cin, device=0)
+    n_steps = (1 << 22) + 12345
+    got = T.chains(32, 3, chain_lambda=np.ones(32, np.int32)).sample(n_steps, burn=1000, traj_every=50000)
+    want = cbind.sample(cin, 32, 3, n_steps, burn=1000, traj_every=50000, chain_lambda=np.ones(32, np.int32), n_threads=16)
+    assert_outputs_equal(got, want)
+
+
+def test_tiny_grids_and_single_state():
+    """Edge cases: 1-point gamma grid, 2-point sigma grid (wrap-around every move), a single state."""
+    rng = np.random.default_rng(5)
+    for S, nsig, G in [(1, 2, 1), (3, 3, 2), (5, 1, 4)]:
+        sig = np.linspace(0.5, 1.5, nsig)
+        def rt(kind):
+            d = dict(kind=kind, name=kind, ref="uniform", ndof=3.0, sigma=sig, nlsig=3.0 * np.log(sig),
+                     two_sig2=2.0 * sig ** 2, cnorm=2.75, grids=[], refsum=None)
+            if kind == "gamma":
+                d["grids"] = [np.linspace(0.8, 1.2, G)]
+                d["sse"] = rng.uniform(1, 5, (S, G)); d["refsum"] = rng.uniform(0, 1, S); d["ref"] = "exponential"
+            else:
+                d["sse"] = rng.uniform(1, 5, S)
+            return d
+        tabs = dict(n_states=S, energy=rng.uniform(0, 2, S), logZ=0.3, restraints=[rt("scalar"), rt("gamma")])
+        got, want = run_both(tabs, 40, 8, 1500, traj_every=3, record_state_trace=True)
+        assert_outputs_equal(got, want)
+
+
 def test_neglogp_matches_oracle(cin):
     from biceps_b200 import engine
     from oracle import sampler_oracle as O
