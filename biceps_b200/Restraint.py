@@ -1,0 +1,382 @@
+"""Ensemble and Restraint_{cs,J,noe,pf}: the reference's restraint API over columnar storage.
+
+Mirrors /root/reference/biceps/Restraint.py:81-894 (same class names, constructor / init_restraint
+arguments, option routing, error messages and attributes), but an ensemble is held as one dense
+fp64 table per restraint type (model[S][J], exp[J], weight[J]) and every S-sized quantity -- the
+sum of squared errors over the gamma grid, the reference-potential sums -- is computed by the
+CUDA kernels of csrc/precompute.cu in one call per restraint type instead of S*J*G Python
+iterations.  `ensemble.to_list()[state][k]` still returns one restraint object per (state, type);
+its `.restraints` list of dicts is materialised lazily from the columns.
+"""
+import inspect
+import sys
+
+import numpy as np
+import pandas as pd
+
+from . import precompute, toolbox
+
+
+def get_restraint_options(input_data=None):
+    """List of default option dicts, one per restraint class (or per restraint of input_data),
+    as biceps.get_restraint_options (Restraint.py:10-75)."""
+    current_module = sys.modules[__name__]
+    restraints = toolbox.list_possible_restraints()
+    extensions = None
+    if input_data is not None:
+        scheme = toolbox.list_res(input_data)
+        extensions = [res.split("_")[-1] for res in scheme]
+        restraints = [r for rest in scheme for r in restraints if r.split("_")[-1] in rest]
+    options = []
+    for k, name in enumerate(restraints):
+        R = getattr(current_module, name)
+        opt = {}
+        for key, par in inspect.signature(R).parameters.items():
+            opt[key] = [] if par.default is inspect._empty else par.default
+        for key, par in inspect.signature(R.init_restraint).parameters.items():
+            opt[key] = np.nan if par.default is inspect._empty else par.default
+        for key in ("data", "energy", "self", "verbose"):
+            opt.pop(key, None)
+        if extensions is not None:
+            opt["extension"] = extensions[k]
+        options.append(opt)
+    return options
+
+
+class Restraint(object):
+    """Parent restraint class (Restraint.py:201-298): sigma grid and reference-potential slots."""
+
+    kind = "scalar"
+    _columns = ("exp", "model")
+
+    def __init__(self, ref="uniform", sigma=[0.05, 20.0, 1.02], use_global_ref_sigma=True, verbose=False):
+        self.betas = None
+        self.neglog_exp_ref = None
+        self.sum_neglog_exp_ref = 0.0
+        self.ref_sigma = None
+        self.ref_mean = None
+        self.neglog_gaussian_ref = None
+        self.sum_neglog_gaussian_ref = 0.0
+        self.use_global_ref_sigma = use_global_ref_sigma
+        self._sse = None
+        self.ref = ref
+        # log-spaced sigma grid, start index len/2 (Restraint.py:235-241)
+        self.dlogsigma = np.log(sigma[2])
+        self.sigma_min = sigma[0]
+        self.sigma_max = sigma[1]
+        self.allowed_sigma = np.exp(np.arange(np.log(self.sigma_min), np.log(self.sigma_max), self.dlogsigma))
+        self.sigma_index = int(len(self.allowed_sigma) / 2)
+        self.sigma = self.allowed_sigma[self.sigma_index]
+        self.verbose = verbose
+        self._frame = None
+        self._restraints = None
+        self._weights = None
+        self.Ndof = None
+
+    # -- data ------------------------------------------------------------------------------
+    def load_data(self, filename, As="pickle"):
+        if self.verbose:
+            print('Loading %s as %s...' % (filename, As))
+        return getattr(pd, "read_%s" % As)(filename)
+
+    def _ingest(self, data, energy, extension, weight, file_fmt):
+        self.extension = extension
+        self.energy = energy
+        frame = self.load_data(data, As=file_fmt)
+        self.n = len(frame.values)
+        self._frame = frame[list(self._columns_present(frame))]
+        self._exp = np.asarray(self._frame["exp"], dtype=np.float64)
+        self._model = np.asarray(self._frame["model"], dtype=np.float64) if "model" in self._frame else None
+        self._weight_option = weight
+
+    def _columns_present(self, frame):
+        return [c for c in self._columns]
+
+    def _compute_weights(self):
+        return np.full(self.n, float(self._weight_option), dtype=np.float64)
+
+    @property
+    def weights(self):
+        if self._weights is None:
+            self._weights = self._compute_weights()
+            self.Ndof = precompute.ndof(self._weights)
+        return self._weights
+
+    @property
+    def restraints(self):
+        """List of per-observable dicts {exp, model, weight, ...} like the reference's
+        self.restraints (Restraint.py:336-341, 414-416, 523-525); built on first access."""
+        if self._restraints is None:
+            cols = {k: self._frame[k].tolist() for k in self._frame.columns}
+            w = self.weights
+            self._restraints = [dict({k: v[j] for k, v in cols.items()}, weight=float(w[j])) for j in range(self.n)]
+        return self._restraints
+
+    def add_restraint(self, restraint):
+        self.restraints.append(restraint)
+
+    # -- sum of squared errors -------------------------------------------------------------
+    @property
+    def sse(self):
+        if self._sse is None:      # stand-alone restraint (not part of an Ensemble): one-state GPU call
+            self._sse = self._gpu_sse(self._model[None, :])[0]
+        return self._sse
+
+    @sse.setter
+    def sse(self, v):
+        self._sse = v
+
+    def _gpu_sse(self, model):
+        out = precompute.restraint_tables(self.kind, model, self._exp, self.weights, ref="uniform",
+                                          gamma=getattr(self, "allowed_gamma", None),
+                                          log_normal=getattr(self, "log_normal", False))
+        return out["sse"]
+
+    def compute_sse(self, f):
+        """(Weighted) sum of squared errors of a list of {model, exp, weight} dicts
+        (Restraint.py:344-353, 445-454, 552-569), evaluated on the GPU."""
+        model = np.array([[d["model"] for d in f]], dtype=np.float64)
+        exp = np.array([d["exp"] for d in f], dtype=np.float64)
+        w = np.array([d["weight"] for d in f], dtype=np.float64)
+        self.Ndof = precompute.ndof(w)
+        out = precompute.restraint_tables(self.kind, model, exp, w, gamma=getattr(self, "allowed_gamma", None),
+                                          log_normal=getattr(self, "log_normal", False))
+        return out["sse"][0]
+
+    # label used in rest_type, reproducing the reference's parsing of str(R.__repr__)
+    # (PosteriorSampler.py:280, 414): 'sigma_J', 'sigma_noe', 'gamma_noe', and for cs 'sigma_H>>'
+    def _label(self):
+        return type(self).__name__.split("_")[-1]
+
+    def _param_names(self):
+        return ["sigma"]
+
+    def _param_grids(self):
+        return [self.allowed_sigma]
+
+    def _param_start(self):
+        return [self.sigma_index]
+
+
+class Restraint_cs(Restraint):
+    """Chemical shifts (Restraint.py:301-383)."""
+
+    _ext = ["H", "Ca", "N"]
+    _columns = ("atom_index1", "exp", "model")
+
+    def __repr__(self):
+        if getattr(self, "extension", None) is not None:
+            return "<%s.Restraint_cs_%s>" % (str(__name__), str(self.extension))
+
+    def init_restraint(self, data, energy, extension="H", weight=1, file_fmt="pickle", verbose=False):
+        self._ingest(data, energy, extension, weight, file_fmt)
+
+    def _label(self):
+        return "%s>>" % self.extension
+
+
+class _Grouped(Restraint):
+    """J and NOE: equivalency groups by restraint_index get weight 1/n (Restraint.py:418-442)."""
+
+    def _compute_weights(self):
+        ri = self._frame["restraint_index"].tolist()
+        w = np.zeros(self.n, dtype=np.float64)
+        groups = {}
+        for i, r in enumerate(ri):
+            if r is not None:
+                groups.setdefault(r, []).append(i)
+        for g in groups.values():
+            w[g] = 1.0 / float(len(g))
+        self.equivalency_groups = groups
+        return w
+
+
+class Restraint_J(_Grouped):
+    """J coupling constants (Restraint.py:386-477)."""
+
+    _ext = ["J"]
+    _columns = ("atom_index1", "atom_index2", "atom_index3", "atom_index4", "exp", "model", "restraint_index")
+
+    def init_restraint(self, data, energy, extension="J", weight=1, file_fmt="pickle", verbose=False):
+        self._ingest(data, energy, extension, weight, file_fmt)
+
+
+class Restraint_noe(_Grouped):
+    """NOE distances with the gamma scaling grid (Restraint.py:481-592)."""
+
+    _ext = ["noe"]
+    _columns = ("exp", "model", "restraint_index")
+    kind = "gamma"
+
+    def init_restraint(self, data, energy, extension="noe", weight=1, file_fmt="pickle", verbose=False,
+                       log_normal=False, gamma=[0.2, 10.0, 1.01]):
+        self.dloggamma = np.log(gamma[2])
+        self.gamma_min = gamma[0]
+        self.gamma_max = gamma[1]
+        self.allowed_gamma = np.exp(np.arange(np.log(self.gamma_min), np.log(self.gamma_max), self.dloggamma))
+        self.gamma_index = int(len(self.allowed_gamma) / 2)
+        self.gamma = self.allowed_gamma[self.gamma_index]
+        self.log_normal = log_normal
+        self._ingest(data, energy, extension, weight, file_fmt)
+
+    def _param_names(self):
+        return ["sigma", "gamma"]
+
+    def _param_grids(self):
+        return [self.allowed_sigma, self.allowed_gamma]
+
+    def _param_start(self):
+        return [self.sigma_index, self.gamma_index]
+
+
+class Restraint_pf(Restraint):
+    """HDX protection factors (Restraint.py:595-894).  Only the `precomputed=True` branch (model
+    ln PF values stored in the data file, one sigma nuisance parameter, Restraint.py:736-741, 881)
+    is on the GPU path in this build; the 6-D (beta_c, beta_h, beta_0, xcs, xhs, bs) grid branch
+    raises NotImplementedError (scope table row a3)."""
+
+    _ext = ["pf"]
+    _columns = ("atom_index1", "exp", "model")
+
+    def init_restraint(self, data, energy, precomputed=False, pf_prior=None, Ncs_fi=None, Nhs_fi=None,
+                       beta_c=(0.05, 0.25, 0.01), beta_h=(0.0, 5.2, 0.2), beta_0=(-10.0, 0.0, 0.2),
+                       xcs=(5.0, 8.5, 0.5), xhs=(2.0, 2.7, 0.1), bs=(15.0, 16.0, 1.0), extension="pf", weight=1,
+                       file_fmt="pickle", states=None, verbose=False):
+        self.precomputed = precomputed
+        if not precomputed:
+            raise NotImplementedError("Restraint_pf on the 6-D nuisance grid (precomputed=False) is not part of "
+                                      "this build's GPU path; use precomputed=True")
+        self._ingest(data, energy, extension, weight, file_fmt)
+
+
+class Ensemble(object):
+    """Container of restraint objects for every conformational state (Restraint.py:81-197)."""
+
+    def __init__(self, lam, energies, debug=False):
+        self.ensemble = []
+        if not isinstance(lam, float):
+            raise ValueError("lambda should be a single number with type of 'float'")
+        self.lam = lam
+        if np.array(energies).dtype != float:
+            raise ValueError("Energies should be array with type of 'float'")
+        self.energies = self.lam * energies      # scale the energies (Restraint.py:99)
+        self.debug = debug
+        self.columns = []                         # one dict per restraint type (device-ready tables)
+        self.options = None
+
+    def to_list(self):
+        return self.ensemble
+
+    @staticmethod
+    def _route_options(R, opts, input_data):
+        """Split an options dict into constructor and init_restraint keyword arguments, rejecting
+        unknown keys with the reference's message (Restraint.py:169-189)."""
+        ctor = [k for k in inspect.signature(R).parameters]
+        init = [k for k in inspect.signature(R.init_restraint).parameters if k != "self"]
+        a1, a2 = {}, {}
+        for key, val in opts.items():
+            if key in ctor:
+                a1[key] = val
+            elif key in init:
+                a2[key] = val
+            else:
+                possible_args = np.unique(np.concatenate([ctor, init]))
+                possible_args = np.delete(possible_args, np.where(possible_args == "data"))
+                raise TypeError(f"{key} is an invalid keyword argument for {R}\n\n\
+Please check your options... \n\
+The input data provided suggests the ordering of dictionaries should be: {toolbox.list_extensions(input_data)}\n\
+Dictionary keys for {R.__name__} are any of: {possible_args}")
+        return a1, a2
+
+    def initialize_restraints(self, input_data, options=None, device=0):
+        """Create a restraint object per (state, data file), then compute every sum of squared
+        errors of the ensemble on the GPU (one bcp_precompute call per restraint type)."""
+        self.options = options
+        if options is None:
+            options = [dict() for _ in range(len(input_data[0]))]
+        current_module = sys.modules[__name__]
+        routed = {}
+        for i in range(self.energies.shape[0]):
+            self.ensemble.append([])
+            energy = self.energies[i]
+            for k in range(len(input_data[0])):
+                data = input_data[i][k]
+                ext = data.split(".")[-1]
+                restraint, extension = ext.split("_")[0], ext.split("_")[-1]
+                R = getattr(current_module, "Restraint_%s" % restraint)
+                if k not in routed:
+                    routed[k] = self._route_options(R, options[k], input_data)
+                a1, a2 = routed[k]
+                obj = R(**a1)
+                obj.init_restraint(data=data, energy=energy, **dict(dict(extension=extension), **a2))
+                self.ensemble[-1].append(obj)
+        self._finalize(device)
+
+    @classmethod
+    def from_arrays(cls, lam, energies, restraints, device=0):
+        """Bulk constructor (no per-state files): restraints = list of dicts
+        {cls: 'cs'|'J'|'noe', extension, model[S][J], exp[J], weight[J] or restraint_index[J], options}."""
+        self = cls(lam, energies)
+        S = self.energies.shape[0]
+        mod = sys.modules[__name__]
+        objs_per_k = []
+        for rd in restraints:
+            R = getattr(mod, "Restraint_%s" % rd["cls"])
+            a1, a2 = cls._route_options(R, rd.get("options", {}), [["x.%s" % rd.get("extension", rd["cls"])]])
+            model = np.asarray(rd["model"], np.float64)
+            exp = np.asarray(rd["exp"], np.float64)
+            J = exp.shape[0]
+            ri = rd.get("restraint_index", list(range(J)))
+            objs = []
+            for i in range(S):
+                o = R(**a1)
+                cols = {"exp": exp, "model": model[i]}
+                for c in R._columns:
+                    if c not in cols:
+                        cols[c] = ri if c == "restraint_index" else list(range(J))
+                o._frame = pd.DataFrame(cols) if i == 0 else objs[0]._frame
+                o.extension = rd.get("extension", rd["cls"])
+                o.energy = self.energies[i]
+                o.n = J
+                o._exp, o._model = exp, model[i]
+                o._weight_option = rd.get("options", {}).get("weight", 1)
+                if "weight" in rd:
+                    o._weights = np.asarray(rd["weight"], np.float64)
+                    o.Ndof = precompute.ndof(o._weights)
+                if R is Restraint_noe:
+                    g = a2.get("gamma", [0.2, 10.0, 1.01])
+                    o.allowed_gamma = np.exp(np.arange(np.log(g[0]), np.log(g[1]), np.log(g[2])))
+                    o.gamma_index = int(len(o.allowed_gamma) / 2)
+                    o.gamma = o.allowed_gamma[o.gamma_index]
+                    o.log_normal = a2.get("log_normal", False)
+                objs.append(o)
+            objs_per_k.append(objs)
+        self.ensemble = [[objs_per_k[k][i] for k in range(len(restraints))] for i in range(S)]
+        for k in range(len(restraints)):                    # share weights of state 0 with every state
+            w = objs_per_k[k][0].weights
+            for o in objs_per_k[k][1:]:
+                o._weights, o.Ndof = w, objs_per_k[k][0].Ndof
+        self._finalize(device)
+        return self
+
+    def _finalize(self, device):
+        """Columnar tables + GPU SSE for each restraint type."""
+        S = len(self.ensemble)
+        self.columns = []
+        for k, R0 in enumerate(self.ensemble[0]):
+            objs = [s[k] for s in self.ensemble]
+            model = np.ascontiguousarray(np.stack([o._model for o in objs]), dtype=np.float64)
+            w = R0.weights
+            col = dict(kind=R0.kind, name=type(R0).__name__.split("_")[-1], extension=R0.extension, ref=R0.ref,
+                       model=model, exp=R0._exp, weight=w, ndof=R0.Ndof, sigma=R0.allowed_sigma,
+                       gamma=getattr(R0, "allowed_gamma", None), log_normal=getattr(R0, "log_normal", False),
+                       use_global_ref_sigma=R0.use_global_ref_sigma)
+            out = precompute.restraint_tables(R0.kind, model, R0._exp, w, ref="uniform", gamma=col["gamma"],
+                                              log_normal=col["log_normal"], device=device)
+            col["sse"] = out["sse"]
+            for i, o in enumerate(objs):
+                o._sse = out["sse"][i]
+                o._weights, o.Ndof = w, R0.Ndof
+            self.columns.append(col)
+        self.device = device
+        assert S == self.energies.shape[0]

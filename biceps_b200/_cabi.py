@@ -170,6 +170,7 @@ _SIGS = {
     "bcp_sample": (C.c_int, [C.c_void_p, C.POINTER(bcp_sample_cfg), C.POINTER(bcp_sample_out)]),
     "bcp_sample_launch": (C.c_int, [C.c_void_p, C.POINTER(bcp_sample_cfg), C.c_void_p]),
     "bcp_chains_sync": (C.c_int, [C.c_void_p]),
+    "bcp_chains_set_state": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_double_p]),
     "bcp_chains_fetch": (C.c_int, [C.c_void_p, C.POINTER(bcp_sample_out)]),
     "bcp_chains_device_hist": (C.c_int, [C.c_void_p, C.POINTER(c_int64_p), C.POINTER(c_int64_p)]),
     "bcp_chains_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), c_int32_p]),

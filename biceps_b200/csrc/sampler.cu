@@ -372,7 +372,7 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
     // packed per-state records for the specialised kernel (tables.cuh)
     T.canonical = 1;
     for (int q = 0; q < T.R; ++q)
-        if (T.r[q].has_gamma && q != T.R - 1) T.canonical = 0;
+        if (T.r[q].has_gamma && (q != T.R - 1 || T.r[q].n_gamma < 2)) T.canonical = 0;
     T.rec_stride = 2 * T.R;
     T.rec = nullptr;
     if (T.canonical) {
@@ -385,6 +385,16 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
             }
         }
         if ((rc = upload(h, rec.data(), rec.size(), &T.rec)) != BCP_OK) return fail(rc);
+        T.gsse_halo = nullptr;
+        if (T.r[T.R - 1].has_gamma) {
+            const int G = T.r[T.R - 1].n_gamma;
+            const double* src = t->restraints[T.R - 1].sse;
+            std::vector<double> halo((size_t)T.S * (G + 4));
+            for (int i = 0; i < T.S; ++i)
+                for (int k = 0; k < G + 4; ++k)
+                    halo[(size_t)i * (G + 4) + k] = src[(size_t)i * G + ((k - 2) % G + G) % G];
+            if ((rc = upload(h, halo.data(), halo.size(), &T.gsse_halo)) != BCP_OK) return fail(rc);
+        }
     }
     if ((rc = upload(h, t->energy, (size_t)T.K * T.S, &T.energy)) != BCP_OK) return fail(rc);
     if ((rc = upload(h, t->logZ, (size_t)T.K, &T.logZ)) != BCP_OK) return fail(rc);
@@ -657,6 +667,42 @@ extern "C" int bcp_chains_fetch(bcp_chains* c, bcp_sample_out* o) {
         }
     }
 #undef D2H
+    return BCP_OK;
+}
+
+extern "C" int bcp_chains_set_state(bcp_chains* c, const int32_t* state, const int32_t* indices, const double* energy) {
+    BCP_REQUIRE(c, "bcp_chains_set_state: NULL argument");
+    bcp_handle* h = c->h;
+    DeviceGuard guard(h->device);
+    const SamplerTables& T = h->T;
+    const size_t n = (size_t)c->C.n_chains;
+    BCP_CUDA(cudaStreamSynchronize(c->last_stream));
+    if (state) {
+        for (size_t i = 0; i < n; ++i)
+            BCP_REQUIRE(state[i] >= 0 && state[i] < T.S, "bcp_chains_set_state: state[%zu] out of range", i);
+        BCP_CUDA(cudaMemcpy(c->C.state, state, n * 4, cudaMemcpyHostToDevice));
+    }
+    if (energy) BCP_CUDA(cudaMemcpy(c->C.E, energy, n * 8, cudaMemcpyHostToDevice));
+    if (indices) {
+        std::vector<int> isg((size_t)T.R * n), igm((size_t)T.R * n, 0);
+        for (size_t i = 0; i < n; ++i) {
+            int p = 0;
+            for (int q = 0; q < T.R; ++q) {
+                const int sg = indices[i * T.P + p];
+                BCP_REQUIRE(sg >= 0 && sg < h->grid_len[p], "bcp_chains_set_state: indices[%zu][%d] out of range", i, p);
+                isg[(size_t)q * n + i] = sg;
+                ++p;
+                if (T.r[q].has_gamma) {
+                    const int gm = indices[i * T.P + p];
+                    BCP_REQUIRE(gm >= 0 && gm < h->grid_len[p], "bcp_chains_set_state: indices[%zu][%d] out of range", i, p);
+                    igm[(size_t)q * n + i] = gm;
+                    ++p;
+                }
+            }
+        }
+        BCP_CUDA(cudaMemcpy(c->C.isg, isg.data(), isg.size() * 4, cudaMemcpyHostToDevice));
+        BCP_CUDA(cudaMemcpy(c->C.igm, igm.data(), igm.size() * 4, cudaMemcpyHostToDevice));
+    }
     return BCP_OK;
 }
 

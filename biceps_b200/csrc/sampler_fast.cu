@@ -25,28 +25,30 @@ namespace bcp {
 __device__ __forceinline__ int wrap1(int v, int n) {      // v in [-1, n]
     return v < 0 ? v + n : (v >= n ? v - n : v);
 }
-__device__ __forceinline__ int inc_wrap(int v, int n) {   // v in [0, n)
-    return v + 1 == n ? 0 : v + 1;
-}
-__device__ __forceinline__ int wrap_any(int v, int n) {   // any v, small |v - [0,n)| distance
-    while (v < 0) v += n;
-    while (v >= n) v -= n;
-    return v;
-}
 __device__ __forceinline__ double sel3(int d, double m, double z, double p) {   // d in {-1,0,1}
     return d < 0 ? m : (d > 0 ? p : z);
 }
+
+// state-move words of the NEXT step, filled one step ahead (ping-pong: no register copies)
+template <int R>
+struct Prefetch {
+    double C;
+    double2 rec[R];
+    double W[5];
+};
 
 template <int R, bool HG>
 __global__ void __launch_bounds__(128)
 mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                  const __grid_constant__ LaunchArgs A) {
-    constexpr int RS = HG ? R - 1 : R;      // scalar restraints
     constexpr int QG = R - 1;               // index of the gamma restraint (if HG)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_sig = reinterpret_cast<double*>(smem_raw);
     __shared__ __align__(8) uint64_t mbar;
-    stage_sigma_table(s_sig, T.sig_tab, T.sig_bytes, &mbar);
+    __shared__ int4 s_meta[BCP_MAX_RESTRAINTS];     // {n_sigma, sig_off, hist_sigma, 0} by restraint
+    if (threadIdx.x < R)
+        s_meta[threadIdx.x] = make_int4(T.r[threadIdx.x].n_sigma, T.r[threadIdx.x].sig_off, T.r[threadIdx.x].hist_sigma, 0);
+    stage_sigma_table(s_sig, T.sig_tab, T.sig_bytes, &mbar);        // contains a __syncthreads
 
     const long long n = C.n_chains;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,48 +60,49 @@ mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     const double* __restrict__ energy = T.energy + (size_t)lam * T.S;
     const double logZ = T.logZ[lam];
     const double2* __restrict__ rec2 = reinterpret_cast<const double2*>(T.rec);
-    const double* __restrict__ gsse = HG ? T.r[QG].sse : nullptr;
-    const int G = HG ? T.r[QG].n_gamma : 1;
+    const double* __restrict__ gsse = HG ? T.gsse_halo : nullptr;     // rows of G + 4 (periodic halo)
+    const int G = HG ? T.r[QG].n_gamma : 1;           // >= 2 (checked on the host)
+    const int GH = G + 4;
     unsigned long long* g_state_counts = C.state_counts + (size_t)grp * T.S;
     unsigned long long* g_param_counts = C.param_counts + (size_t)grp * T.HB;
     const int S = T.S;
     const uint32_t thresh = T.nuis_thresh;
-    const int s_begin = 0, s_end = (int)(A.s_end - A.s_begin);      // launch-local step counter
+    const int s_end = (int)(A.s_end - A.s_begin);                    // launch-local step counter
     const long long burn_l = A.burn - A.s_begin;                     // may be negative
     const int burn = burn_l < 0 ? 0 : (burn_l > s_end ? s_end : (int)burn_l);
     const unsigned long long ctr0 = A.step0 + (unsigned long long)A.s_begin;
+    const uint32_t seed_lo = (uint32_t)C.seed, seed_hi = (uint32_t)(C.seed >> 32);
+    const uint32_t ch_lo = (uint32_t)chain_id, ch_hi = (uint32_t)(chain_id >> 32);
 
     // ---- chain state -------------------------------------------------------------------
     int state = C.state[c];
     double E = C.E[c];
     int isg[R];
     int igm = 0;
-    double cA[R], cD[R];
-    double csse[R], cref[R];            // [QG] entries of csse unused when HG (window instead)
+    double csse[R], cref[R];            // csse[QG] unused when HG (3-wide window instead)
     double W0 = 0.0, W1 = 0.0, W2 = 0.0;
     int since_sg[R];
-    int since_gm = s_begin, since_state = s_begin;
+    int since_gm = 0, since_state = 0;
     unsigned int acc_r[R];
     unsigned int acc_state = 0, acc_total = 0;
 #pragma unroll
     for (int q = 0; q < R; ++q) {
         isg[q] = C.isg[(size_t)q * n + c];
-        cA[q] = s_sig[T.r[q].sig_off + isg[q]];
-        cD[q] = s_sig[T.r[q].sig_off + T.r[q].n_sigma + isg[q]];
         const double2 v = rec2[(size_t)state * R + q];
         csse[q] = v.x;
         cref[q] = v.y;
-        since_sg[q] = s_begin;
+        since_sg[q] = 0;
         acc_r[q] = 0;
     }
     if (HG) {
         igm = C.igm[(size_t)QG * n + c];
-        const double* row = gsse + (size_t)state * G;
-        W0 = row[wrap1(igm - 1, G)];
-        W1 = row[igm];
-        W2 = row[wrap1(igm + 1, G)];
+        const double* row = gsse + (size_t)state * GH + igm + 1;      // halo: [igm-1, igm, igm+1]
+        W0 = row[0];
+        W1 = row[1];
+        W2 = row[2];
     }
     double Cst = __dadd_rn(energy[state], logZ);
+    int pshift = 0;
 
     int next_snap = -1;
     long long snap_idx = 0;
@@ -110,154 +113,122 @@ mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         next_snap = ns < s_end ? (int)ns : -1;
     }
 
-    // ---- software pipeline prologue: RNG + state-move prefetch for the first step ------
-    Philox4 w = step_block(C.seed, chain_id, ctr0);
-    double pC = 0.0;
-    double2 prec[R];
-    double pW[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    // issue the loads a state move to state i2 will need (igm = gamma index before the
+    // current step resolves; the 5-wide window covers a +-1 change)
+    auto prefetch = [&](Prefetch<R>& p, int i2) {
+        p.C = __ldg(energy + i2);
 #pragma unroll
-    for (int q = 0; q < R; ++q) prec[q] = make_double2(0.0, 0.0);
-    int pshift = 0;
-    {
-        const bool nuis0 = w.w0 < thresh;
-        if (!nuis0) {
-            const int i2 = (int)(((uint64_t)w.w1 * (uint32_t)S) >> 32);
-            pC = __ldg(energy + i2);
+        for (int q = 0; q < R; ++q) p.rec[q] = __ldg(rec2 + (size_t)i2 * R + q);
+        if (HG) {
+            const double* row = gsse + (size_t)i2 * GH + igm;            // halo: [igm-2 .. igm+2], no wrap
 #pragma unroll
-            for (int q = 0; q < R; ++q) prec[q] = __ldg(rec2 + (size_t)i2 * R + q);
-            if (HG) {
-                const double* row = gsse + (size_t)i2 * G;
-                int v = wrap_any(igm - 2, G);
-#pragma unroll
-                for (int k = 0; k < 5; ++k) { pW[k] = __ldg(row + v); v = inc_wrap(v, G); }
-            }
+            for (int k = 0; k < 5; ++k) p.W[k] = __ldg(row + k);
         }
-    }
+    };
 
-    for (int s = s_begin; s < s_end; ++s) {
-        // ---- decode the proposal of step s -------------------------------------------
+    // one Metropolis step: consumes `use` (if this step is a state move), fills `fill` for the
+    // next step, reads the RNG block w and produces the next one in wn
+    auto step = [&](const int s, const Philox4& w, Philox4& wn, const Prefetch<R>& use, Prefetch<R>& fill) {
+        // ---- decode the proposal ---------------------------------------------------------
         const bool nuis = w.w0 < thresh;
         const uint64_t pr = (uint64_t)w.w1 * (uint32_t)(nuis ? R : S);
         const int hi = (int)(pr >> 32);
-        uint32_t f = (uint32_t)pr;
         const int pick = nuis ? hi : -1;
         const int nstate = nuis ? state : hi;
-        uint64_t z = (uint64_t)f * 3u;
-        const int dsg = (int)(z >> 32) - 1;
-        f = (uint32_t)z;
-        z = (uint64_t)f * 3u;
+        const uint64_t z1 = (uint64_t)(uint32_t)pr * 3u;
+        const int dsg = (int)(z1 >> 32) - 1;
+        const uint64_t z2 = (uint64_t)(uint32_t)z1 * 3u;
         const bool pg = HG && pick == QG;
-        const int dgm = pg ? (int)(z >> 32) - 1 : 0;
+        const int dgm = pg ? (int)(z2 >> 32) - 1 : 0;
         const double u2 = u2_from_words(w.w2, w.w3);
 
-        int sg_old = 0, nsig = 1, off = 0;
+        const int4 meta = s_meta[nuis ? hi : 0];       // {n_sigma, sig_off, hist_sigma}
+        int sg_old = 0, since_sel = 0;
 #pragma unroll
         for (int q = 0; q < R; ++q)
-            if (q == pick) { sg_old = isg[q]; nsig = T.r[q].n_sigma; off = T.r[q].sig_off; }
-        const int sgn = nuis ? wrap1(sg_old + dsg, nsig) : 0;
-        const double An = s_sig[off + sgn];
-        const double Dn = s_sig[off + nsig + sgn];
+            if (q == pick) { sg_old = isg[q]; since_sel = since_sg[q]; }
+        const int sgn = wrap1(sg_old + dsg, meta.x);   // meaningful for nuisance lanes only
         const int gmn = HG ? wrap1(igm + dgm, G) : 0;
 
-        // ---- operands of the R terms (registers only) --------------------------------
-        double num[R], ref[R];
+        // ---- operands of the R terms -----------------------------------------------------
+        double num[R], ref[R], av[R], dv[R];
 #pragma unroll
-        for (int q = 0; q < RS; ++q) {
-            num[q] = nuis ? csse[q] : prec[q].x;
-            ref[q] = nuis ? cref[q] : prec[q].y;
+        for (int q = 0; q < R; ++q) {
+            const int sq = (q == pick) ? sgn : isg[q];
+            av[q] = s_sig[T.r[q].sig_off + sq];
+            dv[q] = s_sig[T.r[q].sig_off + T.r[q].n_sigma + sq];
+            num[q] = nuis ? csse[q] : use.rec[q].x;
+            ref[q] = nuis ? cref[q] : use.rec[q].y;
         }
-        if (HG) {
-            const double wsel = sel3(dgm, W0, W1, W2);
-            const double psel = sel3(pshift, pW[1], pW[2], pW[3]);
-            num[QG] = nuis ? wsel : psel;
-            ref[QG] = nuis ? cref[QG] : prec[QG].y;
-        }
-        const double Cn = nuis ? Cst : __dadd_rn(pC, logZ);
-        // state-move words that survive an acceptance (consumed before the next prefetch)
         double nW0 = 0.0, nW2 = 0.0;
         if (HG) {
-            nW0 = sel3(pshift, pW[0], pW[1], pW[2]);
-            nW2 = sel3(pshift, pW[2], pW[3], pW[4]);
+            num[QG] = nuis ? sel3(dgm, W0, W1, W2) : sel3(pshift, use.W[1], use.W[2], use.W[3]);
+            nW0 = sel3(pshift, use.W[0], use.W[1], use.W[2]);
+            nW2 = sel3(pshift, use.W[2], use.W[3], use.W[4]);
         }
-        double2 keep[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) keep[q] = prec[q];
+        const double Cn = nuis ? Cst : __dadd_rn(use.C, logZ);
 
-        // ---- next step: RNG and, if it is a state move, its table words ---------------
-        const Philox4 wn = step_block(C.seed, chain_id, ctr0 + (unsigned long long)(s + 1));
-        if (!(wn.w0 < thresh) && s + 1 < s_end) {
-            const int i2 = (int)(((uint64_t)wn.w1 * (uint32_t)S) >> 32);
-            pC = __ldg(energy + i2);
-#pragma unroll
-            for (int q = 0; q < R; ++q) prec[q] = __ldg(rec2 + (size_t)i2 * R + q);
-            if (HG) {
-                const double* row = gsse + (size_t)i2 * G;
-                int v = wrap_any(igm - 2, G);
-#pragma unroll
-                for (int k = 0; k < 5; ++k) { pW[k] = __ldg(row + v); v = inc_wrap(v, G); }
-            }
+        // ---- next step: RNG and, if it is a state move, its table words -------------------
+        {
+            const unsigned long long ctr = ctr0 + (unsigned long long)(s + 1);
+            wn = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), ch_lo, ch_hi, seed_lo, seed_hi);
+            if (!(wn.w0 < thresh)) prefetch(fill, (int)(((uint64_t)wn.w1 * (uint32_t)S) >> 32));
         }
 
-        // ---- energy of the proposal, reference fp64 order ----------------------------
+        // ---- energy of the proposal, reference fp64 order ---------------------------------
         double En = Cn;
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-            const double a = (q == pick) ? An : cA[q];
-            const double d = (q == pick) ? Dn : cD[q];
-            double t = __dadd_rn(a, __ddiv_rn(num[q], d));
+            double t = __dadd_rn(av[q], __ddiv_rn(num[q], dv[q]));
             t = __dadd_rn(t, T.r[q].cnorm);
             t = __dsub_rn(t, ref[q]);
             En = __dadd_rn(En, t);
         }
+        const bool acc = (En < E) || metropolis_accept(__dsub_rn(E, En), u2);
 
-        bool acc;
-        if (En < E) acc = true;
-        else acc = metropolis_accept(__dsub_rn(E, En), u2);
-
-        // ---- update -------------------------------------------------------------------
+        // ---- update (predicated; only the histogram flushes branch) -----------------------
+        const bool acc_n = acc && nuis, acc_s = acc && !nuis;
+        E = acc ? En : E;
+        acc_total += acc ? 1u : 0u;
+        acc_state += acc_s ? 1u : 0u;
+        const bool sg_changed = acc_n && sgn != sg_old;
+        if (sg_changed) {
+            const int lo = since_sel > burn ? since_sel : burn;
+            if (s > lo) atomicAdd(g_param_counts + meta.z + sg_old, (unsigned long long)(s - lo));
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const bool mine = q == pick;
+            acc_r[q] += (acc_n && mine) ? 1u : 0u;
+            isg[q] = (sg_changed && mine) ? sgn : isg[q];
+            since_sg[q] = (sg_changed && mine) ? s : since_sg[q];
+            csse[q] = acc_s ? use.rec[q].x : csse[q];
+            cref[q] = acc_s ? use.rec[q].y : cref[q];
+        }
+        Cst = acc_s ? Cn : Cst;
         pshift = 0;
-        if (acc) {
-            E = En;
-            ++acc_total;
-            if (nuis) {
-#pragma unroll
-                for (int q = 0; q < R; ++q) {
-                    if (q == pick) {
-                        ++acc_r[q];
-                        if (sgn != isg[q]) {
-                            const int lo = since_sg[q] > burn ? since_sg[q] : burn;
-                            if (s > lo) atomicAdd(g_param_counts + T.r[q].hist_sigma + isg[q], (unsigned long long)(s - lo));
-                            since_sg[q] = s;
-                            isg[q] = sgn;
-                            cA[q] = An;
-                            cD[q] = Dn;
-                        }
-                    }
-                }
-                if (HG && dgm != 0) {
-                    const int lo = since_gm > burn ? since_gm : burn;
-                    if (s > lo) atomicAdd(g_param_counts + T.r[QG].hist_gamma + igm, (unsigned long long)(s - lo));
-                    since_gm = s;
-                    igm = gmn;
-                    pshift = dgm;
-                    // slide the window and fetch the new edge
-                    const double edge = __ldg(gsse + (size_t)state * G + wrap1(gmn + dgm, G));
-                    if (dgm > 0) { W0 = W1; W1 = W2; W2 = edge; }
-                    else { W2 = W1; W1 = W0; W0 = edge; }
-                }
-            } else {
-                ++acc_state;
-                if (nstate != state) {
-                    const int lo = since_state > burn ? since_state : burn;
-                    if (s > lo) atomicAdd(g_state_counts + state, (unsigned long long)(s - lo));
-                    since_state = s;
-                    state = nstate;
-                }
-                Cst = Cn;
-#pragma unroll
-                for (int q = 0; q < R; ++q) { csse[q] = keep[q].x; cref[q] = keep[q].y; }
-                if (HG) { W0 = nW0; W1 = num[QG]; W2 = nW2; }
+        if (HG) {
+            const bool gm_changed = acc_n && dgm != 0;
+            if (gm_changed) {
+                const int lo = since_gm > burn ? since_gm : burn;
+                if (s > lo) atomicAdd(g_param_counts + T.r[QG].hist_gamma + igm, (unsigned long long)(s - lo));
+                // slide the window and fetch the new edge
+                const double edge = __ldg(gsse + (size_t)state * GH + (gmn + 2 + dgm));
+                if (dgm > 0) { W0 = W1; W1 = W2; W2 = edge; }
+                else { W2 = W1; W1 = W0; W0 = edge; }
+                since_gm = s;
+                igm = gmn;
+                pshift = dgm;
             }
+            W0 = acc_s ? nW0 : W0;
+            W1 = acc_s ? num[QG] : W1;
+            W2 = acc_s ? nW2 : W2;
+        }
+        if (acc_s && nstate != state) {
+            const int lo = since_state > burn ? since_state : burn;
+            if (s > lo) atomicAdd(g_state_counts + state, (unsigned long long)(s - lo));
+            since_state = s;
+            state = nstate;
         }
 
         if (s >= burn) {
@@ -275,8 +246,23 @@ mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 next_snap = ns < s_end ? (int)ns : -1;
             }
         }
-        w = wn;
+    };
+
+    // ---- software pipeline: prologue, then two steps per iteration (ping-pong buffers) ------
+    Philox4 wa = philox4x32_10((uint32_t)ctr0, (uint32_t)(ctr0 >> 32), ch_lo, ch_hi, seed_lo, seed_hi), wb;
+    Prefetch<R> pa, pb;
+    pa.C = 0.0; pb.C = 0.0;
+#pragma unroll
+    for (int q = 0; q < R; ++q) { pa.rec[q] = make_double2(0.0, 0.0); pb.rec[q] = make_double2(0.0, 0.0); }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { pa.W[k] = 0.0; pb.W[k] = 0.0; }
+    if (!(wa.w0 < thresh)) prefetch(pa, (int)(((uint64_t)wa.w1 * (uint32_t)S) >> 32));
+    int s = 0;
+    for (; s + 1 < s_end; s += 2) {
+        step(s, wa, wb, pa, pb);
+        step(s + 1, wb, wa, pb, pa);
     }
+    if (s < s_end) step(s, wa, wb, pa, pb);
 
     // ---- flush run-length counters, persist the chain ----------------------------------
     {

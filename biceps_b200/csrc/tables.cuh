@@ -35,6 +35,10 @@ struct SamplerTables {
     // then {ref_g, 0} of the gamma restraint (ref = +0.0 where there is no reference potential;
     // t - 0.0 == t bit for bit).
     const double* rec;      // [S][rec_stride]
+    // gamma restraint's sse rows with a 2-element periodic halo on each side, so that the +-2
+    // window around any gamma index is contiguous and needs no wrap arithmetic:
+    // gsse_halo[i][k] = sse[i][(k - 2) mod G], k in [0, G+4)
+    const double* gsse_halo;
     int rec_stride;         // 2 * R doubles
     int canonical;          // 1 if the specialised kernel applies
 };

@@ -124,6 +124,13 @@ class ChainBlock(object):
         A.check(self._lib.bcp_chains_fetch(self._c, C.byref(s)), "bcp_chains_fetch")
         return o
 
+    def set_state(self, state=None, indices=None, energy=None):
+        """Overwrite chain state / indices [n][P] / energy (None = keep): checkpoint restart."""
+        st = None if state is None else A.i32(state)
+        ix = None if indices is None else A.i32(np.asarray(indices).reshape(self.n_chains, self.tables.n_params))
+        en = None if energy is None else A.f64(energy)
+        A.check(self._lib.bcp_chains_set_state(self._c, A.i32ptr(st), A.i32ptr(ix), A.dptr(en)), "bcp_chains_set_state")
+
     def last_kernel_ms(self):
         ms = C.c_float(); nl = C.c_int32()
         A.check(self._lib.bcp_chains_last_kernel_ms(self._c, C.byref(ms), C.byref(nl)), "bcp_chains_last_kernel_ms")

@@ -158,6 +158,11 @@ int bcp_sample(bcp_chains* c, const bcp_sample_cfg* cfg, bcp_sample_out* out);
 int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void* stream);
 int bcp_chains_sync(bcp_chains* c);
 int bcp_chains_fetch(bcp_chains* c, bcp_sample_out* out);
+/* Overwrite the chains' state / parameter indices [n_chains][P] / energy (host arrays, NULL =
+ * keep).  Restart from a checkpoint taken with bcp_chains_fetch, or reproduce what the reference
+ * does when sample() is called a second time (indices jump back to int(len/2) while state and E
+ * persist, PosteriorSampler.py:271-278, 294). */
+int bcp_chains_set_state(bcp_chains* c, const int32_t* state, const int32_t* indices, const double* energy);
 /* device views of the cumulative histograms, for an NCCL all-reduce by the caller */
 int bcp_chains_device_hist(bcp_chains* c, int64_t** d_state_counts, int64_t** d_param_counts);
 /* elapsed device time (ms, CUDA events on the launch stream) of the last sample launch */

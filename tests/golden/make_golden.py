@@ -90,6 +90,9 @@ def make_cineromycin(biceps):
                 for k, v in ob.items():
                     tab_out["obs%d_%s" % (q, k)] = v
             tab_out["obs1_betas"] = np.array(s.ensemble[0][1].betas, np.float64)
+            for q in range(2):
+                tab_out["obs%d_restraint_index" % q] = np.array(
+                    [r["restraint_index"] for r in s.ensemble[0][q].restraints], np.int64)
         with H.quiet():
             s.sample(nsteps, burn=burn)
         pack_traj(tag, s, traj_out)

@@ -1,0 +1,162 @@
+"""GPU: the reference-facing Python API (Ensemble -> PosteriorSampler.sample -> process_results ->
+Analysis) end to end, on per-state DataFrame files written from the golden cineromycin observables."""
+import os
+import pickle
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from helpers import cineromycin_tables, stack_lambdas
+
+pytestmark = pytest.mark.gpu
+
+OPTS = [dict(ref="uniform", sigma=(0.05, 20.0, 1.02)),
+        dict(ref="exponential", sigma=(0.05, 5.0, 1.02), gamma=(0.2, 5.0, 1.02))]
+
+
+@pytest.fixture(scope="module")
+def dataset(tmp_path_factory):
+    """<i>.J and <i>.noe pandas pickles, the reference's per-state input format (Restraint.py:411-416, 521-525)."""
+    z, t0, t1 = cineromycin_tables()
+    d = tmp_path_factory.mktemp("J_NOE")
+    S = z["obs0_model"].shape[0]
+    for i in range(S):
+        J = z["obs0_model"].shape[1]
+        pd.DataFrame({"atom_index1": range(J), "atom_index2": range(J), "atom_index3": range(J), "atom_index4": range(J),
+                      "exp": z["obs0_exp"], "model": z["obs0_model"][i],
+                      "restraint_index": z["obs0_restraint_index"]}).to_pickle(str(d / ("%d.J" % i)))
+        pd.DataFrame({"exp": z["obs1_exp"], "model": z["obs1_model"][i],
+                      "restraint_index": z["obs1_restraint_index"]}).to_pickle(str(d / ("%d.noe" % i)))
+    return str(d), z, t0, t1
+
+
+def test_ensemble_tables_match_the_reference(dataset):
+    import biceps_b200 as biceps
+    d, z, t0, t1 = dataset
+    input_data = biceps.toolbox.sort_data(d)
+    assert len(input_data) == 100 and input_data[3][0].endswith("3.J") and input_data[3][1].endswith("3.noe")
+    ens = biceps.Ensemble(1.0, z["raw_energies"])
+    ens.initialize_restraints(input_data, OPTS)
+    lst = ens.to_list()
+    assert len(lst) == 100 and type(lst[0][1]).__name__ == "Restraint_noe"
+    for k in range(2):
+        want = t1["restraints"][k]
+        got = np.array([s[k].sse for s in lst])
+        assert np.max(np.abs(got - want["sse"]) / np.abs(want["sse"])) < 1e-11          # tolerance stated: 1e-6
+        assert lst[0][k].Ndof == want["ndof"]
+        assert np.array_equal(lst[0][k].allowed_sigma, want["sigma"])
+    r = lst[5][1].restraints
+    assert len(r) == 33 and set(r[0]) == {"exp", "model", "restraint_index", "weight"}
+    assert r[7]["model"] == z["obs1_model"][5, 7] and r[7]["weight"] == z["obs1_weight"][7]
+    s = biceps.PosteriorSampler(ens, seed=3)
+    assert abs(s.logZ - t1["logZ"]) < 1e-12
+    assert np.max(np.abs(lst[0][1].betas - z["obs1_betas"]) / z["obs1_betas"]) < 1e-12
+    assert s.traj.rest_type == ["sigma_J", "sigma_noe", "gamma_noe"]
+    assert s.traj.trajectory_headers[-1] == "para_index = [151, 116, 81]"
+    # energies through the API == oracle on the reference's own tables, to the table tolerance
+    from oracle import sampler_oracle as O
+    e = s.neglogP([7], [[1.0], [1.0, 1.0]], [[150], [100, 80]])
+    assert abs(e - O.neglogP(t1, 7, [150, 100, 80])) < 1e-9 * abs(e)
+
+
+def test_option_errors_like_the_reference(dataset):
+    import biceps_b200 as biceps
+    d, z, t0, t1 = dataset
+    input_data = biceps.toolbox.sort_data(d)
+    with pytest.raises(ValueError):
+        biceps.Ensemble(1, z["raw_energies"])                                   # lambda must be float
+    with pytest.raises(ValueError):
+        biceps.Ensemble(1.0, np.arange(100))                                     # energies must be float
+    ens = biceps.Ensemble(1.0, z["raw_energies"])
+    with pytest.raises(TypeError):
+        ens.initialize_restraints(input_data, [dict(ref="uniform", sgima=(1, 2, 1.1)), dict()])
+    ens = biceps.Ensemble(1.0, z["raw_energies"])
+    ens.initialize_restraints(input_data, [dict(ref="uniform"), dict(ref="exp")])
+    with pytest.raises(ValueError):
+        biceps.PosteriorSampler(ens)                                             # 'exp' is rejected (:57-59)
+    with pytest.raises(ValueError):
+        biceps.Analysis("/nonexistent", nstates=0)
+
+
+def test_full_workflow_matches_oracle_and_mbar(dataset, tmp_path):
+    import biceps_b200 as biceps
+    from oracle import cbind, mbar_oracle as M
+    d, z, t0, t1 = dataset
+    input_data = biceps.toolbox.sort_data(d)
+    out = str(tmp_path)
+    samplers = []
+    for lam in (0.0, 1.0):
+        ens = biceps.Ensemble(lam, z["raw_energies"])
+        ens.initialize_restraints(input_data, OPTS)
+        s = biceps.PosteriorSampler(ens, seed=77)
+        s.sample(20000, burn=1000)
+        s.traj.process_results(os.path.join(out, "traj_lambda%2.2f.npz" % lam))
+        samplers.append(s)
+        # the same chain from the oracle, on the tables the API built
+        o = cbind.sample(s.tables, 1, 77, 20000, burn=1000, traj_every=100, record_state_trace=True)
+        tr = s.traj.trajectory
+        assert len(tr) == 200 and tr[1][0] == 100
+        assert [t[3][0] for t in tr] == list(o["traj_state"][:, 0])
+        assert [float(t[1]) for t in tr] == list(o["traj_energy"][:, 0])
+        assert [int(t[2]) for t in tr] == list(o["traj_accept"][:, 0])
+        assert [list(np.concatenate(t[4])) for t in tr] == [list(x) for x in o["traj_indices"][:, :, 0]]
+        assert s.traj.state_trace == list(o["state_trace"][:, 0])
+        assert np.array_equal(s.traj.state_counts, 1.0 + o["state_counts"][0])
+        assert np.array_equal(np.concatenate(s.traj.sampled_parameters), o["param_counts"][0].astype(float))
+        assert s.accepted == o["accepted"][0] and s.total == 21000
+        assert np.allclose(s.traj.sep_accept[0], o["sep_accepted"][0] / 21000 * 100.)
+        assert s.traj.traces[5] == [s.traj.allowed_parameters[p][tr[5][4][r][j]] for p, (r, j) in enumerate([(0, 0), (1, 0), (1, 1)])]
+    # files: npz dict schema + sampler pickle (PosteriorSampler.py:444-470)
+    npz = np.load(os.path.join(out, "traj_lambda1.00.npz"), allow_pickle=True)["arr_0"].item()
+    assert sorted(npz) == sorted(['rest_type', 'trajectory_headers', 'trajectory', 'sep_accept', 'allowed_parameters',
+                                  'sampled_parameters', 'model', 'ref', 'traces', 'state_trace'])
+    assert len(npz["model"][1]) == 33 and len(npz["model"][1][0]) == 100 and npz["ref"][0] == ['Nan']
+    with open(os.path.join(out, "traj_lambda1.00.pkl"), "rb") as f:
+        assert pickle.load(f).lam == 1.0
+    A = biceps.Analysis(out, nstates=100, precheck=True)
+    assert A.K == 2 and A.lam == [0.0, 1.0] and list(A.N_k) == [200, 200]
+    # oracle analysis on the same trajectories and tables
+    tabs = [dict(s.tables, energy=s.tables["energy"][0], logZ=float(s.tables["logZ"][0])) for s in samplers]
+    trajs = [dict(E=np.array([t[1] for t in s.traj.trajectory]), state=np.array([t[3][0] for t in s.traj.trajectory]),
+                  indices=np.array([np.concatenate(t[4]) for t in s.traj.trajectory])) for s in samplers]
+    want = M.analysis(tabs, trajs, 100)
+    assert np.array_equal(A.u_kln, want["u_kln"])
+    assert np.allclose(A.f_df, want["f_df"], atol=1e-9)
+    ok = ~np.isnan(want["P_dP"])
+    assert np.array_equal(np.isnan(A.P_dP), ~ok) and np.allclose(A.P_dP[ok], want["P_dP"][ok], rtol=1e-7, atol=1e-13)
+    assert np.allclose(np.loadtxt(os.path.join(out, "BS.dat")), A.f_df)
+    assert abs(A.P_dP[:, :2].sum(axis=0) - 1.0).max() < 1e-9
+
+
+def test_many_chains_and_second_sample_call(dataset):
+    import biceps_b200 as biceps
+    d, z, t0, t1 = dataset
+    ens = biceps.Ensemble(1.0, z["raw_energies"])
+    ens.initialize_restraints(biceps.toolbox.sort_data(d), OPTS)
+    s = biceps.PosteriorSampler(ens, nchains=512, seed=5)
+    s.sample(5000, burn=500)
+    assert s.traj.state_counts.sum() == 100 + 512 * 5000
+    assert s.traj.chains["energy"].shape == (50, 512)
+    pops = s.traj.state_counts / s.traj.state_counts.sum()
+    s2 = biceps.PosteriorSampler(ens, nchains=512, seed=6)
+    s2.sample(5000, burn=500)
+    p2 = s2.traj.state_counts / s2.traj.state_counts.sum()
+    assert float(np.sum(pops * np.log(pops / p2))) < 1e-3            # KL between independent runs
+    # second call on the same sampler: counters persist, indices restart (reference quirk)
+    s1 = biceps.PosteriorSampler(ens, seed=9)
+    s1.sample(1000)
+    s1.sample(500)
+    assert s1.total == 1500 and len(s1.traj.trajectory) == 15 and len(s1.traj.sep_accept) == 4
+
+
+def test_from_arrays_bulk_constructor(dataset):
+    import biceps_b200 as biceps
+    d, z, t0, t1 = dataset
+    ens = biceps.Ensemble.from_arrays(1.0, z["raw_energies"], [
+        dict(cls="J", model=z["obs0_model"], exp=z["obs0_exp"], restraint_index=list(z["obs0_restraint_index"]), options=OPTS[0]),
+        dict(cls="noe", model=z["obs1_model"], exp=z["obs1_exp"], restraint_index=list(z["obs1_restraint_index"]), options=OPTS[1])])
+    s = biceps.PosteriorSampler(ens, seed=3)
+    for k in range(2):
+        assert np.max(np.abs(s.tables["restraints"][k]["sse"] - t1["restraints"][k]["sse"]) / t1["restraints"][k]["sse"]) < 1e-11
+    assert np.max(np.abs(s.tables["restraints"][1]["refsum"] - t1["restraints"][1]["refsum"])) < 1e-10
