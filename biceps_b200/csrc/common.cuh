@@ -42,6 +42,7 @@ struct DeviceGuard {
         cudaGetDevice(&prev);
         if (prev != dev) cudaSetDevice(dev);
         else prev = -1;
+        (void)cudaGetLastError();   // a stale error of another library must not be blamed on our launches
     }
     ~DeviceGuard() {
         if (prev >= 0) cudaSetDevice(prev);

@@ -268,6 +268,7 @@ using namespace bcp;
 // ---------------------------------------------------------------------------------------
 struct bcp_handle {
     int device = 0;
+    int refs = 1;            // the owner + one per live bcp_chains (destruction order is free)
     SamplerTables T{};
     std::vector<void*> allocs;
     int32_t rest_index[2 * MAXR];
@@ -404,6 +405,7 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
 
 extern "C" void bcp_destroy(bcp_handle* h) {
     if (!h) return;
+    if (--h->refs > 0) return;      // chains still alive: the last bcp_chains_destroy frees the tables
     DeviceGuard guard(h->device);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
@@ -445,6 +447,7 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
     }
     bcp_chains* c = new bcp_chains();
     c->h = h;
+    ++h->refs;
     c->n_groups = n_groups;
     ChainBuffers& C = c->C;
     C.n_chains = n; C.seed = cfg->seed; C.chain_id0 = cfg->chain_id0;
@@ -496,7 +499,9 @@ extern "C" void bcp_chains_destroy(bcp_chains* c) {
     cudaFree(c->d_trace);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    bcp_handle* h = c->h;
     delete c;
+    bcp_destroy(h);                 // drops this block's reference
 }
 
 template <int R>
@@ -558,8 +563,16 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
     A.traj_idx = c->d_traj_idx; A.state_trace = n_trace ? c->d_trace : nullptr;
     const long long total = cfg->n_steps + cfg->burn;
     // the specialised kernel covers the canonical layout; BCP_FORCE_GENERIC=1 selects the generic one
+    // kernel choice: BCP_KERNEL=generic|fast|coop overrides (BCP_FORCE_GENERIC=1 == generic)
     const char* force = getenv("BCP_FORCE_GENERIC");
-    const bool fast = T.canonical && !(force && force[0] == '1');
+    const char* kern = getenv("BCP_KERNEL");
+    // auto: few chains -> the step time is one warp's instruction stream: spread a chain over L lanes
+    // (coop); many chains -> issue-bound: one thread per chain (fast).  Crossover measured on B200
+    // (profiles/README.md): coop wins at 4096 chains (5.6e9 vs 4.2e9 steps/s), fast from ~16k up.
+    int which = !T.canonical ? 0 : (n <= 8192 ? 2 : 1);              // 0 generic, 1 fast, 2 coop
+    if (kern && T.canonical) which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : 2);
+    if (force && force[0] == '1') which = 0;
+    const bool fast = which == 1;
     int fgrid = grid, fblock = block;
     if (fast) {
         int w = (int)((n_warps + sms - 1) / sms);
@@ -573,7 +586,8 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
         A.s_begin = s0;
         A.s_end = s0 + kMaxStepsPerLaunch < total ? s0 + kMaxStepsPerLaunch : total;
         cudaError_t e;
-        if (fast) e = launch_mcmc_fast(T, c->C, A, fgrid, fblock, st);
+        if (which == 2) e = launch_mcmc_coop(T, c->C, A, st, sms);
+        else if (fast) e = launch_mcmc_fast(T, c->C, A, fgrid, fblock, st);
         else switch (T.R) {
             case 1: e = launch_mcmc<1>(T, c->C, A, grid, block, st); break;
             case 2: e = launch_mcmc<2>(T, c->C, A, grid, block, st); break;

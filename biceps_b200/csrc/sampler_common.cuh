@@ -79,4 +79,7 @@ __device__ __forceinline__ void stage_sigma_table(double* s_sig, const double* g
 cudaError_t launch_mcmc_fast(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, int grid, int block,
                              cudaStream_t st);
 
+// cooperative kernel (sampler_coop.cu): L lanes per chain; canonical layout only
+cudaError_t launch_mcmc_coop(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms);
+
 }  // namespace bcp

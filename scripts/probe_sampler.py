@@ -11,7 +11,7 @@ K = 8
 t = time.time()
 ens = synthetic.make_ensemble(cfg, seed=0, n_lambda=K)
 tabs = PO.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], exact_pow=False)
-print("tables built in %.1fs" % (time.time() - t), flush=True)
+print("tables built in %.1fs kernel=%s" % (time.time() - t, os.environ.get("BCP_KERNEL", "auto")), flush=True)
 T = engine.DeviceTables(tabs, device=0)
 for n_chains, n_steps in [(4096, 20000), (4096 * 8, 10000), (148 * 2048, 4000), (148 * 2048 * 2, 2000)]:
     lam = (np.arange(n_chains) % K).astype(np.int32)

@@ -134,13 +134,13 @@ def test_many_chains_and_second_sample_call(dataset):
     d, z, t0, t1 = dataset
     ens = biceps.Ensemble(1.0, z["raw_energies"])
     ens.initialize_restraints(biceps.toolbox.sort_data(d), OPTS)
-    s = biceps.PosteriorSampler(ens, nchains=512, seed=5)
-    s.sample(5000, burn=500)
-    assert s.traj.state_counts.sum() == 100 + 512 * 5000
-    assert s.traj.chains["energy"].shape == (50, 512)
+    s = biceps.PosteriorSampler(ens, nchains=4096, seed=5)
+    s.sample(20000, burn=2000)
+    assert s.traj.state_counts.sum() == 100 + 4096 * 20000
+    assert s.traj.chains["energy"].shape == (200, 4096)
     pops = s.traj.state_counts / s.traj.state_counts.sum()
-    s2 = biceps.PosteriorSampler(ens, nchains=512, seed=6)
-    s2.sample(5000, burn=500)
+    s2 = biceps.PosteriorSampler(ens, nchains=4096, seed=6)
+    s2.sample(20000, burn=2000)
     p2 = s2.traj.state_counts / s2.traj.state_counts.sum()
     assert float(np.sum(pops * np.log(pops / p2))) < 1e-3            # KL between independent runs
     # second call on the same sampler: counters persist, indices restart (reference quirk)
