@@ -129,7 +129,7 @@ def run_reference(args, rank, world):
     tabs = PO.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], exact_pow=False)
     cores = os.cpu_count() or 1
     n_chains = CHAINS_PER_GPU * args.gpus
-    lam = (np.arange(n_chains) % N_LAMBDA).astype(np.int32)
+    lam = (np.arange(n_chains) // (CHAINS_PER_GPU // N_LAMBDA) % N_LAMBDA).astype(np.int32)
     # size a step to ~3 s of CPU work from a short calibration
     t0 = time.perf_counter()
     cbind.sample(tabs, n_chains, SEED, 50, chain_lambda=lam, n_threads=cores)
@@ -161,18 +161,10 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------
-class _DevArray(object):
-    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
-
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
-                                         "version": 2, "strides": None}
-
-
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from biceps_b200 import _cabi, engine, precompute, synthetic
+    from biceps_b200 import _cabi, distributed, engine, precompute, synthetic
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
@@ -186,17 +178,15 @@ def run_ours(args, rank, world, local_rank):
     packed = _cabi.PackedTables(tabs)
     T = engine.DeviceTables(packed, device=dev)
     n = CHAINS_PER_GPU
-    lam = (np.arange(n) % N_LAMBDA).astype(np.int32)
+    lam = (np.arange(n) // (n // N_LAMBDA)).astype(np.int32)       # 512 consecutive chains per lambda
     blk = T.chains(n, SEED, chain_id0=rank * n, chain_lambda=lam)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     hist_views = None
     if world > 1:
-        p_sc, p_pc = blk.device_hist_ptrs()
-        sc = torch.as_tensor(_DevArray(p_sc, (N_LAMBDA, T.n_states), "<i8"), device="cuda")
-        pc = torch.as_tensor(_DevArray(p_pc, (N_LAMBDA, T.param_bins), "<i8"), device="cuda")
-        hist_views = (sc, pc)
+        hist_views = distributed.device_histograms(blk)
+        sc, pc = hist_views
         red = (torch.empty_like(sc), torch.empty_like(pc))
 
     def one_step():

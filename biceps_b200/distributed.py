@@ -1,0 +1,123 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): chains shard across ranks with no
+data-path collective; the only exchanges are the all-reduce of the per-group histograms after a
+sampling pass and, for MBAR over sample shards, the all-reduce of K + K*K partial sums per
+iteration.  Works with backend "nccl" (device tensors, NVLink) and, for the
+CPU tests of this host logic, "gloo"."""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi as A
+
+
+def shard(n_total, rank, world):
+    """Contiguous block of chains for `rank`: (first global chain id, number of chains)."""
+    base, rem = divmod(int(n_total), int(world))
+    n = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, n
+
+
+class _DevArray(object):
+    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def device_histograms(block):
+    """torch int64 views [n_groups][S] and [n_groups][param_bins] of a ChainBlock's device histograms."""
+    import torch
+    p_sc, p_pc = block.device_hist_ptrs()
+    T = block.tables
+    sc = torch.as_tensor(_DevArray(p_sc, (block.n_groups, T.n_states), "<i8"), device="cuda:%d" % T.device)
+    pc = torch.as_tensor(_DevArray(p_pc, (block.n_groups, T.param_bins), "<i8"), device="cuda:%d" % T.device)
+    return sc, pc
+
+
+def all_reduce_histograms(state_counts, param_counts, group=None):
+    """Sum the per-group histograms over all ranks (torch tensors on the backend's device, or numpy
+    arrays which are reduced through CPU tensors).  Returns the reduced arrays, same type as given."""
+    import torch
+    import torch.distributed as dist
+    out = []
+    for a in (state_counts, param_counts):
+        if isinstance(a, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64).copy())
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            out.append(t.numpy())
+        else:
+            t = a.clone()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            out.append(t)
+    return out[0], out[1]
+
+
+def mbar_solve(pass_fn, N_k, tol=1e-12, max_iter=10000, group=None, reduce=True):
+    """MBAR free energies from sample shards.
+
+    pass_fn(f, want_hess) -> (s[K], M[K][K] or None): the LOCAL sums  s_k = sum_n W_nk and
+    M_kl = sum_n W_nk W_nl  over this rank's samples (on the GPU: bcp_mbar_pass_dev).  The sums are
+    all-reduced, and every rank takes the same Newton / self-consistent step, so f stays replicated.
+    Same iteration as csrc/mbar.cu:mbar_solve.  Returns (f, theta = W^T W, iterations)."""
+    N_k = np.asarray(N_k, dtype=np.float64)
+    K = N_k.shape[0]
+
+    def global_pass(f):
+        s, M = pass_fn(f, True)
+        buf = np.concatenate([np.asarray(s, np.float64).ravel(), np.asarray(M, np.float64).ravel()])
+        if reduce:
+            import torch
+            import torch.distributed as dist
+            t = torch.from_numpy(buf)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            buf = t.numpy()
+        return buf[:K].copy(), buf[K:].reshape(K, K).copy()
+
+    def gnorm(s):
+        return float(np.sqrt(np.sum((N_k * (s - 1.0)) ** 2)))
+
+    f = np.zeros(K)
+    s, M = global_pass(f)
+    for it in range(max_iter):
+        g0 = gnorm(s)
+        step = None
+        if it >= 2 and K > 1:
+            H = np.diag(N_k * s) - (N_k[:, None] * N_k[None, :]) * M
+            try:
+                d = np.linalg.solve(H[1:, 1:], -(N_k * (s - 1.0))[1:])
+                cand = f.copy()
+                cand[1:] += d
+                s2, M2 = global_pass(cand)
+                if gnorm(s2) < g0 or gnorm(s2) == 0.0:
+                    step = (cand, s2, M2)
+            except np.linalg.LinAlgError:
+                pass
+        if step is None:
+            cand = np.where(N_k > 0, f - np.log(s), f)
+            cand = cand - cand[0]
+            s2, M2 = global_pass(cand)
+            step = (cand, s2, M2)
+        fn, s, M = step
+        done = np.max(np.abs(fn - f)) <= tol * max(1.0, float(np.max(np.abs(fn))))
+        f = fn
+        if done:
+            return f, M, it + 1
+    raise RuntimeError("biceps_b200.distributed.mbar_solve: no convergence in %d iterations" % max_iter)
+
+
+def gpu_pass_fn(d_u_kn_ptr, n_local, K, N_k_global, device=0, stream=None):
+    """pass_fn for mbar_solve over a device-resident shard u_kn[K][n_local] (raw device pointer)."""
+    lib = A.lib()
+    N_k = np.ascontiguousarray(N_k_global, dtype=np.int64)
+
+    def fn(f, want_hess):
+        f = A.f64(f)
+        s = np.zeros(K)
+        M = np.zeros((K, K))
+        A.check(lib.bcp_mbar_pass_dev(C.c_void_p(int(d_u_kn_ptr)), int(n_local), int(K), A.i64ptr(N_k), A.dptr(f),
+                                      int(bool(want_hess)), int(device), C.c_void_p(stream or 0), A.dptr(s), A.dptr(M)),
+                "bcp_mbar_pass_dev")
+        return s, M
+    return fn
