@@ -160,6 +160,8 @@ _SIGS = {
     "bcp_abi_version": (C.c_int, []),
     "bcp_last_error": (C.c_char_p, []),
     "bcp_kernel_launches": (C.c_uint64, []),
+    "bcp_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "bcp_host_free": (None, [C.c_void_p]),
     "bcp_create": (C.c_int, [C.POINTER(bcp_tables), C.c_int, C.POINTER(C.c_void_p)]),
     "bcp_destroy": (None, [C.c_void_p]),
     "bcp_n_params": (C.c_int, [C.c_void_p]),
@@ -211,6 +213,37 @@ def lib():
         declare(L, _SIGS)
         _lib = L
     return _lib
+
+
+class PinnedPool(object):
+    """numpy arrays backed by page-locked host memory (bcp_host_alloc); freed with the pool."""
+
+    def __init__(self):
+        self._ptrs = []
+
+    def zeros(self, shape, dtype):
+        shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        n = int(np.prod(shape)) if shape else 1
+        nbytes = max(1, n * np.dtype(dtype).itemsize)
+        p = lib().bcp_host_alloc(nbytes)
+        if not p:
+            raise MemoryError("bcp_host_alloc(%d) failed" % nbytes)
+        self._ptrs.append(p)
+        buf = (C.c_uint8 * nbytes).from_address(p)
+        a = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+        a[...] = 0
+        return a
+
+    def close(self):
+        for p in self._ptrs:
+            lib().bcp_host_free(p)
+        self._ptrs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def check(rc, what=""):

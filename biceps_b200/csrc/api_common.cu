@@ -18,3 +18,19 @@ void set_error(const char* fmt, ...) {
 extern "C" int bcp_abi_version(void) { return BCP_ABI_VERSION; }
 extern "C" const char* bcp_last_error(void) { return bcp::g_err; }
 extern "C" uint64_t bcp_kernel_launches(void) { return bcp::g_kernel_launches.load(); }
+
+// pinned (page-locked) host buffers for the callers' input / output arrays: host<->device copies of
+// pageable memory run at a fraction of the PCIe rate
+extern "C" void* bcp_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 1;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        bcp::set_error("bcp_host_alloc: cudaHostAlloc(%zu) failed", bytes);
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void bcp_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}

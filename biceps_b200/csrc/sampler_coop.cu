@@ -40,6 +40,15 @@ struct CoopPrefetch {
     double W[5];
 };
 
+// Metropolis uniform (2k+1) * 2^-53 from the 52-bit integer k = (w2 << 20) | (w3 >> 12), built with
+// bit operations and two exact fp64 adds: 1.k - 1.0 = k * 2^-52, + 2^-53  (== philox.cuh:u2_from_words)
+__device__ __forceinline__ double u2_fast(uint32_t w2, uint32_t w3) {
+    const uint32_t hi = 0x3FF00000u | (w2 >> 12);
+    const uint32_t lo = (w2 << 20) | (w3 >> 12);
+    const double one_k = __hiloint2double((int)hi, (int)lo);
+    return __dadd_rn(__dadd_rn(one_k, -1.0), 1.1102230246251565e-16);
+}
+
 template <int L, bool HG>
 __global__ void __launch_bounds__(128)
 mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
@@ -66,13 +75,14 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     const unsigned long long chain_id = C.chain_id0 + (unsigned long long)c;
     const double* __restrict__ energy = T.energy + (size_t)lam * T.S;
     const double logZ = T.logZ[lam];
-    const double2* __restrict__ rec2 = reinterpret_cast<const double2*>(T.rec);
+    const double2* __restrict__ rec2 = reinterpret_cast<const double2*>(T.rec) + qr;    // this lane's slice
     const double* __restrict__ gsse = HG ? T.gsse_halo : nullptr;
     const int G = HG ? T.r[R - 1].n_gamma : 1;
     const int GH = G + 4;
     unsigned long long* g_state_counts = C.state_counts + (size_t)grp * T.S;
-    unsigned long long* g_param_counts = C.param_counts + (size_t)grp * T.HB;
-    const int S = T.S;
+    unsigned long long* g_sigma_hist = C.param_counts + (size_t)grp * T.HB + T.r[qr].hist_sigma;
+    unsigned long long* g_gamma_hist = C.param_counts + (size_t)grp * T.HB + (HG ? T.r[R - 1].hist_gamma : 0);
+    const uint32_t S = (uint32_t)T.S;
     const uint32_t thresh = T.nuis_thresh;
     const int s_end = (int)(A.s_end - A.s_begin);
     const long long burn_l = A.burn - A.s_begin;
@@ -81,11 +91,10 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     const uint32_t seed_lo = (uint32_t)C.seed, seed_hi = (uint32_t)(C.seed >> 32);
     const uint32_t ch_lo = (uint32_t)chain_id, ch_hi = (uint32_t)(chain_id >> 32);
 
-    // this lane's restraint (runtime index into the kernel parameter)
+    // this lane's restraint: sigma vectors in shared memory, normalisation constant
     const int nsig = T.r[qr].n_sigma;
-    const int sig_off = T.r[qr].sig_off;
-    const int hist_sigma = T.r[qr].hist_sigma;
-    const int hist_gamma = HG ? T.r[R - 1].hist_gamma : 0;
+    const double* __restrict__ s_a = s_sig + T.r[qr].sig_off;      // Ndof ln(sigma)
+    const double* __restrict__ s_d = s_a + nsig;                   // 2 sigma^2
     const double cnorm = T.r[qr].cnorm;
 
     // ---- chain state (state, E, Cst replicated in every lane of the group) ----------------
@@ -95,7 +104,7 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     int jg = 0;                                              // gamma index (gamma lane only)
     double csse, cref, W0 = 0.0, W1 = 0.0, W2 = 0.0;
     {
-        const double2 v = rec2[(size_t)state * R + qr];
+        const double2 v = rec2[(size_t)state * R];
         csse = v.x;
         cref = v.y;
     }
@@ -117,9 +126,10 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         next_snap = ns < s_end ? (int)ns : -1;
     }
 
-    auto prefetch = [&](CoopPrefetch& p, int i2) {
+    auto prefetch = [&](CoopPrefetch& p, uint32_t n1) {
+        const uint32_t i2 = __umulhi(n1, S);
         p.C = __ldg(energy + i2);
-        p.rec = __ldg(rec2 + (size_t)i2 * R + qr);
+        p.rec = __ldg(rec2 + (size_t)i2 * R);
         if (HG && glane) {
             const double* row = gsse + (size_t)i2 * GH + jg;            // halo: [jg-2 .. jg+2]
 #pragma unroll
@@ -127,36 +137,43 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         }
     };
 
-    // one step; (w0..w3) = this step's Philox block, (n0, n1) = first two words of the next step's
-    auto step = [&](const int s, const uint32_t w0, const uint32_t w1, const uint32_t w2, const uint32_t w3,
-                    const uint32_t n0, const uint32_t n1, const bool has_next, const CoopPrefetch& use,
+    // one step; w = this step's Philox block, nw = the next step's (prefetch decision)
+    auto step = [&](const int s, const Philox4& w, const Philox4& nw, const bool has_next, const CoopPrefetch& use,
                     CoopPrefetch& fill) {
-        const bool nuis = w0 < thresh;
-        const uint64_t pr = (uint64_t)w1 * (uint32_t)(nuis ? R : S);
+        const bool nuis = w.w0 < thresh;
+        const uint64_t pr = (uint64_t)w.w1 * (nuis ? (uint32_t)R : S);
         const int hi = (int)(pr >> 32);
-        const int nstate = nuis ? state : hi;
         const bool mine = nuis && hi == q;
         const uint64_t z1 = (uint64_t)(uint32_t)pr * 3u;
         const int dsg = (int)(z1 >> 32) - 1;
-        const uint64_t z2 = (uint64_t)(uint32_t)z1 * 3u;
-        const bool pg = HG && mine && glane;
-        const int dgm = pg ? (int)(z2 >> 32) - 1 : 0;
-
-        const int sgn = mine ? cwrap1(sg + dsg, nsig) : sg;
-        const double av = s_sig[sig_off + sgn];
-        const double dv = s_sig[sig_off + nsig + sgn];
-        double num = nuis ? csse : use.rec.x;
-        double nW0 = 0.0, nW2 = 0.0;
-        if (HG && glane) {
-            num = nuis ? csel3(dgm, W0, W1, W2) : csel3(pshift, use.W[1], use.W[2], use.W[3]);
-            nW0 = csel3(pshift, use.W[0], use.W[1], use.W[2]);
-            nW2 = csel3(pshift, use.W[2], use.W[3], use.W[4]);
+        int dgm = 0;
+        if (HG) {
+            const uint64_t z2 = (uint64_t)(uint32_t)z1 * 3u;
+            dgm = (mine && glane) ? (int)(z2 >> 32) - 1 : 0;
         }
+        const int sgn = mine ? cwrap1(sg + dsg, nsig) : sg;
+        const double av = s_a[sgn];
+        const double dv = s_d[sgn];
+        double num = nuis ? csse : use.rec.x;
         const double ref = nuis ? cref : use.rec.y;
         const double Cn = nuis ? Cst : __dadd_rn(use.C, logZ);
-        const double2 keep = use.rec;
+        const double keep_x = use.rec.x, keep_y = use.rec.y;
+        double nW0 = 0.0, nW2 = 0.0;
+        if (HG) {
+            // the window prefetched for a state move is centred on the gamma index of one step ago;
+            // only if that step moved gamma (pshift != 0, rare) does the centre have to be re-selected
+            double wc = use.W[2];
+            nW0 = use.W[1];
+            nW2 = use.W[3];
+            if (__any_sync(0xffffffffu, pshift != 0)) {
+                wc = csel3(pshift, use.W[1], use.W[2], use.W[3]);
+                nW0 = csel3(pshift, use.W[0], use.W[1], use.W[2]);
+                nW2 = csel3(pshift, use.W[2], use.W[3], use.W[4]);
+            }
+            if (glane) num = nuis ? csel3(dgm, W0, W1, W2) : wc;
+        }
 
-        if (has_next && !(n0 < thresh)) prefetch(fill, (int)(((uint64_t)n1 * (uint32_t)S) >> 32));
+        if (has_next && !(nw.w0 < thresh)) prefetch(fill, nw.w1);
 
         double t = __dadd_rn(av, __ddiv_rn(num, dv));
         t = __dadd_rn(t, cnorm);
@@ -168,51 +185,47 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
             const double tk = shfl_d<L>(t, k);
             if (k < R) En = __dadd_rn(En, tk);
         }
-        const double u2 = u2_from_words(w2, w3);
-        const bool acc = (En < E) || metropolis_accept(__dsub_rn(E, En), u2);
+        const bool acc = (En < E) || metropolis_accept(__dsub_rn(E, En), u2_fast(w.w2, w.w3));
 
-        const bool acc_n = acc && nuis, acc_s = acc && !nuis;
         E = acc ? En : E;
         acc_total += acc ? 1u : 0u;
-        acc_state += acc_s ? 1u : 0u;
         acc_own += (acc && mine) ? 1u : 0u;
-        if (acc && mine && sgn != sg) {
-            if (owner) {
-                const int lo = since_sg > burn ? since_sg : burn;
-                if (s > lo) atomicAdd(g_param_counts + hist_sigma + sg, (unsigned long long)(s - lo));
-            }
-            since_sg = s;
-            sg = sgn;
-        }
         pshift = 0;
-        if (HG && acc && pg && dgm != 0) {
-            if (live) {
-                const int lo = since_gm > burn ? since_gm : burn;
-                if (s > lo) atomicAdd(g_param_counts + hist_gamma + jg, (unsigned long long)(s - lo));
-            }
-            const int gmn = cwrap1(jg + dgm, G);
-            const double edge = __ldg(gsse + (size_t)state * GH + (gmn + 2 + dgm));
-            if (dgm > 0) { W0 = W1; W1 = W2; W2 = edge; }
-            else { W2 = W1; W1 = W0; W0 = edge; }
-            since_gm = s;
-            jg = gmn;
-            pshift = dgm;
-        }
-        if (acc_s) {
-            csse = keep.x;
-            cref = keep.y;
-            Cst = Cn;
-            if (HG && glane) { W0 = nW0; W1 = num; W2 = nW2; }
-            if (nstate != state) {
-                if (lead) {
-                    const int lo = since_state > burn ? since_state : burn;
-                    if (s > lo) atomicAdd(g_state_counts + state, (unsigned long long)(s - lo));
+        if (acc) {
+            if (nuis) {
+                if (mine) {
+                    if (sgn != sg) {
+                        const int lo = since_sg > burn ? since_sg : burn;
+                        if (owner && s > lo) atomicAdd(g_sigma_hist + sg, (unsigned long long)(s - lo));
+                        since_sg = s;
+                        sg = sgn;
+                    }
+                    if (HG && dgm != 0) {
+                        const int lo = since_gm > burn ? since_gm : burn;
+                        if (live && s > lo) atomicAdd(g_gamma_hist + jg, (unsigned long long)(s - lo));
+                        const int gmn = cwrap1(jg + dgm, G);
+                        const double edge = __ldg(gsse + (size_t)state * GH + (gmn + 2 + dgm));
+                        if (dgm > 0) { W0 = W1; W1 = W2; W2 = edge; }
+                        else { W2 = W1; W1 = W0; W0 = edge; }
+                        since_gm = s;
+                        jg = gmn;
+                        pshift = dgm;
+                    }
                 }
-                since_state = s;
-                state = nstate;
+            } else {
+                ++acc_state;
+                csse = keep_x;
+                cref = keep_y;
+                Cst = Cn;
+                if (HG && glane) { W0 = nW0; W1 = num; W2 = nW2; }
+                if (hi != state) {
+                    const int lo = since_state > burn ? since_state : burn;
+                    if (lead && s > lo) atomicAdd(g_state_counts + state, (unsigned long long)(s - lo));
+                    since_state = s;
+                    state = hi;
+                }
             }
         }
-        (void)acc_n;
 
         if (s >= burn) {
             if (A.state_trace && lead) A.state_trace[(size_t)(A.s_begin + s - A.burn) * n + c] = state;
@@ -232,35 +245,35 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         }
     };
 
-    // ---- batches of L steps: lane j generates the Philox block of step s0 + j ---------------
+    // ---- batches of L steps: lane j generates the Philox block of step s0 + j; two steps per
+    //      loop iteration so the prefetch buffers ping-pong without register copies --------------
     auto block_of = [&](int s) {
         const unsigned long long ctr = ctr0 + (unsigned long long)s;
         return philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), ch_lo, ch_hi, seed_lo, seed_hi);
     };
+    auto bcast = [&](const Philox4& b, int j) {
+        Philox4 r;
+        r.w0 = shfl_u<L>(b.w0, j); r.w1 = shfl_u<L>(b.w1, j);
+        r.w2 = shfl_u<L>(b.w2, j); r.w3 = shfl_u<L>(b.w3, j);
+        return r;
+    };
     Philox4 wb = block_of(q);
-    CoopPrefetch bufs[2];
+    CoopPrefetch pa, pb;
+    pa.C = 0.0; pa.rec = make_double2(0.0, 0.0); pb.C = 0.0; pb.rec = make_double2(0.0, 0.0);
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        bufs[b].C = 0.0; bufs[b].rec = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) bufs[b].W[k] = 0.0;
-    }
-    {
-        const uint32_t f0 = shfl_u<L>(wb.w0, 0), f1 = shfl_u<L>(wb.w1, 0);
-        if (!(f0 < thresh)) prefetch(bufs[0], (int)(((uint64_t)f1 * (uint32_t)S) >> 32));
-    }
+    for (int k = 0; k < 5; ++k) { pa.W[k] = 0.0; pb.W[k] = 0.0; }
+    Philox4 wa = bcast(wb, 0);                                   // block of step 0
+    if (!(wa.w0 < thresh)) prefetch(pa, wa.w1);
     for (int s0 = 0; s0 < s_end; s0 += L) {
         const Philox4 wnext = block_of(s0 + L + q);
-#pragma unroll
-        for (int j = 0; j < L; ++j) {
+        for (int j = 0; j < L; j += 2) {                         // L is even
             const int s = s0 + j;
-            if (s < s_end) {                                        // uniform
-                const uint32_t w0 = shfl_u<L>(wb.w0, j), w1 = shfl_u<L>(wb.w1, j);
-                const uint32_t w2 = shfl_u<L>(wb.w2, j), w3 = shfl_u<L>(wb.w3, j);
-                const uint32_t n0 = (j + 1 < L) ? shfl_u<L>(wb.w0, j + 1) : shfl_u<L>(wnext.w0, 0);
-                const uint32_t n1 = (j + 1 < L) ? shfl_u<L>(wb.w1, j + 1) : shfl_u<L>(wnext.w1, 0);
-                step(s, w0, w1, w2, w3, n0, n1, s + 1 < s_end, bufs[j & 1], bufs[(j + 1) & 1]);
-            }
+            if (s >= s_end) break;                               // uniform
+            const Philox4 w1 = bcast(wb, j + 1);
+            step(s, wa, w1, s + 1 < s_end, pa, pb);
+            if (s + 1 >= s_end) break;
+            wa = (j + 2 < L) ? bcast(wb, j + 2) : bcast(wnext, 0);
+            step(s + 1, w1, wa, s + 2 < s_end, pb, pa);
         }
         wb = wnext;
     }
@@ -276,13 +289,13 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     }
     if (owner) {
         const int lo = since_sg > burn ? since_sg : burn;
-        if (s_end > lo) atomicAdd(g_param_counts + hist_sigma + sg, (unsigned long long)(s_end - lo));
+        if (s_end > lo) atomicAdd(g_sigma_hist + sg, (unsigned long long)(s_end - lo));
         C.isg[(size_t)q * n + c] = sg;
         C.sep[(size_t)q * n + c] += acc_own;
     }
     if (HG && glane && live) {
         const int lo = since_gm > burn ? since_gm : burn;
-        if (s_end > lo) atomicAdd(g_param_counts + hist_gamma + jg, (unsigned long long)(s_end - lo));
+        if (s_end > lo) atomicAdd(g_gamma_hist + jg, (unsigned long long)(s_end - lo));
         C.igm[(size_t)(R - 1) * n + c] = jg;
     }
 }

@@ -12,17 +12,19 @@ def n_snapshots(n_steps, traj_every):
     return (n_steps + traj_every - 1) // traj_every if traj_every > 0 else 0
 
 
-def alloc_outputs(n_chains, n_groups, S, P, HB, n_steps, traj_every, record_state_trace):
-    """numpy buffers + the bcp_sample_out struct pointing at them."""
+def alloc_outputs(n_chains, n_groups, S, P, HB, n_steps, traj_every, record_state_trace, pool=None):
+    """numpy buffers + the bcp_sample_out struct pointing at them.  With a PinnedPool the big
+    trajectory buffers are page-locked (the returned dict keeps the pool alive under "_pool")."""
     ns = n_snapshots(n_steps, traj_every)
+    big = pool.zeros if pool is not None else np.zeros
     o = dict(state_counts=np.zeros((n_groups, S), np.int64), param_counts=np.zeros((n_groups, HB), np.int64),
              accepted=np.zeros(n_chains, np.int64), total=np.zeros(n_chains, np.int64),
              sep_accepted=np.zeros((n_chains, P + 1), np.int64),
              state=np.zeros(n_chains, np.int32), indices=np.zeros((n_chains, P), np.int32),
              energy=np.zeros(n_chains, np.float64),
-             traj_energy=np.zeros((ns, n_chains), np.float64), traj_state=np.zeros((ns, n_chains), np.int32),
-             traj_accept=np.zeros((ns, n_chains), np.uint8), traj_indices=np.zeros((ns, P, n_chains), np.int32),
-             state_trace=np.zeros((n_steps if record_state_trace else 0, n_chains), np.int32))
+             traj_energy=big((ns, n_chains), np.float64), traj_state=big((ns, n_chains), np.int32),
+             traj_accept=big((ns, n_chains), np.uint8), traj_indices=big((ns, P, n_chains), np.int32),
+             state_trace=big((n_steps if record_state_trace else 0, n_chains), np.int32))
     s = A.bcp_sample_out(A.i64ptr(o["state_counts"]), A.i64ptr(o["param_counts"]), A.i64ptr(o["accepted"]),
                          A.i64ptr(o["total"]), A.i64ptr(o["sep_accepted"]), A.i32ptr(o["state"]),
                          A.i32ptr(o["indices"]), A.dptr(o["energy"]),
@@ -99,11 +101,15 @@ class ChainBlock(object):
         A.check(self._lib.bcp_chains_create(tables._h, C.byref(cfg), C.byref(c)), "bcp_chains_create")
         self._c = c
 
-    def sample(self, n_steps, burn=0, traj_every=0, record_state_trace=False):
-        """Synchronous bcp_sample with host output buffers; returns a dict of numpy arrays."""
+    def sample(self, n_steps, burn=0, traj_every=0, record_state_trace=False, pinned=False):
+        """Synchronous bcp_sample with host output buffers; returns a dict of numpy arrays
+        (pinned=True: page-locked trajectory buffers, owned by the returned dict's "_pool")."""
         T = self.tables
+        pool = A.PinnedPool() if pinned else None
         o, s = alloc_outputs(self.n_chains, self.n_groups, T.n_states, T.n_params, T.param_bins, int(n_steps),
-                             int(traj_every), bool(record_state_trace))
+                             int(traj_every), bool(record_state_trace), pool)
+        if pool is not None:
+            o["_pool"] = pool
         cfg = A.bcp_sample_cfg(int(n_steps), int(burn), int(traj_every), int(bool(record_state_trace)), 0)
         A.check(self._lib.bcp_sample(self._c, C.byref(cfg), C.byref(s)), "bcp_sample")
         return o

@@ -17,6 +17,7 @@
 #ifndef BICEPS_B200_H
 #define BICEPS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -87,6 +88,11 @@ int bcp_abi_version(void);
 const char* bcp_last_error(void);
 /* number of CUDA kernels this library has launched in this process (bench gpu_launches) */
 uint64_t bcp_kernel_launches(void);
+
+/* Page-locked host memory for the caller's tables and output buffers (optional; any host pointer
+ * works, pinned ones copy at the full PCIe rate).  NULL on failure. */
+void* bcp_host_alloc(size_t bytes);
+void bcp_host_free(void* p);
 
 /* Upload the flattened ensemble (host pointers) to `device`.  Replaces the table reads of
  * PosteriorSampler.neglogP (PosteriorSampler.py:233-248). */
