@@ -17,6 +17,7 @@
 // reduced deterministically (per-CTA partials, fixed-order finish).
 #include "common.cuh"
 #include "tables.cuh"
+#include "sampler_common.cuh"
 
 #include <math.h>
 #include <algorithm>
@@ -355,7 +356,8 @@ extern "C" int bcp_ukn(bcp_handle* h, int64_t n, const int32_t* state, const int
         STEP(dev_alloc(&d_state, (size_t)n)); STEP(cudaMemcpy(d_state, state, n * 4, cudaMemcpyHostToDevice));
         STEP(dev_alloc(&d_idx, (size_t)n * T.P)); STEP(cudaMemcpy(d_idx, indices, (size_t)n * T.P * 4, cudaMemcpyHostToDevice));
         STEP(dev_alloc(&d_u, (size_t)n * T.K));
-        ukn_kernel<<<(unsigned)((n + 255) / 256), 256>>>(T, n, d_state, d_idx, d_u);
+        if (T.pf.q >= 0) { STEP(launch_energy_pf(T, n, nullptr, d_state, d_idx, d_u, 1, nullptr)); }
+        else ukn_kernel<<<(unsigned)((n + 255) / 256), 256>>>(T, n, d_state, d_idx, d_u);
         BCP_LAUNCHED(1);
         STEP(cudaGetLastError());
         STEP(cudaMemcpy(u_kn, d_u, (size_t)n * T.K * 8, cudaMemcpyDeviceToHost));
@@ -371,7 +373,8 @@ extern "C" int bcp_ukn_dev(bcp_handle* h, int64_t n, const int32_t* d_state, con
     if (n <= 0) return BCP_OK;
     const SamplerTables& T = handle_tables(h);
     DeviceGuard guard(handle_device(h));
-    ukn_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, n, d_state, d_indices, d_u_kn);
+    if (T.pf.q >= 0) BCP_CUDA(launch_energy_pf(T, n, nullptr, d_state, d_indices, d_u_kn, 1, (cudaStream_t)stream));
+    else ukn_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, n, d_state, d_indices, d_u_kn);
     BCP_LAUNCHED(1);
     BCP_CUDA(cudaGetLastError());
     return BCP_OK;

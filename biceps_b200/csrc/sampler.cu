@@ -218,7 +218,7 @@ mcmc_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ Cha
 // initial state of every chain from the Philox block at step 2^64-1 (oracle/philox.py)
 __global__ void init_chains_kernel(long long n, unsigned long long seed, unsigned long long chain_id0,
                                    int S, int R, const int* init_state, int* state, double* E,
-                                   int* isg, int* igm, SamplerTables T) {
+                                   int* isg, int* igm, int* ipf, SamplerTables T) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     int s0;
@@ -234,6 +234,8 @@ __global__ void init_chains_kernel(long long n, unsigned long long seed, unsigne
         isg[(size_t)q * n + c] = T.r[q].n_sigma / 2;
         igm[(size_t)q * n + c] = T.r[q].has_gamma ? T.r[q].n_gamma / 2 : 0;
     }
+    if (ipf)
+        for (int k = 0; k < BCP_PF_NGRID; ++k) ipf[(size_t)k * n + c] = T.pf.n[k] / 2;
 }
 
 // -log P of explicit configurations (PosteriorSampler.neglogP, PosteriorSampler.py:233-248)
@@ -271,8 +273,9 @@ struct bcp_handle {
     int refs = 1;            // the owner + one per live bcp_chains (destruction order is free)
     SamplerTables T{};
     std::vector<void*> allocs;
-    int32_t rest_index[2 * MAXR];
-    int32_t grid_len[2 * MAXR];
+    int32_t rest_index[BCP_MAX_PARAMS];
+    int32_t grid_len[BCP_MAX_PARAMS];
+    int32_t p_slot[BCP_MAX_PARAMS];   // where parameter p lives: 0 sigma, 1 gamma, 2 + k PF grid k
 };
 
 struct bcp_chains {
@@ -324,6 +327,7 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
     SamplerTables& T = h->T;
     T.R = t->n_restraints; T.S = t->n_states; T.K = t->n_lambda;
     T.nuis_thresh = (uint32_t)(((uint64_t)T.R << 32) / (uint64_t)(T.R + 1));
+    T.pf.q = -1;
     int rc = BCP_OK;
     auto fail = [&](int code) { bcp_destroy(h); return code; };
 
@@ -332,14 +336,21 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
     int P = 0, HB = 0;
     for (int q = 0; q < T.R; ++q) {
         const bcp_restraint& r = t->restraints[q];
-        if (r.kind == BCP_KIND_PFGRID) {
-            set_error("bcp_create: restraint %d: BCP_KIND_PFGRID is not supported by this build", q);
-            return fail(BCP_ERR_INVALID);
-        }
-        if (!(r.kind == BCP_KIND_SCALAR || r.kind == BCP_KIND_GAMMA) || r.n_sigma <= 0 || !r.nlsig ||
-            !r.two_sig2 || !r.sse || (r.kind == BCP_KIND_GAMMA && r.n_gamma <= 0)) {
+        const bool is_pf = r.kind == BCP_KIND_PFGRID;
+        if (!(r.kind == BCP_KIND_SCALAR || r.kind == BCP_KIND_GAMMA || is_pf) || r.n_sigma <= 0 || !r.nlsig ||
+            !r.two_sig2 || (!is_pf && !r.sse) || (r.kind == BCP_KIND_GAMMA && r.n_gamma <= 0)) {
             set_error("bcp_create: restraint %d: bad kind/size/pointer", q);
             return fail(BCP_ERR_INVALID);
+        }
+        if (is_pf) {
+            bool ok = T.pf.q < 0 && r.pf_n_obs > 0 && r.pf_grid && r.pf_Nc && r.pf_Nh && r.pf_exp && r.pf_weight &&
+                      (r.pf_ref_kind == 0 || r.pf_ref_kind == 1) && P + 1 + BCP_PF_NGRID <= BCP_MAX_PARAMS;
+            for (int k = 0; k < BCP_PF_NGRID; ++k) ok = ok && r.pf_n[k] > 0;
+            if (!ok) {
+                set_error("bcp_create: restraint %d: bad PFGRID description (one PFGRID restraint per ensemble, "
+                          "all six grids non-empty, ref uniform or exponential)", q);
+                return fail(BCP_ERR_INVALID);
+            }
         }
         RestraintDev& rd = T.r[q];
         rd.n_sigma = r.n_sigma;
@@ -349,11 +360,31 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
         sig.insert(sig.end(), r.nlsig, r.nlsig + r.n_sigma);
         sig.insert(sig.end(), r.two_sig2, r.two_sig2 + r.n_sigma);
         rd.hist_sigma = HB; HB += rd.n_sigma;
-        h->rest_index[P] = q; h->grid_len[P] = rd.n_sigma; ++P;
+        h->rest_index[P] = q; h->grid_len[P] = rd.n_sigma; h->p_slot[P] = 0; ++P;
         rd.has_gamma = r.kind == BCP_KIND_GAMMA;
         if (rd.has_gamma) {
             rd.hist_gamma = HB; HB += rd.n_gamma;
-            h->rest_index[P] = q; h->grid_len[P] = rd.n_gamma; ++P;
+            h->rest_index[P] = q; h->grid_len[P] = rd.n_gamma; h->p_slot[P] = 1; ++P;
+        }
+        if (is_pf) {
+            PfDev& pf = T.pf;
+            pf.q = q; pf.J = r.pf_n_obs; pf.ref_kind = r.pf_ref_kind;
+            size_t ngrid = 0, cells = 1;
+            for (int k = 0; k < BCP_PF_NGRID; ++k) {
+                pf.n[k] = r.pf_n[k]; pf.hist[k] = HB; HB += r.pf_n[k];
+                h->rest_index[P] = q; h->grid_len[P] = r.pf_n[k]; h->p_slot[P] = 2 + k; ++P;
+                ngrid += r.pf_n[k]; cells *= (size_t)r.pf_n[k];
+            }
+            const size_t J = (size_t)pf.J;
+            if ((rc = upload(h, r.pf_grid, ngrid, &pf.grid)) != BCP_OK) return fail(rc);
+            if ((rc = upload(h, r.pf_Nc, (size_t)T.S * pf.n[3] * pf.n[5] * J, &pf.Nc)) != BCP_OK) return fail(rc);
+            if ((rc = upload(h, r.pf_Nh, (size_t)T.S * pf.n[4] * pf.n[5] * J, &pf.Nh)) != BCP_OK) return fail(rc);
+            if ((rc = upload(h, r.pf_exp, J, &pf.exp)) != BCP_OK) return fail(rc);
+            if ((rc = upload(h, r.pf_weight, J, &pf.weight)) != BCP_OK) return fail(rc);
+            pf.prior = nullptr;
+            if (r.pf_prior && (rc = upload(h, r.pf_prior, cells, &pf.prior)) != BCP_OK) return fail(rc);
+            rd.sse = nullptr; rd.refsum = nullptr;
+            continue;
         }
         if ((rc = upload(h, r.sse, (size_t)T.S * rd.n_gamma, &rd.sse)) != BCP_OK) return fail(rc);
         rd.refsum = nullptr;
@@ -371,7 +402,7 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
     }
     if ((rc = upload(h, sig.data(), sig.size(), &T.sig_tab)) != BCP_OK) return fail(rc);
     // packed per-state records for the specialised kernel (tables.cuh)
-    T.canonical = 1;
+    T.canonical = T.pf.q < 0 ? 1 : 0;
     for (int q = 0; q < T.R; ++q)
         if (T.r[q].has_gamma && (q != T.R - 1 || T.r[q].n_gamma < 2)) T.canonical = 0;
     T.rec_stride = 2 * T.R;
@@ -381,7 +412,7 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
         for (int q = 0; q < T.R; ++q) {
             const bcp_restraint& r = t->restraints[q];
             for (int i = 0; i < T.S; ++i) {
-                rec[(size_t)i * T.rec_stride + 2 * q] = T.r[q].has_gamma ? 0.0 : r.sse[i];
+                rec[(size_t)i * T.rec_stride + 2 * q] = (T.r[q].has_gamma || !r.sse) ? 0.0 : r.sse[i];
                 rec[(size_t)i * T.rec_stride + 2 * q + 1] = r.has_ref ? r.refsum[i] : 0.0;
             }
         }
@@ -461,6 +492,8 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
     TRY_CUDA(dev_alloc(&C.state, n));
     TRY_CUDA(dev_alloc(&C.isg, (size_t)T.R * n));
     TRY_CUDA(dev_alloc(&C.igm, (size_t)T.R * n));
+    C.ipf = nullptr;
+    if (T.pf.q >= 0) TRY_CUDA(dev_alloc(&C.ipf, (size_t)BCP_PF_NGRID * n));
     TRY_CUDA(dev_alloc(&C.E, n));
     TRY_CUDA(dev_alloc(&C.accepted, n));
     TRY_CUDA(dev_alloc(&C.sep, (size_t)(T.R + 1) * n));
@@ -477,7 +510,7 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
     }
     const int tpb = 256;
     init_chains_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb>>>(n, C.seed, C.chain_id0, T.S, T.R, d_init,
-                                                                 C.state, C.E, C.isg, C.igm, T);
+                                                                 C.state, C.E, C.isg, C.igm, C.ipf, T);
     BCP_LAUNCHED(1);
     TRY_CUDA(cudaGetLastError());
     TRY_CUDA(cudaDeviceSynchronize());
@@ -493,7 +526,7 @@ extern "C" void bcp_chains_destroy(bcp_chains* c) {
     if (!c) return;
     DeviceGuard guard(c->h->device);
     cudaFree(c->d_lam); cudaFree(c->d_group);
-    cudaFree(c->C.state); cudaFree(c->C.isg); cudaFree(c->C.igm); cudaFree(c->C.E);
+    cudaFree(c->C.state); cudaFree(c->C.isg); cudaFree(c->C.igm); cudaFree(c->C.ipf); cudaFree(c->C.E);
     cudaFree(c->C.accepted); cudaFree(c->C.sep); cudaFree(c->C.state_counts); cudaFree(c->C.param_counts);
     cudaFree(c->d_traj_E); cudaFree(c->d_traj_state); cudaFree(c->d_traj_accept); cudaFree(c->d_traj_idx);
     cudaFree(c->d_trace);
@@ -586,7 +619,8 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
         A.s_begin = s0;
         A.s_end = s0 + kMaxStepsPerLaunch < total ? s0 + kMaxStepsPerLaunch : total;
         cudaError_t e;
-        if (which == 2) e = launch_mcmc_coop(T, c->C, A, st, sms);
+        if (T.pf.q >= 0) e = launch_mcmc_pf(T, c->C, A, st);
+        else if (which == 2) e = launch_mcmc_coop(T, c->C, A, st, sms);
         else if (fast) e = launch_mcmc_fast(T, c->C, A, fgrid, fblock, st);
         else switch (T.R) {
             case 1: e = launch_mcmc<1>(T, c->C, A, grid, block, st); break;
@@ -649,23 +683,22 @@ extern "C" int bcp_chains_fetch(bcp_chains* c, bcp_sample_out* o) {
     D2H(o->state, c->C.state, n * 4);
     D2H(o->energy, c->C.E, n * 8);
     if (o->indices || o->sep_accepted) {
-        std::vector<int> isg((size_t)T.R * n), igm((size_t)T.R * n);
+        std::vector<int> isg((size_t)T.R * n), igm((size_t)T.R * n), ipf;
         std::vector<unsigned long long> sep((size_t)(T.R + 1) * n);
         BCP_CUDA(cudaMemcpy(isg.data(), c->C.isg, isg.size() * 4, cudaMemcpyDeviceToHost));
         BCP_CUDA(cudaMemcpy(igm.data(), c->C.igm, igm.size() * 4, cudaMemcpyDeviceToHost));
+        if (c->C.ipf) {
+            ipf.resize((size_t)BCP_PF_NGRID * n);
+            BCP_CUDA(cudaMemcpy(ipf.data(), c->C.ipf, ipf.size() * 4, cudaMemcpyDeviceToHost));
+        }
         BCP_CUDA(cudaMemcpy(sep.data(), c->C.sep, sep.size() * 8, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < n; ++i) {
-            int p = 0;
-            for (int q = 0; q < T.R; ++q) {
-                const bool has_gamma = (p + 1 < T.P) && h->rest_index[p + 1] == q;
-                if (o->indices) o->indices[i * T.P + p] = isg[(size_t)q * n + i];
+            for (int p = 0; p < T.P; ++p) {
+                const int q = h->rest_index[p], slot = h->p_slot[p];
+                if (o->indices)
+                    o->indices[i * T.P + p] = slot == 0 ? isg[(size_t)q * n + i]
+                                              : (slot == 1 ? igm[(size_t)q * n + i] : ipf[(size_t)(slot - 2) * n + i]);
                 if (o->sep_accepted) o->sep_accepted[i * (T.P + 1) + p] = (int64_t)sep[(size_t)q * n + i];
-                ++p;
-                if (has_gamma) {
-                    if (o->indices) o->indices[i * T.P + p] = igm[(size_t)q * n + i];
-                    if (o->sep_accepted) o->sep_accepted[i * (T.P + 1) + p] = (int64_t)sep[(size_t)q * n + i];
-                    ++p;
-                }
             }
             if (o->sep_accepted) o->sep_accepted[i * (T.P + 1) + T.P] = (int64_t)sep[(size_t)T.R * n + i];
         }
@@ -698,24 +731,18 @@ extern "C" int bcp_chains_set_state(bcp_chains* c, const int32_t* state, const i
     }
     if (energy) BCP_CUDA(cudaMemcpy(c->C.E, energy, n * 8, cudaMemcpyHostToDevice));
     if (indices) {
-        std::vector<int> isg((size_t)T.R * n), igm((size_t)T.R * n, 0);
-        for (size_t i = 0; i < n; ++i) {
-            int p = 0;
-            for (int q = 0; q < T.R; ++q) {
-                const int sg = indices[i * T.P + p];
-                BCP_REQUIRE(sg >= 0 && sg < h->grid_len[p], "bcp_chains_set_state: indices[%zu][%d] out of range", i, p);
-                isg[(size_t)q * n + i] = sg;
-                ++p;
-                if (T.r[q].has_gamma) {
-                    const int gm = indices[i * T.P + p];
-                    BCP_REQUIRE(gm >= 0 && gm < h->grid_len[p], "bcp_chains_set_state: indices[%zu][%d] out of range", i, p);
-                    igm[(size_t)q * n + i] = gm;
-                    ++p;
-                }
+        std::vector<int> isg((size_t)T.R * n), igm((size_t)T.R * n, 0), ipf((size_t)BCP_PF_NGRID * n, 0);
+        for (size_t i = 0; i < n; ++i)
+            for (int p = 0; p < T.P; ++p) {
+                const int v = indices[i * T.P + p], q = h->rest_index[p], slot = h->p_slot[p];
+                BCP_REQUIRE(v >= 0 && v < h->grid_len[p], "bcp_chains_set_state: indices[%zu][%d] out of range", i, p);
+                if (slot == 0) isg[(size_t)q * n + i] = v;
+                else if (slot == 1) igm[(size_t)q * n + i] = v;
+                else ipf[(size_t)(slot - 2) * n + i] = v;
             }
-        }
         BCP_CUDA(cudaMemcpy(c->C.isg, isg.data(), isg.size() * 4, cudaMemcpyHostToDevice));
         BCP_CUDA(cudaMemcpy(c->C.igm, igm.data(), igm.size() * 4, cudaMemcpyHostToDevice));
+        if (c->C.ipf) BCP_CUDA(cudaMemcpy(c->C.ipf, ipf.data(), ipf.size() * 4, cudaMemcpyHostToDevice));
     }
     return BCP_OK;
 }
@@ -749,7 +776,8 @@ extern "C" int bcp_neglogp(bcp_handle* h, int64_t n, const int32_t* lam, const i
         STEP(dev_alloc(&d_state, (size_t)n)); STEP(cudaMemcpy(d_state, state, n * 4, cudaMemcpyHostToDevice));
         STEP(dev_alloc(&d_idx, (size_t)n * T.P)); STEP(cudaMemcpy(d_idx, indices, (size_t)n * T.P * 4, cudaMemcpyHostToDevice));
         STEP(dev_alloc(&d_out, (size_t)n));
-        neglogp_kernel<<<(unsigned)((n + 255) / 256), 256>>>(T, n, d_lam, d_state, d_idx, d_out);
+        if (T.pf.q >= 0) { STEP(launch_energy_pf(T, n, d_lam, d_state, d_idx, d_out, 0, nullptr)); }
+        else neglogp_kernel<<<(unsigned)((n + 255) / 256), 256>>>(T, n, d_lam, d_state, d_idx, d_out);
         BCP_LAUNCHED(1);
         STEP(cudaGetLastError());
         STEP(cudaMemcpy(energy_out, d_out, n * 8, cudaMemcpyDeviceToHost));

@@ -13,6 +13,7 @@ struct ChainBuffers {
     int* state;             // [n]
     int* isg;               // [R][n]
     int* igm;               // [R][n]
+    int* ipf;               // [6][n]  PF grid indices (ensembles with a PFGRID restraint)
     double* E;              // [n]
     unsigned long long* accepted;     // [n]
     unsigned long long* sep;          // [R+1][n]  (this sample() call)
@@ -81,5 +82,11 @@ cudaError_t launch_mcmc_fast(const SamplerTables& T, const ChainBuffers& C, cons
 
 // cooperative kernel (sampler_coop.cu): L lanes per chain; canonical layout only
 cudaError_t launch_mcmc_coop(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms);
+
+// warp-per-chain kernel for ensembles with a PFGRID restraint (sampler_pf.cu); any layout
+cudaError_t launch_mcmc_pf(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st);
+// -log P of explicit configurations when the ensemble has a PFGRID restraint (warp per configuration)
+cudaError_t launch_energy_pf(const SamplerTables& T, long long N, const int* d_lam, const int* d_state,
+                             const int* d_indices, double* d_out, int all_lambdas, cudaStream_t st);
 
 }  // namespace bcp

@@ -21,6 +21,23 @@ struct RestraintDev {
     int has_gamma;          // Restraint_noe: gamma moves together with sigma
 };
 
+// Restraint_pf on the 6-D nuisance grid (at most one per ensemble): raw <N_c>/<N_h> counts, the term
+// is evaluated on the fly (the dense table would be 11.6 MB per state)
+struct PfDev {
+    const double* grid;     // concatenated grid values beta_c, beta_h, beta_0, xcs, xhs, bs
+    const double* Nc;       // [S][n_xcs][n_bs][J]
+    const double* Nh;       // [S][n_xhs][n_bs][J]
+    const double* exp;      // [J]
+    const double* weight;   // [J]
+    const double* prior;    // [prod n] or nullptr
+    int n[BCP_PF_NGRID];
+    int hist[BCP_PF_NGRID]; // histogram bin offsets of the six grid parameters
+    int J;
+    int ref_kind;           // 0 uniform, 1 exponential
+    int q;                  // restraint index, -1 if the ensemble has none
+    int pad;
+};
+
 struct SamplerTables {
     RestraintDev r[MAXR];
     const double* energy;   // [K][S]
@@ -34,6 +51,7 @@ struct SamplerTables {
     // that a state move touches one or two sectors: {sse_q, ref_q} for every scalar restraint,
     // then {ref_g, 0} of the gamma restraint (ref = +0.0 where there is no reference potential;
     // t - 0.0 == t bit for bit).
+    PfDev pf;
     const double* rec;      // [S][rec_stride]
     // gamma restraint's sse rows with a 2-element periodic halo on each side, so that the +-2
     // window around any gamma index is contiguous and needs no wrap arithmetic:

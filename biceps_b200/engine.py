@@ -12,12 +12,13 @@ def n_snapshots(n_steps, traj_every):
     return (n_steps + traj_every - 1) // traj_every if traj_every > 0 else 0
 
 
-def alloc_outputs(n_chains, n_groups, S, P, HB, n_steps, traj_every, record_state_trace, pool=None):
+def alloc_outputs(n_chains, n_groups, S, P, HB, n_steps, traj_every, record_state_trace, pool=None, reuse=None):
     """numpy buffers + the bcp_sample_out struct pointing at them.  With a PinnedPool the big
-    trajectory buffers are page-locked (the returned dict keeps the pool alive under "_pool")."""
+    trajectory buffers are page-locked (the returned dict keeps the pool alive under "_pool");
+    `reuse` = a dict returned earlier for the same sizes: its buffers are used again."""
     ns = n_snapshots(n_steps, traj_every)
     big = pool.zeros if pool is not None else np.zeros
-    o = dict(state_counts=np.zeros((n_groups, S), np.int64), param_counts=np.zeros((n_groups, HB), np.int64),
+    o = reuse if reuse is not None else dict(state_counts=np.zeros((n_groups, S), np.int64), param_counts=np.zeros((n_groups, HB), np.int64),
              accepted=np.zeros(n_chains, np.int64), total=np.zeros(n_chains, np.int64),
              sep_accepted=np.zeros((n_chains, P + 1), np.int64),
              state=np.zeros(n_chains, np.int32), indices=np.zeros((n_chains, P), np.int32),
@@ -101,13 +102,18 @@ class ChainBlock(object):
         A.check(self._lib.bcp_chains_create(tables._h, C.byref(cfg), C.byref(c)), "bcp_chains_create")
         self._c = c
 
-    def sample(self, n_steps, burn=0, traj_every=0, record_state_trace=False, pinned=False):
+    def sample(self, n_steps, burn=0, traj_every=0, record_state_trace=False, pinned=False, out=None):
         """Synchronous bcp_sample with host output buffers; returns a dict of numpy arrays
-        (pinned=True: page-locked trajectory buffers, owned by the returned dict's "_pool")."""
+        (pinned=True: page-locked trajectory buffers, owned by the returned dict's "_pool";
+        out=<dict of an earlier call with the same sizes>: reuse its buffers)."""
         T = self.tables
-        pool = A.PinnedPool() if pinned else None
+        pool = A.PinnedPool() if (pinned and out is None) else None
+        if out is not None:
+            ns = n_snapshots(int(n_steps), int(traj_every))
+            if out["traj_energy"].shape != (ns, self.n_chains) or out["state_counts"].shape != (self.n_groups, T.n_states):
+                raise ValueError("out= buffers do not match this call's sizes")
         o, s = alloc_outputs(self.n_chains, self.n_groups, T.n_states, T.n_params, T.param_bins, int(n_steps),
-                             int(traj_every), bool(record_state_trace), pool)
+                             int(traj_every), bool(record_state_trace), pool, reuse=out)
         if pool is not None:
             o["_pool"] = pool
         cfg = A.bcp_sample_cfg(int(n_steps), int(burn), int(traj_every), int(bool(record_state_trace)), 0)

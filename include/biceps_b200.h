@@ -43,6 +43,7 @@ typedef enum bcp_status {
 
 #define BCP_MAX_RESTRAINTS 8
 #define BCP_PF_NGRID 6
+#define BCP_MAX_PARAMS 24      /* nuisance parameters over all restraints */
 
 /* One restraint type of the ensemble, flattened over states.
  *   term(i, idx) = ((nlsig[s] + SSE / two_sig2[s]) [+ prior[cell]] + cnorm) [- REF]

@@ -61,7 +61,47 @@ static double orc_exp(double x) {
 
 double orc_bcp_exp(double x) { return orc_exp(x); }
 
-static int n_params_of(const bcp_restraint* r) { return r->kind == BCP_KIND_GAMMA ? 2 : 1; }
+static int n_params_of(const bcp_restraint* r) {
+    return r->kind == BCP_KIND_GAMMA ? 2 : (r->kind == BCP_KIND_PFGRID ? 1 + BCP_PF_NGRID : 1);
+}
+
+/* Restraint_pf on the 6-D nuisance grid, evaluated on the fly from <N_c>, <N_h>
+ * (Restraint.py:742-749 sse, :765-801 model, :843-849 exponential reference, :873-894 term).
+ * The reference sums the residues left to right; here -- and in the CUDA kernel, which splits the
+ * residues over the 32 lanes of a warp -- the order is FIXED as: 32 strided partial sums
+ * (j = l, l+32, ...) followed by an xor-butterfly (16, 8, 4, 2, 1).  The result differs from the
+ * reference-order sum by rounding only (~1e-15 relative; pinned in tests/test_pf_oracle.py). */
+static void pf_eval(const bcp_restraint* r, int n_states, int state, const int* ci, double* sse_out, double* ref_out) {
+    (void)n_states;
+    const int J = r->pf_n_obs;
+    const int nxc = r->pf_n[3], nxh = r->pf_n[4], nb = r->pf_n[5];
+    const double* g = r->pf_grid;
+    const double bc = g[ci[0]], bh = g[r->pf_n[0] + ci[1]], b0 = g[r->pf_n[0] + r->pf_n[1] + ci[2]];
+    const double* Nc = r->pf_Nc + (((size_t)state * nxc + ci[3]) * nb + ci[5]) * J;
+    const double* Nh = r->pf_Nh + (((size_t)state * nxh + ci[4]) * nb + ci[5]) * J;
+    double ps[32], pr[32], qs[32], qr[32];
+    for (int l = 0; l < 32; ++l) { ps[l] = 0.0; pr[l] = 0.0; }
+    for (int j = 0; j < J; ++j) {
+        const int l = j & 31;
+        const double model = (bc * Nc[j] + bh * Nh[j]) + b0;
+        const double err = model - r->pf_exp[j];
+        ps[l] = ps[l] + r->pf_weight[j] * (err * err);
+        const double neg = -1.0 * model;
+        pr[l] = pr[l] + r->pf_weight[j] * (neg > 0.0 ? neg : 0.0);
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        for (int l = 0; l < 32; ++l) { qs[l] = ps[l] + ps[l ^ off]; qr[l] = pr[l] + pr[l ^ off]; }
+        memcpy(ps, qs, sizeof(ps)); memcpy(pr, qr, sizeof(pr));
+    }
+    *sse_out = ps[0];
+    *ref_out = pr[0];
+}
+
+static size_t pf_cell(const bcp_restraint* r, const int* ci) {
+    size_t c = 0;
+    for (int k = 0; k < BCP_PF_NGRID; ++k) c = c * (size_t)r->pf_n[k] + (size_t)ci[k];
+    return c;
+}
 
 /* PosteriorSampler.neglogP (:233-248) + compute_neglogP (Restraint.py:374-383, 583-592) */
 static double neglogp(const bcp_tables* t, int lam, int state, const int* idx) {
@@ -73,6 +113,17 @@ static double neglogp(const bcp_tables* t, int lam, int state, const int* idx) {
         double term = 0;
         const int sg = idx[p];
         term += r->nlsig[sg];
+        if (r->kind == BCP_KIND_PFGRID) {
+            double sse, ref;
+            pf_eval(r, t->n_states, state, idx + p + 1, &sse, &ref);
+            term += sse / r->two_sig2[sg];
+            if (r->pf_prior) term += r->pf_prior[pf_cell(r, idx + p + 1)];
+            term += r->cnorm;
+            if (r->pf_ref_kind == 1) term -= ref;
+            result += term;
+            p += n_params_of(r);
+            continue;
+        }
         if (r->kind == BCP_KIND_GAMMA)
             term += r->sse[(size_t)state * r->n_gamma + idx[p + 1]] / r->two_sig2[sg];
         else
@@ -96,7 +147,7 @@ typedef struct orc_job {
     const int32_t* init_state;
     int64_t n_steps, burn, traj_every;
     int P, HB;
-    int hist_off[2 * BCP_MAX_RESTRAINTS], glen[2 * BCP_MAX_RESTRAINTS], rest_index[2 * BCP_MAX_RESTRAINTS];
+    int hist_off[BCP_MAX_PARAMS], glen[BCP_MAX_PARAMS], rest_index[BCP_MAX_PARAMS];
     /* outputs, same layouts as bcp_sample_out; histograms are per worker then merged */
     int64_t* state_counts; int64_t* param_counts;
     int64_t* accepted; int64_t* sep_accepted;
@@ -119,7 +170,7 @@ static void* worker(void* arg) {
         int64_t* sc = j->state_counts + (size_t)grp * S;
         int64_t* pc = j->param_counts + (size_t)grp * j->HB;
         uint32_t w[4];
-        int state, idx[2 * BCP_MAX_RESTRAINTS], nidx[2 * BCP_MAX_RESTRAINTS];
+        int state, idx[BCP_MAX_PARAMS], nidx[BCP_MAX_PARAMS];
         double E;
         if (j->step0 == 0) {
             if (j->init_state) state = j->init_state[c];
@@ -212,9 +263,14 @@ int orc_sample(const bcp_tables* t, const bcp_chain_cfg* cc, const bcp_sample_cf
     int P = 0, HB = 0;
     for (int q = 0; q < t->n_restraints; ++q) {
         const bcp_restraint* r = &t->restraints[q];
-        if (r->kind != BCP_KIND_SCALAR && r->kind != BCP_KIND_GAMMA) return -1;
+        if (r->kind != BCP_KIND_SCALAR && r->kind != BCP_KIND_GAMMA && r->kind != BCP_KIND_PFGRID) return -1;
         base.rest_index[P] = q; base.glen[P] = r->n_sigma; base.hist_off[P] = HB; HB += r->n_sigma; ++P;
         if (r->kind == BCP_KIND_GAMMA) { base.rest_index[P] = q; base.glen[P] = r->n_gamma; base.hist_off[P] = HB; HB += r->n_gamma; ++P; }
+        if (r->kind == BCP_KIND_PFGRID)
+            for (int k = 0; k < BCP_PF_NGRID; ++k) {
+                if (P >= BCP_MAX_PARAMS) return -1;
+                base.rest_index[P] = q; base.glen[P] = r->pf_n[k]; base.hist_off[P] = HB; HB += r->pf_n[k]; ++P;
+            }
     }
     base.P = P; base.HB = HB;
     int64_t* sc_tmp = NULL; int64_t* pc_tmp = NULL;

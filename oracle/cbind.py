@@ -42,6 +42,9 @@ def param_layout(packed):
         P += 1; HB += r.n_sigma
         if r.kind == A.BCP_KIND_GAMMA:
             P += 1; HB += r.n_gamma
+        if r.kind == A.BCP_KIND_PFGRID:
+            for k in range(A.BCP_PF_NGRID):
+                P += 1; HB += r.pf_n[k]
     return P, HB
 
 

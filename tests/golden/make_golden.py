@@ -15,6 +15,9 @@ Fixtures (all small .npz, committed):
   tutorial_mbar.npz        the reference's stored tutorial results (2 lambdas x 1000 snapshots, tables
                            from its pickled samplers, BS.dat and populations.dat written by its own
                            Analysis with the real pymbar) -- the golden for u_kn + MBAR
+  pf_grid.npz              HDX protection factors on a reduced 6-D nuisance grid, 6 states x 107 residues:
+                           raw <N_c>/<N_h>, dense reference tables (sse, exponential ref, prior) and the
+                           MT-seeded reference trajectory (7 parameters moving together)
   apomyoglobin_tables.npz  13 states, cs_H / cs_Ca / cs_N (gaussian / exponential / uniform refs)
                            and their MT-seeded reference trajectory (exercises Restraint_cs and
                            both reference potentials on three restraints)
@@ -152,8 +155,64 @@ def make_tutorial_mbar(biceps):
     np.savez_compressed(os.path.join(HERE, "tutorial_mbar.npz"), **out)
 
 
+PF_OPTS = dict(ref="exponential", sigma=(0.5, 8.0, 1.2), beta_c=(0.05, 0.15, 0.05), beta_h=(0.0, 0.6, 0.2),
+               beta_0=(-1.0, 0.0, 0.5), xcs=(5.0, 8.5, 0.5), xhs=(2.0, 2.7, 0.1), bs=(15.0, 16.0, 1.0))
+
+
+def make_pf(biceps):
+    """HDX protection factors on the 6-D nuisance grid (Restraint.py:595-894) with a reduced grid and
+    a synthetic prior.  The reference's loader gives every state the LAST listed state's <N_c>/<N_h>
+    (Restraint.py:634-644), so per-state arrays are injected after construction and the models / SSE
+    recomputed with the reference's own methods."""
+    import tempfile
+    import pandas as pd
+    rng = np.random.default_rng(42)
+    S, J = 6, 107
+    tmp = tempfile.mkdtemp(prefix="pf_golden_")
+    xcs = np.arange(5.0, 8.5, 0.5); xhs = np.arange(2.0, 2.7, 0.1); bs = np.arange(15.0, 16.0, 1.0)
+    exp = rng.uniform(0.0, 10.0, J)
+    Nc = np.sort(rng.uniform(0.0, 60.0, (S, len(xcs), len(bs), J)), axis=1)      # increasing in x_c
+    Nh = np.sort(rng.uniform(0.0, 4.0, (S, len(xhs), len(bs), J)), axis=1)
+    for o, xc in enumerate(xcs):
+        for q, b in enumerate(bs):
+            np.save("%s/Nc_x%0.1f_b%d_state%03d.npy" % (tmp, xc, b, 0), Nc[0, o, q])
+    for p_, xh in enumerate(xhs):
+        for q, b in enumerate(bs):
+            np.save("%s/Nh_x%0.1f_b%d_state%03d.npy" % (tmp, xh, b, 0), Nh[0, p_, q])
+    files = []
+    for i in range(S):
+        fn = "%s/%d.pf" % (tmp, i)
+        pd.DataFrame({"atom_index1": np.arange(J), "exp": exp}).to_pickle(fn)
+        files.append([fn])
+    nshape = (2, 3, 2, len(xcs), len(xhs), len(bs))
+    prior = rng.uniform(0.0, 2.0, nshape)
+    np.save(tmp + "/prior.npy", prior)
+    energies = np.linspace(0.0, 2.5, S)
+    opts = dict(PF_OPTS, Ncs_fi=tmp, Nhs_fi=tmp, states=[0], pf_prior=tmp + "/prior.npy")
+    ens = biceps.Ensemble(1.0, energies)
+    ens.initialize_restraints(files, [opts])
+    for i, st in enumerate(ens.to_list()):
+        R = st[0]
+        assert R.sse.shape == nshape
+        R.Ncs, R.Nhs = Nc[i], Nh[i]
+        for j in range(J):
+            R.restraints[j]["model"] = R.compute_PF_multi(R.Ncs[:, :, j], R.Nhs[:, :, j])
+        R.sse = R.compute_sse(R.restraints)
+    np.random.seed(5)
+    s = biceps.PosteriorSampler(ens)
+    out = {"raw_energies": energies, "Nc": Nc, "Nh": Nh, "exp": exp, "weight": np.ones(J)}
+    pack_tables("t_", H.extract_tables(s), out)
+    out["t_r0_prior"] = prior
+    with H.quiet():
+        s.sample(4000, burn=0)
+    pack_traj("t_", s, out)
+    out["t_seed"] = np.int64(5); out["t_nsteps"] = np.int64(4000)
+    np.savez_compressed(os.path.join(HERE, "pf_grid.npz"), **out)
+
+
 if __name__ == "__main__":
     biceps = H.import_reference()
+    make_pf(biceps)
     make_cineromycin(biceps)
     make_apomyoglobin(biceps)
     make_tutorial_mbar(biceps)

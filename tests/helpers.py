@@ -23,6 +23,8 @@ def tables_from_npz(z, prefix):
                   refsum=z[p + "refsum"] if (p + "refsum") in z else None)
         if (p + "log_normal") in z:
             rt["log_normal"] = bool(z[p + "log_normal"])
+        if (p + "prior") in z:
+            rt["prior"] = z[p + "prior"]
         t["restraints"].append(rt)
     return t
 
@@ -49,3 +51,12 @@ def assert_outputs_equal(a, b, keys=None):
             assert np.array_equal(a[k].view(np.int64), b[k].view(np.int64)), "%s differs (bitwise)" % k
         else:
             assert np.array_equal(a[k], b[k]), "%s differs" % k
+
+
+def pf_raw_tables(g, dense):
+    """On-the-fly PF tables (raw <N_c>/<N_h>) matching the dense reference tables of pf_grid.npz."""
+    rt = dense["restraints"][0]
+    raw = dict(kind="pfgrid", name="pf", ref=rt["ref"], ndof=rt["ndof"], sigma=rt["sigma"], nlsig=rt["nlsig"],
+               two_sig2=rt["two_sig2"], cnorm=rt["cnorm"], grids=rt["grids"], prior=rt.get("prior"),
+               pf=dict(Nc=g["Nc"], Nh=g["Nh"], exp=g["exp"], weight=g["weight"]), refsum=None, sse=None)
+    return dict(n_states=dense["n_states"], energy=dense["energy"], logZ=dense["logZ"], restraints=[raw])
