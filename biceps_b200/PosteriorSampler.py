@@ -33,6 +33,13 @@ def build_tables(ensembles, device=0):
             raise ValueError('Please choose a reference potential of the following:\n \
                     {%s,%s,%s}' % ('uniform', 'exponential', 'gaussian'))
         nlsig, two, cnorm = precompute.sigma_vectors(col["ndof"], col["sigma"])
+        if col["kind"] == "pfgrid":
+            if col["ref"] == "gaussian":      # the reference fails here too (PosteriorSampler.py:52 vs :181)
+                raise TypeError("build_gaussian_ref_pf() got an unexpected keyword argument 'use_global_ref_sigma'")
+            tabs["restraints"].append(dict(kind="pfgrid", name="pf", extension=col["extension"], ref=col["ref"],
+                                           ndof=col["ndof"], sigma=col["sigma"], nlsig=nlsig, two_sig2=two, cnorm=cnorm,
+                                           grids=col["grids"], prior=col["prior"], pf=col["pf"], sse=None, refsum=None))
+            continue
         d = dict(kind=col["kind"], name=col["name"], extension=col["extension"], ref=col["ref"], ndof=col["ndof"],
                  sigma=col["sigma"], nlsig=nlsig, two_sig2=two, cnorm=cnorm, sse=col["sse"],
                  grids=[col["gamma"]] if col["kind"] == "gamma" else [], refsum=None)
@@ -237,7 +244,7 @@ class PosteriorSamplingTrajectory(object):
         if filename is None:
             filename = f"traj_lambda{self.lam}.npz"
         for rest_index in range(len(self.ensemble[0])):
-            if not self.model[rest_index]:
+            if not self.model[rest_index] and self.ensemble[0][rest_index]._model is not None:
                 model = np.stack([s[rest_index]._model for s in self.ensemble])     # [S][J]
                 self.model[rest_index] = [list(model[:, n]) for n in range(model.shape[1])]
         for key in ('rest_type', 'trajectory_headers', 'trajectory', 'sep_accept', 'allowed_parameters',

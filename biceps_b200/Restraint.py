@@ -230,10 +230,19 @@ class Restraint_noe(_Grouped):
 
 
 class Restraint_pf(Restraint):
-    """HDX protection factors (Restraint.py:595-894).  Only the `precomputed=True` branch (model
-    ln PF values stored in the data file, one sigma nuisance parameter, Restraint.py:736-741, 881)
-    is on the GPU path in this build; the 6-D (beta_c, beta_h, beta_0, xcs, xhs, bs) grid branch
-    raises NotImplementedError (scope table row a3)."""
+    """HDX protection factors (Restraint.py:595-894).
+
+    precomputed=True : model ln PF values come with the data file, one sigma nuisance parameter
+                       (Restraint.py:736-741, 881) -- a scalar-SSE restraint.
+    precomputed=False: <ln PF> = beta_c <N_c> + beta_h <N_h> + beta_0 on the 6-D nuisance grid
+                       (beta_c, beta_h, beta_0, xcs, xhs, bs), Restraint.py:654-703, 765-801.  The dense
+                       6-D SSE / reference arrays of the reference (11.6 MB per state by default) are
+                       never built: the CUDA sampler evaluates the term from the raw <N_c>/<N_h>
+                       counts (csrc/sampler_pf.cu).
+    <N_c>/<N_h> files: '<Ncs_fi>/Nc_x%0.1f_b%d_state%03d.npy', '<Nhs_fi>/Nh_x...' (Restraint.py:637-644).
+    With `states=[...]` the reference keeps the LAST listed state's arrays for every state
+    (Restraint.py:634-644); that behaviour is reproduced.  `states=None` (not possible in the
+    reference) loads the state whose index is the data file's stem (`<i>.pf`)."""
 
     _ext = ["pf"]
     _columns = ("atom_index1", "exp", "model")
@@ -243,10 +252,57 @@ class Restraint_pf(Restraint):
                        xcs=(5.0, 8.5, 0.5), xhs=(2.0, 2.7, 0.1), bs=(15.0, 16.0, 1.0), extension="pf", weight=1,
                        file_fmt="pickle", states=None, verbose=False):
         self.precomputed = precomputed
-        if not precomputed:
-            raise NotImplementedError("Restraint_pf on the 6-D nuisance grid (precomputed=False) is not part of "
-                                      "this build's GPU path; use precomputed=True")
+        if precomputed:
+            self._ingest(data, energy, extension, weight, file_fmt)
+            return
+        self.kind = "pfgrid"
+        self._columns = ("atom_index1", "exp")
         self._ingest(data, energy, extension, weight, file_fmt)
+        for name, g in (("beta_c", beta_c), ("beta_h", beta_h), ("beta_0", beta_0), ("xcs", xcs), ("xhs", xhs), ("bs", bs)):
+            grid = np.arange(g[0], g[1], g[2])
+            setattr(self, "allowed_" + name, grid)
+            setattr(self, name + "_index", int(len(grid) / 2))
+            setattr(self, name, grid[int(len(grid) / 2)])
+        if states is None:
+            states = [int(__import__("os").path.basename(data).split(".")[0])]
+        st = states[-1]
+        nxc, nxh, nb = len(self.allowed_xcs), len(self.allowed_xhs), len(self.allowed_bs)
+        self.Ncs = np.zeros((nxc, nb, self.n))
+        self.Nhs = np.zeros((nxh, nb, self.n))
+        for o in range(nxc):
+            for q in range(nb):
+                self.Ncs[o, q, :] = np.load('%s/Nc_x%0.1f_b%d_state%03d.npy' % (Ncs_fi, self.allowed_xcs[o], self.allowed_bs[q], st))
+        for p_ in range(nxh):
+            for q in range(nb):
+                self.Nhs[p_, q, :] = np.load('%s/Nh_x%0.1f_b%d_state%03d.npy' % (Nhs_fi, self.allowed_xhs[p_], self.allowed_bs[q], st))
+        self.pf_prior = np.load(pf_prior) if pf_prior is not None else None
+
+    def _pf_grids(self):
+        return [self.allowed_beta_c, self.allowed_beta_h, self.allowed_beta_0, self.allowed_xcs, self.allowed_xhs,
+                self.allowed_bs]
+
+    @property
+    def sse(self):
+        if self.kind == "pfgrid":
+            raise NotImplementedError("the dense 6-D SSE of a PF-grid restraint is never materialised; "
+                                      "energies come from PosteriorSampler.neglogP")
+        return Restraint.sse.fget(self)
+
+    @sse.setter
+    def sse(self, v):
+        self._sse = v
+
+    def _param_names(self):
+        return ["sigma"] if self.kind != "pfgrid" else ["sigma", "c", "h", "0", "xcs", "xhs", "bs"]
+
+    def _param_grids(self):
+        return [self.allowed_sigma] if self.kind != "pfgrid" else [self.allowed_sigma] + self._pf_grids()
+
+    def _param_start(self):
+        if self.kind != "pfgrid":
+            return [self.sigma_index]
+        return [self.sigma_index, self.beta_c_index, self.beta_h_index, self.beta_0_index, self.xcs_index,
+                self.xhs_index, self.bs_index]
 
 
 class Ensemble(object):
@@ -365,8 +421,17 @@ Dictionary keys for {R.__name__} are any of: {possible_args}")
         self.columns = []
         for k, R0 in enumerate(self.ensemble[0]):
             objs = [s[k] for s in self.ensemble]
-            model = np.ascontiguousarray(np.stack([o._model for o in objs]), dtype=np.float64)
             w = R0.weights
+            if R0.kind == "pfgrid":
+                col = dict(kind="pfgrid", name="pf", extension=R0.extension, ref=R0.ref, ndof=R0.Ndof, sigma=R0.allowed_sigma,
+                           grids=R0._pf_grids(), prior=R0.pf_prior, exp=R0._exp, weight=w,
+                           pf=dict(Nc=np.ascontiguousarray(np.stack([o.Ncs for o in objs])),
+                                   Nh=np.ascontiguousarray(np.stack([o.Nhs for o in objs])), exp=R0._exp, weight=w))
+                for o in objs:
+                    o._weights, o.Ndof = w, R0.Ndof
+                self.columns.append(col)
+                continue
+            model = np.ascontiguousarray(np.stack([o._model for o in objs]), dtype=np.float64)
             col = dict(kind=R0.kind, name=type(R0).__name__.split("_")[-1], extension=R0.extension, ref=R0.ref,
                        model=model, exp=R0._exp, weight=w, ndof=R0.Ndof, sigma=R0.allowed_sigma,
                        gamma=getattr(R0, "allowed_gamma", None), log_normal=getattr(R0, "log_normal", False),

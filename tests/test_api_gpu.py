@@ -160,3 +160,43 @@ def test_from_arrays_bulk_constructor(dataset):
     for k in range(2):
         assert np.max(np.abs(s.tables["restraints"][k]["sse"] - t1["restraints"][k]["sse"]) / t1["restraints"][k]["sse"]) < 1e-11
     assert np.max(np.abs(s.tables["restraints"][1]["refsum"] - t1["restraints"][1]["refsum"])) < 1e-10
+
+
+def test_pf_grid_through_the_api(tmp_path):
+    """Restraint_pf(precomputed=False) from per-state <N_c>/<N_h> .npy files; energies and the chain must
+    equal the oracle on the reference-derived golden data."""
+    import biceps_b200 as biceps
+    from helpers import load_npz, tables_from_npz, pf_raw_tables
+    from oracle import cbind
+    g = load_npz("pf_grid.npz")
+    dense = tables_from_npz(g, "t_")
+    raw = pf_raw_tables(g, dense)
+    d = str(tmp_path)
+    S, J = g["Nc"].shape[0], g["Nc"].shape[-1]
+    xcs = np.arange(5.0, 8.5, 0.5); xhs = np.arange(2.0, 2.7, 0.1); bs = np.arange(15.0, 16.0, 1.0)
+    files = []
+    for i in range(S):
+        for o, xc in enumerate(xcs):
+            np.save("%s/Nc_x%0.1f_b%d_state%03d.npy" % (d, xc, bs[0], i), g["Nc"][i, o, 0])
+        for p_, xh in enumerate(xhs):
+            np.save("%s/Nh_x%0.1f_b%d_state%03d.npy" % (d, xh, bs[0], i), g["Nh"][i, p_, 0])
+        pd.DataFrame({"atom_index1": np.arange(J), "exp": g["exp"]}).to_pickle("%s/%d.pf" % (d, i))
+        files.append(["%s/%d.pf" % (d, i)])
+    np.save(d + "/prior.npy", dense["restraints"][0]["prior"])
+    opts = dict(ref="exponential", sigma=(0.5, 8.0, 1.2), beta_c=(0.05, 0.15, 0.05), beta_h=(0.0, 0.6, 0.2),
+                beta_0=(-1.0, 0.0, 0.5), xcs=(5.0, 8.5, 0.5), xhs=(2.0, 2.7, 0.1), bs=(15.0, 16.0, 1.0),
+                Ncs_fi=d, Nhs_fi=d, pf_prior=d + "/prior.npy")
+    ens = biceps.Ensemble(1.0, g["raw_energies"])
+    ens.initialize_restraints(files, [opts])
+    s = biceps.PosteriorSampler(ens, seed=12)
+    assert s.traj.rest_type == ["sigma_pf", "c_pf", "h_pf", "0_pf", "xcs_pf", "xhs_pf", "bs_pf"]
+    assert np.array_equal(s.tables["restraints"][0]["nlsig"], dense["restraints"][0]["nlsig"])
+    s.sample(3000, burn=100)
+    o = cbind.sample(raw, 1, 12, 3000, burn=100, traj_every=100, record_state_trace=True)
+    assert s.traj.state_trace == list(o["state_trace"][:, 0])
+    assert [list(np.concatenate(t[4])) for t in s.traj.trajectory] == [list(x) for x in o["traj_indices"][:, :, 0]]
+    assert [t[1] for t in s.traj.trajectory] == list(o["traj_energy"][:, 0])
+    with pytest.raises(TypeError):
+        e2 = biceps.Ensemble(1.0, g["raw_energies"])
+        e2.initialize_restraints(files, [dict(opts, ref="gaussian")])
+        biceps.PosteriorSampler(e2)
