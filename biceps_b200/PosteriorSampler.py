@@ -77,6 +77,8 @@ class PosteriorSampler(object):
         self.logZ = float(self.tables["logZ"][0])
         # reference-potential parameters back onto the restraint objects (PosteriorSampler.py:102-104, 147-150)
         for k, rt in enumerate(self.tables["restraints"]):
+            if rt["kind"] == "pfgrid":      # its reference term is evaluated on the fly by the sampler
+                continue
             for i, s in enumerate(self.ensemble):
                 R = s[k]
                 if rt["ref"] == "exponential":
@@ -98,7 +100,7 @@ class PosteriorSampler(object):
             if rt["ref"] == "uniform":
                 self.traj.ref[i].append('Nan')
             elif rt["ref"] == "exponential":
-                self.traj.ref[i].append(rt["betas"])
+                self.traj.ref[i].append(rt.get("betas"))
             else:
                 self.traj.ref[i].append(rt["ref_mean"])
                 self.traj.ref[i].append(rt["ref_sigma"])
