@@ -157,7 +157,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -312,10 +312,27 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "mcmc_steps_per_chain": N_MCMC_E2E, "traj_every": 100},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "saturated": saturated}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else any library prints to fd 1 during the
+    run (e.g. NCCL's version banner) has been redirected to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -13,6 +13,20 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+void keep_pool_memory(int device) {
+    static std::atomic<uint64_t> done{0};
+    if (device < 0 || device >= 64) return;
+    const uint64_t bit = 1ull << device;
+    if (done.load(std::memory_order_relaxed) & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    (void)cudaGetLastError();
+    done.fetch_or(bit, std::memory_order_relaxed);
+}
+
 }  // namespace bcp
 
 extern "C" int bcp_abi_version(void) { return BCP_ABI_VERSION; }

@@ -36,12 +36,15 @@ extern std::atomic<uint64_t> g_kernel_launches;
 
 // RAII device-selection guard: every entry point runs on the handle's device and restores
 // the caller's current device afterwards.
+void keep_pool_memory(int device);
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
         cudaGetDevice(&prev);
         if (prev != dev) cudaSetDevice(dev);
         else prev = -1;
+        keep_pool_memory(dev);
         (void)cudaGetLastError();   // a stale error of another library must not be blamed on our launches
     }
     ~DeviceGuard() {
@@ -55,6 +58,10 @@ static inline cudaError_t dev_alloc(T** p, size_t n) {
     if (n == 0) return cudaSuccess;
     return cudaMalloc((void**)p, n * sizeof(T));
 }
+
+// keep the stream-ordered pool's memory across synchronisations (the default release threshold of 0
+// gives every block back to the driver at each sync, which makes cudaMallocAsync as slow as cudaMalloc)
+void keep_pool_memory(int device);
 
 static inline int num_sms(int device) {
     int n = 148;

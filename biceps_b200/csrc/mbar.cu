@@ -188,11 +188,12 @@ struct MbarWork {
     int n_acc_h = 0, grid = 0;
     double *d_a = nullptr, *d_rn = nullptr, *d_partial = nullptr, *d_out = nullptr;
     std::vector<double> lnN, rn;
-    ~MbarWork() { cudaFree(d_a); cudaFree(d_rn); cudaFree(d_partial); cudaFree(d_out); }
+    cudaStream_t st = nullptr;      // workspace is stream-ordered (cudaMallocAsync pool)
+    ~MbarWork() { cudaFreeAsync(d_a, st); cudaFreeAsync(d_rn, st); cudaFreeAsync(d_partial, st); cudaFreeAsync(d_out, st); }
 };
 
-static int mbar_work_init(MbarWork& w, int device, int K, long long N, const int64_t* N_k) {
-    w.device = device; w.K = K; w.N = N; w.sms = num_sms(device);
+static int mbar_work_init(MbarWork& w, int device, int K, long long N, const int64_t* N_k, cudaStream_t st) {
+    w.device = device; w.K = K; w.N = N; w.sms = num_sms(device); w.st = st;
     w.n_acc_h = K + K * (K + 1) / 2;
     const long long tiles = (N + MB_TILE - 1) / MB_TILE;
     w.grid = (int)std::min<long long>(tiles, (long long)w.sms * 4);
@@ -202,9 +203,10 @@ static int mbar_work_init(MbarWork& w, int device, int K, long long N, const int
         w.lnN[k] = N_k[k] > 0 ? log((double)N_k[k]) : -INFINITY;
         w.rn[k] = N_k[k] > 0 ? 1.0 / (double)N_k[k] : 0.0;
     }
-    BCP_CUDA(dev_alloc(&w.d_a, K)); BCP_CUDA(dev_alloc(&w.d_rn, K));
-    BCP_CUDA(dev_alloc(&w.d_partial, (size_t)w.grid * w.n_acc_h)); BCP_CUDA(dev_alloc(&w.d_out, w.n_acc_h));
-    BCP_CUDA(cudaMemcpy(w.d_rn, w.rn.data(), K * 8, cudaMemcpyHostToDevice));
+    BCP_CUDA(cudaMallocAsync((void**)&w.d_a, K * 8, st)); BCP_CUDA(cudaMallocAsync((void**)&w.d_rn, K * 8, st));
+    BCP_CUDA(cudaMallocAsync((void**)&w.d_partial, (size_t)w.grid * w.n_acc_h * 8, st));
+    BCP_CUDA(cudaMallocAsync((void**)&w.d_out, (size_t)w.n_acc_h * 8, st));
+    BCP_CUDA(cudaMemcpyAsync(w.d_rn, w.rn.data(), K * 8, cudaMemcpyHostToDevice, st));
     const size_t sm = pass_smem(K, w.n_acc_h);
     BCP_CUDA(cudaFuncSetAttribute(mbar_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     BCP_CUDA(cudaFuncSetAttribute(mbar_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -401,7 +403,7 @@ static int mbar_impl(const double* d_u, const int32_t* d_state, const int64_t* N
                      double tol, int max_iter, double* f_k, double* theta, double* pops, double* dpops, int32_t* iters,
                      cudaStream_t st) {
     MbarWork w;
-    int rc = mbar_work_init(w, device, K, N, N_k);
+    int rc = mbar_work_init(w, device, K, N, N_k, st);
     if (rc != BCP_OK) return rc;
     std::vector<double> th((size_t)K * K);
     int it = 0;
@@ -476,7 +478,7 @@ extern "C" int bcp_mbar_pass_dev(const double* d_u_kn, int64_t n_local, int32_t 
     BCP_REQUIRE(K >= 1 && K <= MB_MAXK && n_local > 0, "bcp_mbar_pass_dev: bad K or n_local");
     DeviceGuard guard(device);
     MbarWork w;
-    int rc = mbar_work_init(w, device, K, n_local, N_k_global);
+    int rc = mbar_work_init(w, device, K, n_local, N_k_global, (cudaStream_t)stream);
     if (rc != BCP_OK) return rc;
     return mbar_pass(w, d_u_kn, f_k, want_hess != 0, s_out, M_out, (cudaStream_t)stream);
 }

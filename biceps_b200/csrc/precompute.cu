@@ -35,8 +35,11 @@ enum RowMode { ROW_SSE = 0, ROW_LIN = 1, ROW_GAMMA = 2, ROW_GAMMA_LOG = 3 };
 template <int MODE>
 __global__ void __launch_bounds__(256)
 row_kernel(const double* __restrict__ model, const double* __restrict__ a, const double* __restrict__ b,
-           double c0, int S, int J, int L, const double* __restrict__ gam1, const double* __restrict__ gam2,
-           int G, double see, double* __restrict__ out) {
+           const double* __restrict__ c0_ptr, int S, int J, int L, const double* __restrict__ gam1,
+           const double* __restrict__ gam2, int G, const double* __restrict__ see_ptr, double* __restrict__ out) {
+    // scalars produced by the preceding tiny kernels stay on the device (no host round trip)
+    const double c0 = c0_ptr ? *c0_ptr : 0.0;
+    const double see = see_ptr ? *see_ptr : 0.0;
     const int lane = threadIdx.x & 31;
     const int sub = lane / L;                 // which row of this warp's pass
     const int l = lane - sub * L;
@@ -228,11 +231,14 @@ static int lanes_per_row(int J) {
     return L;
 }
 
+// stream-ordered scratch (cudaMallocAsync pool): a plain cudaMalloc/cudaFree pair costs ~0.5 ms and an
+// implicit device synchronisation per call, more than the kernels themselves
 struct Scratch {
     std::vector<void*> p;
-    ~Scratch() { for (void* q : p) cudaFree(q); }
+    cudaStream_t st = nullptr;
+    ~Scratch() { for (void* q : p) cudaFreeAsync(q, st); }
     template <typename T> cudaError_t get(T** out, size_t n) {
-        cudaError_t e = cudaMalloc((void**)out, (n ? n : 1) * sizeof(T));
+        cudaError_t e = cudaMallocAsync((void**)out, (n ? n : 1) * sizeof(T), st);
         if (e == cudaSuccess) p.push_back(*out);
         return e;
     }
@@ -251,19 +257,16 @@ static int precompute_device(const bcp_obs& o, int S, int device, cudaStream_t s
     int launches = 0;
 
     if (o.kind == BCP_KIND_SCALAR) {
-        row_kernel<ROW_SSE><<<grid, 256, 0, st>>>(o.model, o.weight, o.exp, 0.0, S, J, L, nullptr, nullptr, 1, 0.0, d_sse);
+        row_kernel<ROW_SSE><<<grid, 256, 0, st>>>(o.model, o.weight, o.exp, nullptr, S, J, L, nullptr, nullptr, 1, nullptr, d_sse);
         ++launches;
     } else {
         double *g1, *g2, *see;
         BCP_CUDA(scr.get(&g1, o.n_gamma)); BCP_CUDA(scr.get(&g2, o.n_gamma)); BCP_CUDA(scr.get(&see, 1));
         gamma_prep_kernel<<<1, 256, 0, st>>>(J, o.weight, o.exp, o.log_normal, o.n_gamma, o.gamma, g1, g2, see);
-        double h_see = 0.0;     // scalar needed as a kernel argument
-        BCP_CUDA(cudaMemcpyAsync(&h_see, see, sizeof(double), cudaMemcpyDeviceToHost, st));
-        BCP_CUDA(cudaStreamSynchronize(st));
         if (o.log_normal)
-            row_kernel<ROW_GAMMA_LOG><<<grid, 256, 0, st>>>(o.model, o.weight, o.exp, 0.0, S, J, L, g1, g2, o.n_gamma, h_see, d_sse);
+            row_kernel<ROW_GAMMA_LOG><<<grid, 256, 0, st>>>(o.model, o.weight, o.exp, nullptr, S, J, L, g1, g2, o.n_gamma, see, d_sse);
         else
-            row_kernel<ROW_GAMMA><<<grid, 256, 0, st>>>(o.model, o.weight, o.exp, 0.0, S, J, L, g1, g2, o.n_gamma, h_see, d_sse);
+            row_kernel<ROW_GAMMA><<<grid, 256, 0, st>>>(o.model, o.weight, o.exp, nullptr, S, J, L, g1, g2, o.n_gamma, see, d_sse);
         launches += 2;
     }
     BCP_CUDA(cudaGetLastError());
@@ -289,13 +292,10 @@ static int precompute_device(const bcp_obs& o, int S, int device, cudaStream_t s
             launches += 2;
         }
         ref_coef_kernel<<<1, 256, 0, st>>>(o.ref_kind, J, o.weight, d_par0, d_par1, o.use_global_ref_sigma, coef, c0);
-        double h_c0 = 0.0;
-        BCP_CUDA(cudaMemcpyAsync(&h_c0, c0, sizeof(double), cudaMemcpyDeviceToHost, st));
-        BCP_CUDA(cudaStreamSynchronize(st));
         if (o.ref_kind == 1)
-            row_kernel<ROW_LIN><<<grid, 256, 0, st>>>(o.model, coef, nullptr, h_c0, S, J, L, nullptr, nullptr, 1, 0.0, d_refsum);
+            row_kernel<ROW_LIN><<<grid, 256, 0, st>>>(o.model, coef, nullptr, c0, S, J, L, nullptr, nullptr, 1, nullptr, d_refsum);
         else
-            row_kernel<ROW_SSE><<<grid, 256, 0, st>>>(o.model, coef, d_par0, h_c0, S, J, L, nullptr, nullptr, 1, 0.0, d_refsum);
+            row_kernel<ROW_SSE><<<grid, 256, 0, st>>>(o.model, coef, d_par0, c0, S, J, L, nullptr, nullptr, 1, nullptr, d_refsum);
         launches += 2;
         BCP_CUDA(cudaGetLastError());
     }
@@ -323,10 +323,8 @@ extern "C" int bcp_precompute_dev(const bcp_obs* o, int32_t n_states, int device
     BCP_REQUIRE(d_sse, "bcp_precompute_dev: NULL sse output");
     DeviceGuard guard(device);
     Scratch scr;
-    rc = precompute_device(*o, n_states, device, (cudaStream_t)stream, d_sse, d_refsum, d_ref_par0, d_ref_par1, scr);
-    if (rc != BCP_OK) return rc;
-    BCP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));   // scratch is freed on return
-    return BCP_OK;
+    scr.st = (cudaStream_t)stream;
+    return precompute_device(*o, n_states, device, (cudaStream_t)stream, d_sse, d_refsum, d_ref_par0, d_ref_par1, scr);
 }
 
 extern "C" int bcp_precompute(const bcp_obs* o, int32_t n_states, int device, double* sse, double* refsum,

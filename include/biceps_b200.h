@@ -204,8 +204,8 @@ typedef struct bcp_obs {
  * ~1e-13 relative (reduction order and the gamma moment expansion differ), tolerance 1e-6.  */
 int bcp_precompute(const bcp_obs* obs, int32_t n_states, int device, double* sse, double* refsum,
                    double* ref_par0, double* ref_par1);
-/* same with every pointer (inside obs too) a device pointer; asynchronous kernels on `stream`,
- * returns after the stream has drained */
+/* same with every pointer (inside obs too) a device pointer; asynchronous on `stream` (scratch comes
+ * from the stream-ordered pool, nothing synchronises) */
 int bcp_precompute_dev(const bcp_obs* obs, int32_t n_states, int device, void* stream, double* d_sse,
                        double* d_refsum, double* d_ref_par0, double* d_ref_par1);
 /* logZ[k] = ln sum_i exp(-energy[k][i])   (PosteriorSampler.py:64-71); host pointers */

@@ -1,0 +1,108 @@
+"""Stage benchmarks (device-resident, CUDA events): precompute K1/K2/K4, u_kn K6, MBAR K7 against the
+measured HBM peak.  Prints one JSON object; profiles/README.md quotes it.  Not the headline bench."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from biceps_b200 import _cabi as A, engine, mbar, precompute, synthetic
+
+lib = A.lib()
+dev = torch.device("cuda:0")
+peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+out = {"hbm_peak_gbs": peak}
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timed(fn, reps=5):
+    best = 1e9
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); b.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+# ---- K1 / K2 / K4 on C3-shaped observables ----
+S = 10000
+rng = np.random.default_rng(0)
+for name, J, kind, ref, G in [("K1_sse_scalar_J300", 300, A.BCP_KIND_SCALAR, 0, 1), ("K2_sse_gamma_J400_G163", 400, A.BCP_KIND_GAMMA, 0, 163),
+                              ("K2K4_gamma_expref_J400", 400, A.BCP_KIND_GAMMA, 1, 163), ("K1K4_scalar_gaussref_J1000", 1000, A.BCP_KIND_SCALAR, 2, 1)]:
+    e = rng.uniform(2, 6, J)
+    model = torch.from_numpy(np.clip(e * (1 + 0.15 * rng.standard_normal((S, J))), 0.5, None)).to(dev)
+    exp = torch.from_numpy(e).to(dev); w = torch.ones(J, dtype=torch.float64, device=dev)
+    gam = torch.from_numpy(precompute.log_grid(0.2, 5.0, 1.02)).to(dev)
+    sse = torch.empty((S, G), dtype=torch.float64, device=dev)
+    refsum = torch.empty(S, dtype=torch.float64, device=dev); p0 = torch.empty(J, dtype=torch.float64, device=dev); p1 = torch.empty(J, dtype=torch.float64, device=dev)
+    obs = A.bcp_obs(kind, J, ref, 0, 1, G, C.cast(model.data_ptr(), A.c_double_p), C.cast(exp.data_ptr(), A.c_double_p),
+                    C.cast(w.data_ptr(), A.c_double_p), C.cast(gam.data_ptr(), A.c_double_p))
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        A.check(lib.bcp_precompute_dev(C.byref(obs), S, 0, C.c_void_p(st), ptr(sse), ptr(refsum), ptr(p0), ptr(p1)), "precompute")
+    run(); torch.cuda.synchronize()
+    ms = timed(run)
+    passes = 1 + (0 if ref == 0 else (2 if ref == 1 else 3))
+    nbytes = 8.0 * S * J * passes + 8.0 * S * G + (8.0 * S if ref else 0)
+    out[name] = {"ms": ms, "algorithmic_GB": nbytes / 1e9, "GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
+                 "passes_over_model": passes}
+
+# ---- K6 / K7 at C5 scale: K = 11 lambdas, N = 11 x 64 x 1e4 snapshots ----
+ens = synthetic.make_ensemble("C3", seed=0, n_lambda=11)
+tabs = precompute.build_tables(ens["energies"], ens["lambdas"], ens["restraints"])
+T = engine.DeviceTables(tabs)
+K, per = 11, 64 * 10000
+N = K * per
+blk = T.chains(per // 50, 3, chain_lambda=np.zeros(per // 50, np.int32))
+st_h = rng.integers(0, S, N).astype(np.int32)
+idx_h = np.stack([rng.integers(gl // 2 - 3, gl // 2 + 3, N) for gl in T.grid_len], axis=1).astype(np.int32)
+d_state = torch.from_numpy(st_h).to(dev); d_idx = torch.from_numpy(idx_h).to(dev)
+d_u = torch.empty((K, N), dtype=torch.float64, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+
+
+def run_ukn():
+    A.check(lib.bcp_ukn_dev(T._h, N, ptr(d_state), ptr(d_idx), ptr(d_u), C.c_void_p(st)), "ukn")
+run_ukn(); torch.cuda.synchronize()
+ms = timed(run_ukn)
+nb = 8.0 * K * N + 4.0 * N * (1 + T.n_params)
+out["K6_ukn_K11_N7e6"] = {"ms": ms, "algorithmic_GB": nb / 1e9, "GBps": nb / ms / 1e6, "frac_of_hbm_peak": nb / ms / 1e6 / peak}
+
+# a well-posed MBAR problem of the same size: samples of run k drawn around lambda_k
+en = torch.from_numpy(tabs["energy"]).to(dev)            # [K][S]
+samp_state = torch.cat([torch.multinomial(torch.softmax(-en[k], 0), per, replacement=True) for k in range(K)])
+base = torch.from_numpy(rng.normal(50.0, 3.0, N)).to(dev)
+d_u2 = (en[:, samp_state] + base[None, :]).contiguous()
+N_k = np.full(K, per, dtype=np.int64)
+f = np.zeros(K); s_out = np.zeros(K); M_out = np.zeros((K, K))
+
+
+def run_pass(hess):
+    A.check(lib.bcp_mbar_pass_dev(ptr(d_u2), N, K, A.i64ptr(N_k), A.dptr(f), hess, 0, C.c_void_p(st), A.dptr(s_out), A.dptr(M_out)), "pass")
+for hess, nm in [(0, "K7_mbar_pass_sci"), (1, "K7_mbar_pass_newton")]:
+    run_pass(hess); torch.cuda.synchronize()
+    ms = timed(lambda: run_pass(hess))
+    nb = 8.0 * K * N
+    out[nm] = {"ms": ms, "algorithmic_GB": nb / 1e9, "GBps": nb / ms / 1e6, "frac_of_hbm_peak": nb / ms / 1e6 / peak,
+               "note": "one streaming pass over u_kn incl. the allocation of the per-call workspace"}
+fk = np.zeros(K); theta = np.zeros((K, K)); it = C.c_int32(0)
+d_st32 = samp_state.to(torch.int32)
+pops = np.zeros((S, K)); dpops = np.zeros((S, K))
+t0 = time.perf_counter()
+A.check(lib.bcp_mbar_dev(ptr(d_u2), A.i64ptr(N_k), K, N, ptr(d_st32), S, 0, C.c_void_p(st), 0.0, 0, A.dptr(fk), A.dptr(theta),
+                         A.dptr(pops), A.dptr(dpops), C.byref(it)), "mbar")
+torch.cuda.synchronize()
+out["K7_mbar_solve_K11_N7e6"] = {"seconds": time.perf_counter() - t0, "iterations": int(it.value), "f": [float(x) for x in fk],
+                                 "pop_sum": float(pops[:, -1].sum())}
+print(json.dumps(out, indent=1))
