@@ -253,7 +253,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- the same tables with enough chains to fill the machine (issue-bound regime): not the headline
     #      configuration (C3 names 4096 chains per GPU), reported for the throughput ceiling ----
     sat_n = 148 * 2048
-    sat_lam = (np.arange(sat_n) // (sat_n // N_LAMBDA + 1)).astype(np.int32)
+    sat_lam = (np.arange(sat_n) % N_LAMBDA).astype(np.int32)      # interleaved: a warp's histogram flushes spread over 8 tables
     sat_blk = T.chains(sat_n, SEED + 2, chain_id0=(world + rank) * sat_n, chain_lambda=sat_lam)
     sat_steps = 4000
     sat_blk.launch(200, stream=stream)

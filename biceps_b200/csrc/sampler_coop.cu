@@ -49,7 +49,7 @@ __device__ __forceinline__ double u2_fast(uint32_t w2, uint32_t w3) {
     return __dadd_rn(__dadd_rn(one_k, -1.0), 1.1102230246251565e-16);
 }
 
-template <int L, bool HG>
+template <int L, int R, bool HG>
 __global__ void __launch_bounds__(128)
 mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                  const __grid_constant__ LaunchArgs A) {
@@ -58,7 +58,6 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     __shared__ __align__(8) uint64_t mbar;
     stage_sigma_table(s_sig, T.sig_tab, T.sig_bytes, &mbar);
 
-    const int R = T.R;
     const long long n = C.n_chains;
     const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int q = (int)(threadIdx.x & (L - 1));             // lane within the chain's group
@@ -300,10 +299,10 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     }
 }
 
-template <int L, bool HG>
+template <int L, int R, bool HG>
 static cudaError_t launch_coop_one(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st,
                                    int sms) {
-    cudaError_t e = cudaFuncSetAttribute(mcmc_coop_kernel<L, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.sig_bytes);
+    cudaError_t e = cudaFuncSetAttribute(mcmc_coop_kernel<L, R, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.sig_bytes);
     if (e != cudaSuccess) return e;
     const long long threads = C.n_chains * L;
     const long long n_warps = (threads + 31) / 32;
@@ -311,17 +310,22 @@ static cudaError_t launch_coop_one(const SamplerTables& T, const ChainBuffers& C
     wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
     const int block = wpb * 32;
     const int grid = (int)((threads + block - 1) / block);
-    mcmc_coop_kernel<L, HG><<<grid, block, T.sig_bytes, st>>>(T, C, A);
+    mcmc_coop_kernel<L, R, HG><<<grid, block, T.sig_bytes, st>>>(T, C, A);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mcmc_coop(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms) {
     if (!T.canonical || T.R < 1 || T.R > 8) return cudaErrorNotSupported;
     const bool hg = T.r[T.R - 1].has_gamma != 0;
-    const int L = T.R <= 2 ? 2 : (T.R <= 4 ? 4 : 8);
-    if (L == 2) return hg ? launch_coop_one<2, true>(T, C, A, st, sms) : launch_coop_one<2, false>(T, C, A, st, sms);
-    if (L == 4) return hg ? launch_coop_one<4, true>(T, C, A, st, sms) : launch_coop_one<4, false>(T, C, A, st, sms);
-    return hg ? launch_coop_one<8, true>(T, C, A, st, sms) : launch_coop_one<8, false>(T, C, A, st, sms);
+#define BCP_COOP(l, r)                                                                              \
+    case r:                                                                                         \
+        return hg ? launch_coop_one<l, r, true>(T, C, A, st, sms) : launch_coop_one<l, r, false>(T, C, A, st, sms);
+    switch (T.R) {          // L = smallest of 2, 4, 8 that holds one lane per restraint
+        BCP_COOP(2, 1) BCP_COOP(2, 2) BCP_COOP(4, 3) BCP_COOP(4, 4)
+        BCP_COOP(8, 5) BCP_COOP(8, 6) BCP_COOP(8, 7) BCP_COOP(8, 8)
+        default: return cudaErrorNotSupported;
+    }
+#undef BCP_COOP
 }
 
 }  // namespace bcp
