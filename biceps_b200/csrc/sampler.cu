@@ -417,7 +417,7 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
             }
         }
         if ((rc = upload(h, rec.data(), rec.size(), &T.rec)) != BCP_OK) return fail(rc);
-        T.gsse_halo = nullptr;
+        T.gsse_halo = nullptr; T.gsse_halo3 = nullptr; T.gsse_rows = nullptr; T.gamma_row_stride = 0;
         if (T.r[T.R - 1].has_gamma) {
             const int G = T.r[T.R - 1].n_gamma;
             const double* src = t->restraints[T.R - 1].sse;
@@ -426,6 +426,17 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
                 for (int k = 0; k < G + 4; ++k)
                     halo[(size_t)i * (G + 4) + k] = src[(size_t)i * G + ((k - 2) % G + G) % G];
             if ((rc = upload(h, halo.data(), halo.size(), &T.gsse_halo)) != BCP_OK) return fail(rc);
+            std::vector<double> halo3((size_t)T.S * (G + 6));
+            const int Gp = (G + 1) & ~1;
+            std::vector<double> rows((size_t)T.S * Gp, 0.0);
+            for (int i = 0; i < T.S; ++i) {
+                for (int k = 0; k < G + 6; ++k)
+                    halo3[(size_t)i * (G + 6) + k] = src[(size_t)i * G + ((k - 3) % G + G) % G];
+                for (int k = 0; k < G; ++k) rows[(size_t)i * Gp + k] = src[(size_t)i * G + k];
+            }
+            T.gamma_row_stride = Gp;
+            if ((rc = upload(h, halo3.data(), halo3.size(), &T.gsse_halo3)) != BCP_OK) return fail(rc);
+            if ((rc = upload(h, rows.data(), rows.size(), &T.gsse_rows)) != BCP_OK) return fail(rc);
         }
     }
     if ((rc = upload(h, t->energy, (size_t)T.K * T.S, &T.energy)) != BCP_OK) return fail(rc);
@@ -603,7 +614,8 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
     // (coop); many chains -> issue-bound: one thread per chain (fast).  Crossover measured on B200
     // (profiles/README.md): coop wins at 4096 chains (5.6e9 vs 4.2e9 steps/s), fast from ~16k up.
     int which = !T.canonical ? 0 : (n <= 8192 ? 2 : 1);              // 0 generic, 1 fast, 2 coop
-    if (kern && T.canonical) which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : 2);
+    if (kern && T.canonical)
+        which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "coop2") ? 3 : 2));
     if (force && force[0] == '1') which = 0;
     const bool fast = which == 1;
     int fgrid = grid, fblock = block;
@@ -620,6 +632,10 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
         A.s_end = s0 + kMaxStepsPerLaunch < total ? s0 + kMaxStepsPerLaunch : total;
         cudaError_t e;
         if (T.pf.q >= 0) e = launch_mcmc_pf(T, c->C, A, st);
+        else if (which == 3) {
+            e = launch_mcmc_coop2(T, c->C, A, st, sms);
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); }
+        }
         else if (which == 2) e = launch_mcmc_coop(T, c->C, A, st, sms);
         else if (fast) e = launch_mcmc_fast(T, c->C, A, fgrid, fblock, st);
         else switch (T.R) {

@@ -57,6 +57,13 @@ struct SamplerTables {
     // window around any gamma index is contiguous and needs no wrap arithmetic:
     // gsse_halo[i][k] = sse[i][(k - 2) mod G], k in [0, G+4)
     const double* gsse_halo;
+    // for the two-steps-per-iteration kernel: the same rows with a 3-element halo (7-wide windows),
+    // gsse_halo3[i][k] = sse[i][(k - 3) mod G], k in [0, G+6), and 16-byte aligned plain rows
+    // gsse_rows[i][k], k in [0, gamma_row_stride), gamma_row_stride = G rounded up to even
+    const double* gsse_halo3;
+    const double* gsse_rows;
+    int gamma_row_stride;
+    int pad2;
     int rec_stride;         // 2 * R doubles
     int canonical;          // 1 if the specialised kernel applies
 };

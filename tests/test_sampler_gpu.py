@@ -8,9 +8,9 @@ from helpers import cineromycin_tables, stack_lambdas, assert_outputs_equal, loa
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["coop", "fast", "generic"], autouse=True)
+@pytest.fixture(params=["coop2", "coop", "fast", "generic"], autouse=True)
 def kernel(request, monkeypatch):
-    """Every parity case runs through all three Metropolis kernels (cooperative lanes-per-chain,
+    """Every parity case runs through all Metropolis kernels (cooperative two-steps-per-iteration, cooperative lanes-per-chain,
     thread-per-chain specialised, generic); BCP_KERNEL is read at each launch."""
     monkeypatch.setenv("BCP_KERNEL", request.param)
     return request.param
@@ -159,7 +159,7 @@ def test_synthetic_c2_five_restraints_eight_lambdas():
 
 
 def test_statistical_agreement_of_independent_streams(cin, kernel):
-    if kernel != "coop":
+    if kernel != "coop2":
         pytest.skip("statistics do not depend on the kernel (all three are bit-identical)")
     """Posterior populations from two independent seeds agree (KL < 1e-3, north_star tolerance)."""
     from biceps_b200 import engine
