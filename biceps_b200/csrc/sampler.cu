@@ -417,7 +417,7 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
             }
         }
         if ((rc = upload(h, rec.data(), rec.size(), &T.rec)) != BCP_OK) return fail(rc);
-        T.gsse_halo = nullptr; T.gsse_halo3 = nullptr; T.gsse_rows = nullptr; T.gamma_row_stride = 0;
+        T.gsse_halo = nullptr; T.gsse_halo4 = nullptr; T.gh4_stride = 0;
         if (T.r[T.R - 1].has_gamma) {
             const int G = T.r[T.R - 1].n_gamma;
             const double* src = t->restraints[T.R - 1].sse;
@@ -426,18 +426,37 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
                 for (int k = 0; k < G + 4; ++k)
                     halo[(size_t)i * (G + 4) + k] = src[(size_t)i * G + ((k - 2) % G + G) % G];
             if ((rc = upload(h, halo.data(), halo.size(), &T.gsse_halo)) != BCP_OK) return fail(rc);
-            std::vector<double> halo3((size_t)T.S * (G + 6));
-            const int Gp = (G + 1) & ~1;
-            std::vector<double> rows((size_t)T.S * Gp, 0.0);
-            for (int i = 0; i < T.S; ++i) {
-                for (int k = 0; k < G + 6; ++k)
-                    halo3[(size_t)i * (G + 6) + k] = src[(size_t)i * G + ((k - 3) % G + G) % G];
-                for (int k = 0; k < G; ++k) rows[(size_t)i * Gp + k] = src[(size_t)i * G + k];
-            }
-            T.gamma_row_stride = Gp;
-            if ((rc = upload(h, halo3.data(), halo3.size(), &T.gsse_halo3)) != BCP_OK) return fail(rc);
-            if ((rc = upload(h, rows.data(), rows.size(), &T.gsse_rows)) != BCP_OK) return fail(rc);
+            const int GS = (G + 9 + 1) & ~1;
+            std::vector<double> halo4((size_t)T.S * GS);
+            for (int i = 0; i < T.S; ++i)
+                for (int k = 0; k < GS; ++k)
+                    halo4[(size_t)i * GS + k] = src[(size_t)i * G + ((k - 4) % G + G) % G];
+            T.gh4_stride = GS;
+            if ((rc = upload(h, halo4.data(), halo4.size(), &T.gsse_halo4)) != BCP_OK) return fail(rc);
         }
+        // packed sigma entries for the speculative kernel; 1 / (2 sigma^2) is the correctly rounded
+        // IEEE reciprocal (host division), which is what makes the device-side Markstein division exact
+        std::vector<double> sig4;
+        T.div_safe = 1;
+        for (int q = 0; q < T.R; ++q) {
+            const bcp_restraint& r = t->restraints[q];
+            const int ns = r.n_sigma;
+            T.ent_off[q] = (int)(sig4.size() / 3);
+            for (int e = 0; e < ns + 4; ++e) {
+                const int k = ((e - 2) % ns + ns) % ns;
+                const double d = r.two_sig2[k];
+                if (!(d > 1e-140 && d < 1e140)) T.div_safe = 0;
+                sig4.push_back(r.nlsig[k]); sig4.push_back(d); sig4.push_back(1.0 / d);
+            }
+            const size_t cnt = (size_t)T.S * T.r[q].n_gamma;
+            for (size_t k = 0; k < cnt && T.div_safe; ++k) {
+                const double v = r.sse[k];
+                if (!(v == 0.0 || (v > 1e-140 && v < 1e140))) T.div_safe = 0;
+            }
+        }
+        while (sig4.size() % 2) sig4.push_back(0.0);
+        T.sig4_bytes = (int)(sig4.size() * sizeof(double));
+        if ((rc = upload(h, sig4.data(), sig4.size(), &T.sig4)) != BCP_OK) return fail(rc);
     }
     if ((rc = upload(h, t->energy, (size_t)T.K * T.S, &T.energy)) != BCP_OK) return fail(rc);
     if ((rc = upload(h, t->logZ, (size_t)T.K, &T.logZ)) != BCP_OK) return fail(rc);
@@ -613,9 +632,9 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
     // auto: few chains -> the step time is one warp's instruction stream: spread a chain over L lanes
     // (coop); many chains -> issue-bound: one thread per chain (fast).  Crossover measured on B200
     // (profiles/README.md): coop wins at 4096 chains (5.6e9 vs 4.2e9 steps/s), fast from ~16k up.
-    int which = !T.canonical ? 0 : (n <= 8192 ? 2 : 1);              // 0 generic, 1 fast, 2 coop
+    int which = !T.canonical ? 0 : (n <= 8192 ? 3 : 1);              // 0 generic, 1 fast, 2 coop, 3 spec
     if (kern && T.canonical)
-        which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "coop2") ? 3 : 2));
+        which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : 2));
     if (force && force[0] == '1') which = 0;
     const bool fast = which == 1;
     int fgrid = grid, fblock = block;
@@ -633,7 +652,7 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
         cudaError_t e;
         if (T.pf.q >= 0) e = launch_mcmc_pf(T, c->C, A, st);
         else if (which == 3) {
-            e = launch_mcmc_coop2(T, c->C, A, st, sms);
+            e = launch_mcmc_spec(T, c->C, A, st, sms);
             if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); }
         }
         else if (which == 2) e = launch_mcmc_coop(T, c->C, A, st, sms);

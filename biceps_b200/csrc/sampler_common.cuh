@@ -83,8 +83,9 @@ cudaError_t launch_mcmc_fast(const SamplerTables& T, const ChainBuffers& C, cons
 // cooperative kernel (sampler_coop.cu): L lanes per chain; canonical layout only
 cudaError_t launch_mcmc_coop(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms);
 
-// cooperative kernel resolving two steps per iteration (sampler_coop2.cu); canonical layout only
-cudaError_t launch_mcmc_coop2(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms);
+// speculative cooperative kernel (sampler_spec.cu): canonical layout, chain blocks in shared memory;
+// cudaErrorNotSupported if the tables do not qualify (layout, shared-memory budget, division range)
+cudaError_t launch_mcmc_spec(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms);
 // warp-per-chain kernel for ensembles with a PFGRID restraint (sampler_pf.cu); any layout
 cudaError_t launch_mcmc_pf(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st);
 // -log P of explicit configurations when the ensemble has a PFGRID restraint (warp per configuration)

@@ -1,0 +1,551 @@
+// K5, speculative cooperative Metropolis kernel: L lanes per chain, one lane per restraint, the
+// candidate energy of step s+1 prepared while step s is being resolved.
+//
+// With few chains per GPU (the C3 configuration runs 4096 = one warp per SM sub-partition at L = 4)
+// a step costs the time ONE warp needs to issue its instruction stream in order.  The design therefore
+// minimises (i) the dependent latency between two consecutive accept decisions, (ii) the number of
+// instructions per step and (iii) the number of basic blocks per step, so that ptxas can interleave the
+// independent work (measured latencies: scripts/microbench.cu -> profiles/r01_microbench.json).
+//
+//   * Proposals depend only on the counter-based RNG, so while step s is resolved every lane
+//     evaluates ITS restraint term of step s+1's proposal under both outcomes of step s
+//     (H0: s rejected, H1: s accepted; they differ only in the lane that step s moves).  The accept
+//     decision then selects one of the two.  Dependent path per step: select -> R shuffles ->
+//     R-1 fp64 adds (reference order; lane 0 has pre-added energy + logZ) -> subtract -> compare.
+//   * sse / (2 sigma^2) uses a correctly rounded reciprocal table and Markstein's correction
+//     (5 dependent FMA-class operations instead of the ~124-cycle IEEE division sequence); the result
+//     is bit-identical to IEEE division (see div_markstein).
+//   * The Metropolis test u < exp(d) is decided as d - ln(u) > +-2^-13 with ln(u) computed in fp32 by
+//     the lane that generated the step's Philox block, ahead of time; inside the guard band the
+//     specified exact rule (exp_det.cuh) is evaluated, so the decision is always the specified one.
+//   * All state-dependent words of a chain live in shared memory: the current state's record and its
+//     whole gamma row (periodic halo, so index +-2 needs no wrap), and, for the state moves of the
+//     next batches, the proposed state's record + a 10-wide gamma window, fetched with cp.async
+//     D batches (D L steps) ahead by the lane that generated that step's Philox block.  Chain blocks are
+//     laid out 16 B apart modulo the 128-B bank period, so the 8 chains of a warp never collide.
+//   * Lane j of a group generates the Philox block of position j of a batch of L steps; the 10 rounds are
+//     spread over the L steps of the batch D batches earlier (software pipelined by hand).
+//   * The sigma vectors {Ndof ln sigma, 2 sigma^2, 1/(2 sigma^2)} of all restraints are staged once per
+//     CTA by a 1-D TMA bulk copy (UBLKCP).
+//   * One step is ONE basic block: histogram flushes are predicated REDs, and everything rare (guard band
+//     of the accept test, an accepted state move = record copy + gamma row reload, a gamma index that
+//     drifted out of a prefetched window, a trajectory snapshot / state-trace store) sits behind a single
+//     warp-uniform, out-of-line branch that re-does the step's commit exactly.
+// Same RNG stream, same fp64 operation order and the same outputs as the other kernels (parity with the
+// oracle is bit for bit); canonical restraint layout only (tables.cuh).
+#include "exp_det.cuh"
+#include "philox.cuh"
+#include "sampler_common.cuh"
+
+namespace bcp {
+
+#define SPEC_FULL 0xffffffffu
+#define SPEC_MARGIN 1.220703125e-4f      // 2^-13: >> fp32 error of ln(u) (< 1e-5) + rounding of (float)d (< 3e-6)
+constexpr int SPEC_WIN_BYTES = 80;       // 10 doubles
+constexpr int SPEC_ENT_BYTES = 24;       // one sigma entry {Ndof ln sigma, 2 sigma^2, 1/(2 sigma^2)}
+
+// a / b with y = RN(1/b) given (host table).  q0 = RN(a y) is within 1.5 ulp of a/b; one Newton
+// correction makes q1 faithful (error < 1 ulp); then r1 = a - b q1 is exactly representable and, by
+// Markstein's theorem (y correctly rounded, q1 faithful), RN(q1 + r1 y) == RN(a / b).  No exponent
+// range issues for the magnitudes admitted by SamplerTables::div_safe.
+__device__ __forceinline__ double div_markstein(double a, double b, double y) {
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-q, b, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-q, b, a);
+    return __fma_rn(r, y, q);
+}
+
+__device__ __forceinline__ double lds64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// predicated histogram flush without a branch (keeps the step a single basic block)
+__device__ __forceinline__ void red_add_if(unsigned long long* p, unsigned int v, bool pred) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u64 w;\n"
+        "setp.ne.b32 p, %2, 0;\n"
+        "cvt.u64.u32 w, %1;\n"
+        "@p red.global.add.u64 [%0], w;\n"
+        "}\n" ::"l"(p), "r"(v), "r"((int)pred)
+        : "memory");
+}
+
+// Metropolis uniform (2k+1) * 2^-53, k = (w2 << 20) | (w3 >> 12)  (== philox.cuh:u2_from_words)
+__device__ __forceinline__ double spec_u2(uint32_t w2, uint32_t w3) {
+    const uint32_t hi = 0x3FF00000u | (w2 >> 12);
+    const uint32_t lo = (w2 << 20) | (w3 >> 12);
+    const double one_k = __hiloint2double((int)hi, (int)lo);
+    return __dadd_rn(__dadd_rn(one_k, -1.0), 1.1102230246251565e-16);
+}
+
+// One generated step: the proposal packed in 32 bits, ln(u) in fp32 and u itself (guard band only).
+//   nuisance move: bit 31 | restraint (bits 0-3) | dsigma + 1 (bits 4-5) | dgamma + 1 (bits 6-7)
+//   state move:    proposed state (< 2^31)
+struct SpecGen {
+    uint32_t desc;
+    float lu;
+    double u;
+};
+
+struct SpecLayout {          // byte offsets inside a chain's shared-memory block
+    int cur_rec, cur_row, slot0, slot_bytes, slot_c, slot_win, chain_bytes;
+};
+
+template <int L>
+struct SpecCfg {
+    static constexpr int D = L == 2 ? 3 : 2;     // batches between the generation of a step and its batch
+    static constexpr int NSLOT = 4 * L;          // proposal slots per chain (4 batches, power of two)
+};
+
+__host__ __device__ inline SpecLayout spec_layout(int L, int R, bool hg, int gh4_stride) {
+    SpecLayout o;
+    o.cur_rec = 0;
+    o.cur_row = 16 * R;
+    o.slot0 = o.cur_row + (hg ? gh4_stride * 8 : 0);
+    o.slot_c = 16 * R;
+    o.slot_win = 16 * R + 16;
+    o.slot_bytes = o.slot_win + (hg ? SPEC_WIN_BYTES : 0);
+    int b = o.slot0 + 4 * L * o.slot_bytes;
+    b = (b + 15) & ~15;
+    while ((b & 127) != 16) b += 16;      // consecutive chains start 16 B apart modulo the 128-B bank period
+    o.chain_bytes = b;
+    return o;
+}
+
+template <int L, int R, bool HG>
+__global__ void __launch_bounds__(128)
+mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
+                 const __grid_constant__ LaunchArgs A) {
+    constexpr int D = SpecCfg<L>::D;
+    constexpr int NSLOT = SpecCfg<L>::NSLOT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    stage_sigma_table(reinterpret_cast<double*>(smem_raw), T.sig4, T.sig4_bytes, &mbar);
+
+    const long long n = C.n_chains;
+    const long long gthread = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = (int)(threadIdx.x & (L - 1));             // lane within the chain's group
+    long long c = gthread / L;
+    const bool live = c < n;                                // dead groups shadow the last chain, no stores
+    if (!live) c = n - 1;
+    const int qr = q < R ? q : 0;                           // restraint this lane evaluates (idle lanes: 0)
+    const bool owner = live && q < R;
+    const bool lead = live && q == 0;
+    const bool glane = HG && q == R - 1;                    // lane of the gamma restraint
+    const uint32_t own_tag = q < R ? (0x80000000u | (uint32_t)q) : 0xFFFFFFFFu;
+
+    const int lam = C.lam[c];
+    const int grp = C.group[c];
+    const unsigned long long chain_id = C.chain_id0 + (unsigned long long)c;
+    const double* __restrict__ energy = T.energy + (size_t)lam * T.S;
+    const double logZ = T.logZ[lam];
+    const double* __restrict__ rec = T.rec;
+    const double* __restrict__ gh4 = HG ? T.gsse_halo4 : nullptr;
+    const int G = HG ? T.r[R - 1].n_gamma : 1;
+    const int GS = HG ? T.gh4_stride : 0;
+    unsigned long long* g_state_counts = C.state_counts + (size_t)grp * T.S;
+    unsigned long long* g_sigma_hist = C.param_counts + (size_t)grp * T.HB + T.r[qr].hist_sigma;
+    unsigned long long* g_gamma_hist = C.param_counts + (size_t)grp * T.HB + (HG ? T.r[R - 1].hist_gamma : 0);
+    const uint32_t S = (uint32_t)T.S;
+    const uint32_t thresh = T.nuis_thresh;
+    const int s_end = (int)(A.s_end - A.s_begin);
+    const long long burn_l = A.burn - A.s_begin;
+    const int burn = burn_l < 0 ? 0 : (burn_l > s_end ? s_end : (int)burn_l);
+    const unsigned long long ctr0 = A.step0 + (unsigned long long)A.s_begin;
+    const uint32_t seed_lo = (uint32_t)C.seed, seed_hi = (uint32_t)(C.seed >> 32);
+    const uint32_t ch_lo = (uint32_t)chain_id, ch_hi = (uint32_t)(chain_id >> 32);
+
+    const SpecLayout ly = spec_layout(L, R, HG, GS);
+    const uint32_t smem0 = smem_u32(smem_raw);
+    const uint32_t chain_base = smem0 + (uint32_t)T.sig4_bytes + (uint32_t)(threadIdx.x / L) * (uint32_t)ly.chain_bytes;
+    const uint32_t cur_rec = chain_base + ly.cur_rec + 16 * qr;
+    const uint32_t cur_row = chain_base + ly.cur_row;
+    const uint32_t slots = chain_base + ly.slot0;
+    const int nsig = T.r[qr].n_sigma;
+    const uint32_t ent_base = smem0 + (uint32_t)SPEC_ENT_BYTES * (uint32_t)(T.ent_off[qr] + 2);   // entry of sigma index 0
+    const double cnorm = T.r[qr].cnorm;
+
+    // ---- chain state: E and state replicated in every lane of the group --------------------------
+    int state = C.state[c];
+    double E = C.E[c];
+    int sg = C.isg[(size_t)qr * n + c];
+    int gm = glane ? C.igm[(size_t)(R - 1) * n + c] : 0;
+    int pg = gm;                                             // unwrapped gamma position (window bookkeeping)
+    // lane 0 adds energy + logZ to its term (reference order (C + t_0) + t_1 ...); x + (-0.0) == x bitwise
+    double Cst = q == 0 ? __dadd_rn(energy[state], logZ) : -0.0;
+    int since_sg = burn, since_gm = burn, since_state = burn;
+    unsigned int acc_own = 0, acc_state = 0, acc_total = 0;
+
+    if (q < R) sts128(cur_rec, *reinterpret_cast<const double2*>(rec + ((size_t)state * R + q) * 2));
+    if (HG) {
+        const double2* src = reinterpret_cast<const double2*>(gh4 + (size_t)state * GS);
+        for (int k = q; k < GS / 2; k += L) sts128(cur_row + 16 * k, src[k]);
+    }
+
+    int next_snap = -1;
+    long long snap_idx = 0;
+    if (A.traj_every > 0) {
+        const long long m = A.s_begin <= A.burn ? 0 : (A.s_begin - A.burn + A.traj_every - 1) / A.traj_every;
+        snap_idx = m;
+        const long long ns = A.burn + m * A.traj_every - A.s_begin;
+        next_snap = ns < s_end ? (int)ns : -1;
+    }
+    int next_ev = A.state_trace ? 0 : next_snap;             // next step that must take the out-of-line path
+
+    // ---- Philox block of one step, generated by the lane whose index is the step's batch position ----
+    uint32_t pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0, pk0 = 0, pk1 = 0;
+    auto philox_begin = [&](int s) {
+        const unsigned long long ctr = ctr0 + (unsigned long long)s;
+        pc0 = (uint32_t)ctr; pc1 = (uint32_t)(ctr >> 32); pc2 = ch_lo; pc3 = ch_hi; pk0 = seed_lo; pk1 = seed_hi;
+    };
+    auto philox_round = [&]() {
+        const uint64_t p0 = (uint64_t)BCP_PHILOX_M0 * pc0;
+        const uint64_t p1 = (uint64_t)BCP_PHILOX_M1 * pc2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ pc1 ^ pk0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ pc3 ^ pk1;
+        pc1 = (uint32_t)p1; pc3 = (uint32_t)p0; pc0 = n0; pc2 = n2;
+        pk0 += BCP_PHILOX_W0; pk1 += BCP_PHILOX_W1;
+    };
+    auto philox_finish = [&](int s) {
+        const bool nuis = pc0 < thresh;
+        const uint64_t pr = (uint64_t)pc1 * (nuis ? (uint32_t)R : S);
+        const uint32_t hi = (uint32_t)(pr >> 32);
+        const uint64_t z1 = (uint64_t)(uint32_t)pr * 3u;
+        const uint64_t z2 = (uint64_t)(uint32_t)z1 * 3u;
+        const uint32_t a = (uint32_t)(z1 >> 32);
+        const uint32_t b = (HG && hi == (uint32_t)(R - 1)) ? (uint32_t)(z2 >> 32) : 1u;
+        SpecGen g;
+        g.desc = nuis ? (0x80000000u | hi | (a << 4) | (b << 6)) : hi;
+        g.u = spec_u2(pc2, pc3);
+        // steps past the end of the launch are executed as padding of the last batch: never accepted
+        g.lu = s < s_end ? __logf((float)g.u) : __int_as_float(0x7f800000);
+        return g;
+    };
+    // cp.async of the proposed state's words for a generated state move into the step's slot
+    auto prefetch = [&](const SpecGen& g, int s, int gm_now) {
+        if (!((int)g.desc < 0)) {
+            const uint32_t i2 = g.desc;
+            const uint32_t slot = slots + (uint32_t)(s & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
+            const double* r2 = rec + (size_t)i2 * (2 * R);
+#pragma unroll
+            for (int k = 0; k < R; ++k) cp_async16(slot + 16 * k, r2 + 2 * k);
+            cp_async8(slot + ly.slot_c, energy + i2);
+            if (HG) {
+                const double* w = gh4 + (size_t)i2 * GS + (gm_now & ~1);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) cp_async16(slot + ly.slot_win + 16 * k, w + 2 * k);
+            }
+        }
+    };
+    auto bcast_i = [&](int v, int src) { return __shfl_sync(SPEC_FULL, v, src, L); };
+    auto bcast_u = [&](uint32_t v, int src) { return __shfl_sync(SPEC_FULL, v, src, L); };
+    auto bcast_f = [&](float v, int src) { return __shfl_sync(SPEC_FULL, v, src, L); };
+    auto bcast_d = [&](double v, int src) { return __shfl_sync(SPEC_FULL, v, src, L); };
+    // window offset of a batch prefetched now: smem window index of unwrapped position p is wofs + p
+    auto window_ofs = [&](int gm_now) { return (gm_now & 1) + 4 - pg; };
+
+    // ---- this lane's contribution to the energy of step `sn` (descriptor dn): its restraint term, plus
+    //      energy + logZ in lane 0.  A: on the committed state, B: on the committed state shifted by the
+    //      pending step (d0, g0).  Window misses are only flagged here (out-of-line path re-evaluates).
+    struct Cand { double xA, xB; int d1, g1; bool own, miss; };
+    auto evaluate = [&](uint32_t dn, int sn, int wofs, int d0_, int g0_) {
+        Cand k;
+        const bool nuis_n = (int)dn < 0;
+        k.own = (dn & 0x8000000Fu) == own_tag;
+        k.d1 = k.own ? (int)((dn >> 4) & 3u) - 1 : 0;
+        k.g1 = k.own ? (int)((dn >> 6) & 3u) - 1 : 0;
+        const uint32_t eA = ent_base + (uint32_t)(SPEC_ENT_BYTES * (sg + k.d1));   // unwrapped: entries carry a halo of 2
+        const uint32_t eB = eA + (uint32_t)(SPEC_ENT_BYTES * d0_);
+        const double nlA = lds64(eA), dvA = lds64(eA + 8), yA = lds64(eA + 16);
+        const double nlB = lds64(eB), dvB = lds64(eB + 8), yB = lds64(eB + 16);
+        const uint32_t slot = slots + (uint32_t)(sn & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
+        const double2 rv = lds128(nuis_n ? cur_rec : slot + 16 * qr);
+        double numA = rv.x, numB = rv.x;
+        k.miss = false;
+        if (HG) {
+            const int wi = wofs + pg;                        // window index of the current position (state move)
+            const bool out = (unsigned)(wi - 1) > 7u;        // wi +- 1 must stay inside the 10-wide window
+            const int ia = nuis_n ? gm + 4 + k.g1 : (out ? 4 : wi);
+            const uint32_t na = (nuis_n ? cur_row : slot + ly.slot_win) + 8u * (uint32_t)ia;
+            if (glane) {
+                numA = lds64(na);
+                numB = lds64(na + (uint32_t)(8 * g0_));
+            }
+            k.miss = glane && !nuis_n && out;
+        }
+        double Cn = Cst;
+        if (!nuis_n && q == 0) Cn = __dadd_rn(lds64(slot + ly.slot_c), logZ);
+        double t = __dadd_rn(nlA, div_markstein(numA, dvA, yA));
+        t = __dadd_rn(t, cnorm);
+        t = __dsub_rn(t, rv.y);
+        k.xA = __dadd_rn(t, Cn);
+        t = __dadd_rn(nlB, div_markstein(numB, dvB, yB));
+        t = __dadd_rn(t, cnorm);
+        t = __dsub_rn(t, rv.y);
+        k.xB = __dadd_rn(t, Cn);
+        return k;
+    };
+    // the same on the committed state only, gamma value of a proposed state read from global memory
+    auto evaluate_exact = [&](uint32_t dn, int sn, int d1, int g1) {
+        const bool nuis_n = (int)dn < 0;
+        const uint32_t eA = ent_base + (uint32_t)(SPEC_ENT_BYTES * (sg + d1));
+        const double nlA = lds64(eA), dvA = lds64(eA + 8), yA = lds64(eA + 16);
+        const uint32_t slot = slots + (uint32_t)(sn & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
+        const double2 rv = lds128(nuis_n ? cur_rec : slot + 16 * qr);
+        double num = rv.x;
+        if (HG) {
+            if (glane) num = nuis_n ? lds64(cur_row + 8u * (uint32_t)(gm + 4 + g1)) : __ldg(gh4 + (size_t)dn * GS + (gm + 4));
+        }
+        double Cn = Cst;
+        if (!nuis_n && q == 0) Cn = __dadd_rn(lds64(slot + ly.slot_c), logZ);
+        double t = __dadd_rn(nlA, div_markstein(num, dvA, yA));
+        t = __dadd_rn(t, cnorm);
+        t = __dsub_rn(t, rv.y);
+        return __dadd_rn(t, Cn);
+    };
+
+    // ---- pending step (to be resolved next) and the commit of a decision ---------------------------
+    uint32_t desc_s;
+    float lu_s;
+    double x_prop;
+    int d0, g0;
+    bool own_s;
+    auto commit = [&](bool acc, int s, double En) {
+        const bool accown = acc && own_s;
+        const bool rec_on = s > burn;
+        E = acc ? En : E;
+        acc_total += acc ? 1u : 0u;
+        acc_own += accown ? 1u : 0u;
+        {
+            int v = sg + d0;
+            v += v < 0 ? nsig : 0;
+            v -= v >= nsig ? nsig : 0;
+            const int sg_new = accown ? v : sg;
+            const bool ch = rec_on && sg_new != sg;
+            red_add_if(g_sigma_hist + sg, (unsigned int)(s - since_sg), ch && owner);
+            since_sg = ch ? s : since_sg;
+            sg = sg_new;
+        }
+        if (HG) {
+            int v = gm + g0;
+            v += v < 0 ? G : 0;
+            v -= v >= G ? G : 0;
+            const int gm_new = accown ? v : gm;
+            const bool ch = rec_on && gm_new != gm;
+            red_add_if(g_gamma_hist + gm, (unsigned int)(s - since_gm), ch && live);
+            since_gm = ch ? s : since_gm;
+            gm = gm_new;
+            pg += accown ? g0 : 0;
+        }
+    };
+
+    // ---- prologue: batches 0 .. D-1 generated and prefetched, contribution of step 0 ----------------
+    SpecGen gen[D];
+    int wofs[D + 1];
+    {
+        const int gm_b = HG ? bcast_i(gm, R - 1) : 0;
+#pragma unroll
+        for (int b = 0; b < D; ++b) {
+            philox_begin(b * L + q);
+#pragma unroll
+            for (int r = 0; r < 10; ++r) philox_round();
+            gen[b] = philox_finish(b * L + q);
+            prefetch(gen[b], b * L + q, gm_b);
+            wofs[b] = window_ofs(gm_b);
+        }
+        wofs[D] = wofs[0];
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        desc_s = bcast_u(gen[0].desc, 0);
+        lu_s = bcast_f(gen[0].lu, 0);
+        own_s = (desc_s & 0x8000000Fu) == own_tag;
+        d0 = own_s ? (int)((desc_s >> 4) & 3u) - 1 : 0;
+        g0 = own_s ? (int)((desc_s >> 6) & 3u) - 1 : 0;
+        x_prop = evaluate_exact(desc_s, 0, d0, g0);
+    }
+
+    for (int s0 = 0; s0 < s_end; s0 += L) {
+        philox_begin(s0 + D * L + q);                        // the batch generated during this one
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+            const int s = s0 + j;
+            // Philox rounds scheduled into this step
+#pragma unroll
+            for (int r = 0; r < 10; ++r)
+                if (r * L / 10 == j) philox_round();
+            // the proposals of the next batch are first read by the last step of this one
+            if (j == L - 1) {
+                cp_async_wait<D - 2>();
+                __syncwarp();
+            }
+            // descriptor of step s+1 (from this batch's or the next batch's generating lane)
+            constexpr int dummy = 0; (void)dummy;
+            const bool nb = j + 1 == L;
+            const uint32_t desc_n = bcast_u(nb ? gen[1].desc : gen[0].desc, (j + 1) & (L - 1));
+            const float lu_n = bcast_f(nb ? gen[1].lu : gen[0].lu, (j + 1) & (L - 1));
+
+            // (1) resolve step s: energy in the reference's summation order, accept in the log domain
+            double En = bcast_d(x_prop, 0);
+#pragma unroll
+            for (int r = 1; r < R; ++r) En = __dadd_rn(En, bcast_d(x_prop, r));
+            const double d = __dsub_rn(E, En);
+            const float tt = (float)d - lu_s;
+            const bool acc_f = tt > SPEC_MARGIN;
+            const bool unsure = !acc_f && !(tt < -SPEC_MARGIN);          // guard band, also NaN
+            const bool state_s = (int)desc_s >= 0;
+
+            // (2) contributions to step s+1 under both outcomes of step s
+            const Cand k = evaluate(desc_n, s + 1, nb ? wofs[1] : wofs[0], d0, g0);
+
+            // (3) commit; everything rare goes through one out-of-line path
+            const bool rare = __any_sync(SPEC_FULL, unsure || (acc_f && state_s) || k.miss) || s == next_ev;
+            if (__builtin_expect(rare, 0)) {
+                const double u = bcast_d(gen[0].u, j);
+                const bool exact = s < s_end && ((En < E) || (d >= BCP_ACCEPT_CUTOFF && u < exp_det(d)));
+                const bool acc = unsure ? exact : acc_f;
+                commit(acc, s, En);
+                const bool accst = acc && state_s;
+                const bool redo = __any_sync(SPEC_FULL, accst || k.miss);
+                if (__any_sync(SPEC_FULL, accst)) {
+                    if (accst) {       // adopt the slot as the current state, reload the gamma row
+                        const int i2 = (int)desc_s;
+                        const uint32_t slot = slots + (uint32_t)(s & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
+                        if (q < R) sts128(cur_rec, lds128(slot + 16 * qr));
+                        if (q == 0) Cst = __dadd_rn(lds64(slot + ly.slot_c), logZ);
+                        ++acc_state;
+                        if (i2 != state) {
+                            if (s > burn && lead)
+                                atomicAdd(g_state_counts + state, (unsigned long long)(s - since_state));
+                            if (s > burn) since_state = s;
+                            state = i2;
+                        }
+                        if (HG) {
+                            const double2* src = reinterpret_cast<const double2*>(gh4 + (size_t)i2 * GS);
+                            for (int kk = q; kk < GS / 2; kk += L) sts128(cur_row + 16 * kk, __ldg(src + kk));
+                        }
+                    }
+                    __syncwarp();
+                }
+                x_prop = redo ? evaluate_exact(desc_n, s + 1, k.d1, k.g1) : (acc ? k.xB : k.xA);
+                if (s >= burn && s < s_end) {
+                    if (A.state_trace && lead) A.state_trace[(size_t)(A.s_begin + s - A.burn) * n + c] = state;
+                    if (s == next_snap) {
+                        const size_t o = (size_t)snap_idx * n + c;
+                        if (lead) {
+                            A.traj_E[o] = E;
+                            A.traj_state[o] = state;
+                            A.traj_accept[o] = acc ? 1 : 0;
+                        }
+                        if (owner) A.traj_idx[((size_t)snap_idx * T.P + q) * n + c] = sg;
+                        if (HG && glane && live) A.traj_idx[((size_t)snap_idx * T.P + R) * n + c] = gm;
+                        ++snap_idx;
+                        const long long ns = (long long)next_snap + A.traj_every;
+                        next_snap = ns < s_end ? (int)ns : -1;
+                    }
+                }
+                next_ev = A.state_trace ? s + 1 : next_snap;
+            } else {
+                commit(acc_f, s, En);
+                x_prop = acc_f ? k.xB : k.xA;
+            }
+            desc_s = desc_n; lu_s = lu_n; d0 = k.d1; g0 = k.g1; own_s = k.own;
+        }
+        // end of batch: finish the generated batch, prefetch its state moves, rotate
+        {
+            const int sb = s0 + D * L + q;
+            const SpecGen g = philox_finish(sb);
+            const int gm_now = HG ? bcast_i(gm, R - 1) : 0;
+            prefetch(g, sb, gm_now);
+            cp_async_commit();
+            wofs[D] = window_ofs(gm_now);
+#pragma unroll
+            for (int b = 0; b + 1 < D; ++b) gen[b] = gen[b + 1];
+            gen[D - 1] = g;
+#pragma unroll
+            for (int b = 0; b < D; ++b) wofs[b] = wofs[b + 1];
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- flush run-length counters, persist the chain -------------------------------------
+    if (lead) {
+        if (s_end > since_state) atomicAdd(g_state_counts + state, (unsigned long long)(s_end - since_state));
+        C.state[c] = state;
+        C.E[c] = E;
+        C.accepted[c] += acc_total;
+        C.sep[(size_t)R * n + c] += acc_state;
+    }
+    if (owner) {
+        if (s_end > since_sg) atomicAdd(g_sigma_hist + sg, (unsigned long long)(s_end - since_sg));
+        C.isg[(size_t)q * n + c] = sg;
+        C.sep[(size_t)q * n + c] += acc_own;
+    }
+    if (HG && glane && live) {
+        if (s_end > since_gm) atomicAdd(g_gamma_hist + gm, (unsigned long long)(s_end - since_gm));
+        C.igm[(size_t)(R - 1) * n + c] = gm;
+    }
+}
+
+template <int L, int R, bool HG>
+static cudaError_t launch_spec_one(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st,
+                                   int sms) {
+    const SpecLayout ly = spec_layout(L, R, HG, T.gh4_stride);
+    const long long threads = C.n_chains * L;
+    const long long n_warps = (threads + 31) / 32;
+    int wpb = (int)((n_warps + sms - 1) / sms);
+    wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
+    int dev = 0, max_optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    size_t smem = 0;
+    for (; wpb >= 1; --wpb) {
+        smem = (size_t)T.sig4_bytes + (size_t)(wpb * 32 / L) * ly.chain_bytes + 128;
+        if (smem + 64 <= (size_t)max_optin) break;
+    }
+    if (wpb < 1) return cudaErrorNotSupported;
+    cudaError_t e = cudaFuncSetAttribute(mcmc_spec_kernel<L, R, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int block = wpb * 32;
+    const int grid = (int)((threads + block - 1) / block);
+    mcmc_spec_kernel<L, R, HG><<<grid, block, smem, st>>>(T, C, A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mcmc_spec(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms) {
+    if (!T.canonical || !T.div_safe || T.R < 1 || T.R > 8 || T.S < 1) return cudaErrorNotSupported;
+    const bool hg = T.r[T.R - 1].has_gamma != 0;
+#define BCP_SPEC(l, r)                                                                              \
+    case r:                                                                                         \
+        return hg ? launch_spec_one<l, r, true>(T, C, A, st, sms) : launch_spec_one<l, r, false>(T, C, A, st, sms);
+    switch (T.R) {          // L = smallest of 2, 4, 8 that holds one lane per restraint
+        BCP_SPEC(2, 1) BCP_SPEC(2, 2) BCP_SPEC(4, 3) BCP_SPEC(4, 4)
+        BCP_SPEC(8, 5) BCP_SPEC(8, 6) BCP_SPEC(8, 7) BCP_SPEC(8, 8)
+        default: return cudaErrorNotSupported;
+    }
+#undef BCP_SPEC
+}
+
+}  // namespace bcp

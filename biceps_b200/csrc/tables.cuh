@@ -57,12 +57,20 @@ struct SamplerTables {
     // window around any gamma index is contiguous and needs no wrap arithmetic:
     // gsse_halo[i][k] = sse[i][(k - 2) mod G], k in [0, G+4)
     const double* gsse_halo;
-    // for the two-steps-per-iteration kernel: the same rows with a 3-element halo (7-wide windows),
-    // gsse_halo3[i][k] = sse[i][(k - 3) mod G], k in [0, G+6), and 16-byte aligned plain rows
-    // gsse_rows[i][k], k in [0, gamma_row_stride), gamma_row_stride = G rounded up to even
-    const double* gsse_halo3;
-    const double* gsse_rows;
-    int gamma_row_stride;
+    // for the speculative kernel (sampler_spec.cu): the same rows with a 4-element periodic halo,
+    // gsse_halo4[i][k] = sse[i][(k - 4) mod G], k in [0, gh4_stride), gh4_stride = G + 9 rounded up
+    // to even (16-byte aligned rows; any 9-wide window around a gamma index, widened to an aligned
+    // 10-wide one, stays inside the row)
+    const double* gsse_halo4;
+    int gh4_stride;
+    // packed sigma entries with a 2-element periodic halo: restraint q owns entries
+    // [ent_off, ent_off + n_sigma + 4), entry e <-> sigma index e - 2 (mod n_sigma), each entry
+    // the three doubles {Ndof ln sigma, 2 sigma^2, RN(1 / (2 sigma^2))} (24-byte stride: neighbouring
+    // entries fall into different shared-memory banks)
+    int sig4_bytes;         // multiple of 16
+    const double* sig4;
+    int ent_off[MAXR];
+    int div_safe;           // every sse / 2 sigma^2 is far from under/overflow (Markstein division is exact)
     int pad2;
     int rec_stride;         // 2 * R doubles
     int canonical;          // 1 if the specialised kernel applies

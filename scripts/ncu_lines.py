@@ -8,7 +8,7 @@ for r in rows:
     if len(r) == 2 and r[0] == 'File Path': cur = r[1].split('/')[-1]; continue
     if len(r) < 8 or r[0] == 'Line No': continue
     if r[0] != '':
-        key = (cur, int(r[0]), r[1].strip()[:90]); per[key] = per.get(key, 0) + int(r[7])
+        key = (cur, int(r[0]), r[1].strip()[:90]); per[key] = per.get(key, 0) + (int(r[7]) if r[7].isdigit() else 0)
     elif r[3] not in ('-', '') and r[7] not in ('-', ''):
         t = r[3].split(); op = t[1] if t[0].startswith('@') else t[0]
         ops[op.split('.')[0] if not op.startswith('IMAD') else op] += int(r[7]); tot += int(r[7])
