@@ -59,6 +59,19 @@ static inline cudaError_t dev_alloc(T** p, size_t n) {
     return cudaMalloc((void**)p, n * sizeof(T));
 }
 
+// stream-ordered allocation on the legacy default stream: with the pool's release threshold raised
+// (keep_pool_memory) a create/destroy cycle recycles the same blocks and costs microseconds, where
+// cudaMalloc/cudaFree cost ~0.5 ms each and synchronise the device
+template <typename T>
+static inline cudaError_t pool_alloc(T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) return cudaSuccess;
+    return cudaMallocAsync((void**)p, n * sizeof(T), (cudaStream_t)0);
+}
+static inline void pool_free(void* p) {
+    if (p) cudaFreeAsync(p, (cudaStream_t)0);
+}
+
 // keep the stream-ordered pool's memory across synchronisations (the default release threshold of 0
 // gives every block back to the driver at each sync, which makes cudaMallocAsync as slow as cudaMalloc)
 void keep_pool_memory(int device);

@@ -261,6 +261,38 @@ __global__ void neglogp_kernel(const SamplerTables T, long long n, const int* la
     out[i] = E;
 }
 
+// canonical layout (tables.cuh) from the uploaded per-restraint tables: packed records, the gamma
+// restraint's rows with periodic halos of 2 and 4, and the range check behind SamplerTables::div_safe
+__global__ void build_layouts_kernel(const SamplerTables T, double* rec, double* halo2, double* halo4, int* bad) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int R = T.R;
+    const int width = T.gh4_stride > 2 * R ? T.gh4_stride : 2 * R;
+    const long long i = idx / width;
+    const int k = (int)(idx - i * width);
+    if (i >= T.S) return;
+    bool flag = false;
+    if (k < 2 * R) {
+        const int q = k >> 1;
+        const RestraintDev& rd = T.r[q];
+        double v;
+        if (k & 1) v = rd.refsum ? rd.refsum[i] : 0.0;
+        else {
+            v = rd.has_gamma ? 0.0 : rd.sse[i];
+            flag = !(v == 0.0 || (v > 1e-140 && v < 1e140));
+        }
+        rec[i * (2 * R) + k] = v;
+    }
+    if (halo4 && k < T.gh4_stride) {
+        const int G = T.r[R - 1].n_gamma;
+        const double* src = T.r[R - 1].sse + i * G;
+        const double v = src[((k - 4) % G + G) % G];
+        halo4[i * T.gh4_stride + k] = v;
+        if (k < G + 4) halo2[i * (G + 4) + k] = src[((k - 2) % G + G) % G];
+        flag = flag || !(v == 0.0 || (v > 1e-140 && v < 1e140));
+    }
+    if (flag) *bad = 1;
+}
+
 }  // namespace bcp
 
 using namespace bcp;
@@ -294,7 +326,9 @@ struct bcp_chains {
     int* d_trace = nullptr;
     size_t cap_snap = 0, cap_trace = 0;
     cudaStream_t last_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk = nullptr;
+    cudaStream_t copy_stream = nullptr;     // device -> host copies of finished snapshots (bcp_sample)
+    long long snaps_piped = 0;
     int last_launches = 0;
     bool sampled = false;
 };
@@ -303,7 +337,7 @@ template <typename T>
 static int upload(bcp_handle* h, const T* host, size_t n, const T** dev) {
     T* d = nullptr;
     if (n == 0) { *dev = nullptr; return BCP_OK; }
-    BCP_CUDA(cudaMalloc((void**)&d, n * sizeof(T)));
+    BCP_CUDA(pool_alloc(&d, n));
     h->allocs.push_back(d);
     BCP_CUDA(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
     *dev = d;
@@ -408,32 +442,33 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
     T.rec_stride = 2 * T.R;
     T.rec = nullptr;
     if (T.canonical) {
-        std::vector<double> rec((size_t)T.S * T.rec_stride, 0.0);
-        for (int q = 0; q < T.R; ++q) {
-            const bcp_restraint& r = t->restraints[q];
-            for (int i = 0; i < T.S; ++i) {
-                rec[(size_t)i * T.rec_stride + 2 * q] = (T.r[q].has_gamma || !r.sse) ? 0.0 : r.sse[i];
-                rec[(size_t)i * T.rec_stride + 2 * q + 1] = r.has_ref ? r.refsum[i] : 0.0;
-            }
-        }
-        if ((rc = upload(h, rec.data(), rec.size(), &T.rec)) != BCP_OK) return fail(rc);
+        // derived layouts are built on the device from the uploaded tables (a host-side build of the
+        // 2 x 13 MB halo tables dominated bcp_create)
+        double* d_rec = nullptr;
+        if (pool_alloc(&d_rec, (size_t)T.S * T.rec_stride) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
+        h->allocs.push_back(d_rec);
+        T.rec = d_rec;
         T.gsse_halo = nullptr; T.gsse_halo4 = nullptr; T.gh4_stride = 0;
+        double *d_h2 = nullptr, *d_h4 = nullptr;
+        int G = 1;
         if (T.r[T.R - 1].has_gamma) {
-            const int G = T.r[T.R - 1].n_gamma;
-            const double* src = t->restraints[T.R - 1].sse;
-            std::vector<double> halo((size_t)T.S * (G + 4));
-            for (int i = 0; i < T.S; ++i)
-                for (int k = 0; k < G + 4; ++k)
-                    halo[(size_t)i * (G + 4) + k] = src[(size_t)i * G + ((k - 2) % G + G) % G];
-            if ((rc = upload(h, halo.data(), halo.size(), &T.gsse_halo)) != BCP_OK) return fail(rc);
-            const int GS = (G + 9 + 1) & ~1;
-            std::vector<double> halo4((size_t)T.S * GS);
-            for (int i = 0; i < T.S; ++i)
-                for (int k = 0; k < GS; ++k)
-                    halo4[(size_t)i * GS + k] = src[(size_t)i * G + ((k - 4) % G + G) % G];
-            T.gh4_stride = GS;
-            if ((rc = upload(h, halo4.data(), halo4.size(), &T.gsse_halo4)) != BCP_OK) return fail(rc);
+            G = T.r[T.R - 1].n_gamma;
+            T.gh4_stride = (G + 9 + 1) & ~1;
+            if (pool_alloc(&d_h2, (size_t)T.S * (G + 4)) != cudaSuccess || pool_alloc(&d_h4, (size_t)T.S * T.gh4_stride) != cudaSuccess) {
+                if (d_h2) h->allocs.push_back(d_h2);
+                set_error("bcp_create: out of device memory");
+                return fail(BCP_ERR_CUDA);
+            }
+            h->allocs.push_back(d_h2); h->allocs.push_back(d_h4);
+            T.gsse_halo = d_h2; T.gsse_halo4 = d_h4;
         }
+        int* d_flag = nullptr;
+        if (pool_alloc(&d_flag, 1) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
+        h->allocs.push_back(d_flag);
+        cudaMemsetAsync(d_flag, 0, sizeof(int), 0);
+        const long long work = (long long)T.S * (T.gh4_stride > 2 * T.R ? T.gh4_stride : 2 * T.R);
+        build_layouts_kernel<<<(unsigned)((work + 255) / 256), 256>>>(T, d_rec, d_h2, d_h4, d_flag);
+        BCP_LAUNCHED(1);
         // packed sigma entries for the speculative kernel; 1 / (2 sigma^2) is the correctly rounded
         // IEEE reciprocal (host division), which is what makes the device-side Markstein division exact
         std::vector<double> sig4;
@@ -448,15 +483,16 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
                 if (!(d > 1e-140 && d < 1e140)) T.div_safe = 0;
                 sig4.push_back(r.nlsig[k]); sig4.push_back(d); sig4.push_back(1.0 / d);
             }
-            const size_t cnt = (size_t)T.S * T.r[q].n_gamma;
-            for (size_t k = 0; k < cnt && T.div_safe; ++k) {
-                const double v = r.sse[k];
-                if (!(v == 0.0 || (v > 1e-140 && v < 1e140))) T.div_safe = 0;
-            }
         }
         while (sig4.size() % 2) sig4.push_back(0.0);
         T.sig4_bytes = (int)(sig4.size() * sizeof(double));
         if ((rc = upload(h, sig4.data(), sig4.size(), &T.sig4)) != BCP_OK) return fail(rc);
+        int flag = 0;
+        if (cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("bcp_create: layout kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(BCP_ERR_CUDA);
+        }
+        if (flag) T.div_safe = 0;       // some sse value is not finite or far outside the normal range
     }
     if ((rc = upload(h, t->energy, (size_t)T.K * T.S, &T.energy)) != BCP_OK) return fail(rc);
     if ((rc = upload(h, t->logZ, (size_t)T.K, &T.logZ)) != BCP_OK) return fail(rc);
@@ -468,7 +504,7 @@ extern "C" void bcp_destroy(bcp_handle* h) {
     if (!h) return;
     if (--h->refs > 0) return;      // chains still alive: the last bcp_chains_destroy frees the tables
     DeviceGuard guard(h->device);
-    for (void* p : h->allocs) cudaFree(p);
+    for (void* p : h->allocs) pool_free(p);
     delete h;
 }
 
@@ -514,28 +550,28 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
     C.n_chains = n; C.seed = cfg->seed; C.chain_id0 = cfg->chain_id0;
     auto fail = [&](int code) { bcp_chains_destroy(c); return code; };
 #define TRY_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(e_)); return fail(BCP_ERR_CUDA); } } while (0)
-    TRY_CUDA(dev_alloc(&c->d_lam, n));
-    TRY_CUDA(dev_alloc(&c->d_group, n));
+    TRY_CUDA(pool_alloc(&c->d_lam, n));
+    TRY_CUDA(pool_alloc(&c->d_group, n));
     TRY_CUDA(cudaMemcpy(c->d_lam, lam.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     TRY_CUDA(cudaMemcpy(c->d_group, grp.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     C.lam = c->d_lam; C.group = c->d_group;
-    TRY_CUDA(dev_alloc(&C.state, n));
-    TRY_CUDA(dev_alloc(&C.isg, (size_t)T.R * n));
-    TRY_CUDA(dev_alloc(&C.igm, (size_t)T.R * n));
+    TRY_CUDA(pool_alloc(&C.state, n));
+    TRY_CUDA(pool_alloc(&C.isg, (size_t)T.R * n));
+    TRY_CUDA(pool_alloc(&C.igm, (size_t)T.R * n));
     C.ipf = nullptr;
-    if (T.pf.q >= 0) TRY_CUDA(dev_alloc(&C.ipf, (size_t)BCP_PF_NGRID * n));
-    TRY_CUDA(dev_alloc(&C.E, n));
-    TRY_CUDA(dev_alloc(&C.accepted, n));
-    TRY_CUDA(dev_alloc(&C.sep, (size_t)(T.R + 1) * n));
-    TRY_CUDA(dev_alloc(&C.state_counts, (size_t)n_groups * T.S));
-    TRY_CUDA(dev_alloc(&C.param_counts, (size_t)n_groups * T.HB));
+    if (T.pf.q >= 0) TRY_CUDA(pool_alloc(&C.ipf, (size_t)BCP_PF_NGRID * n));
+    TRY_CUDA(pool_alloc(&C.E, n));
+    TRY_CUDA(pool_alloc(&C.accepted, n));
+    TRY_CUDA(pool_alloc(&C.sep, (size_t)(T.R + 1) * n));
+    TRY_CUDA(pool_alloc(&C.state_counts, (size_t)n_groups * T.S));
+    TRY_CUDA(pool_alloc(&C.param_counts, (size_t)n_groups * T.HB));
     TRY_CUDA(cudaMemset(C.accepted, 0, n * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.sep, 0, (size_t)(T.R + 1) * n * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.state_counts, 0, (size_t)n_groups * T.S * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.param_counts, 0, (size_t)n_groups * T.HB * sizeof(unsigned long long)));
     int* d_init = nullptr;
     if (cfg->init_state) {
-        TRY_CUDA(dev_alloc(&d_init, n));
+        TRY_CUDA(pool_alloc(&d_init, n));
         TRY_CUDA(cudaMemcpy(d_init, cfg->init_state, n * sizeof(int), cudaMemcpyHostToDevice));
     }
     const int tpb = 256;
@@ -544,7 +580,7 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
     BCP_LAUNCHED(1);
     TRY_CUDA(cudaGetLastError());
     TRY_CUDA(cudaDeviceSynchronize());
-    if (d_init) cudaFree(d_init);
+    if (d_init) pool_free(d_init);
     TRY_CUDA(cudaEventCreate(&c->ev0));
     TRY_CUDA(cudaEventCreate(&c->ev1));
 #undef TRY_CUDA
@@ -555,11 +591,14 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
 extern "C" void bcp_chains_destroy(bcp_chains* c) {
     if (!c) return;
     DeviceGuard guard(c->h->device);
-    cudaFree(c->d_lam); cudaFree(c->d_group);
-    cudaFree(c->C.state); cudaFree(c->C.isg); cudaFree(c->C.igm); cudaFree(c->C.ipf); cudaFree(c->C.E);
-    cudaFree(c->C.accepted); cudaFree(c->C.sep); cudaFree(c->C.state_counts); cudaFree(c->C.param_counts);
-    cudaFree(c->d_traj_E); cudaFree(c->d_traj_state); cudaFree(c->d_traj_accept); cudaFree(c->d_traj_idx);
-    cudaFree(c->d_trace);
+    if (c->sampled) cudaStreamSynchronize(c->last_stream);      // frees are ordered on the default stream only
+    pool_free(c->d_lam); pool_free(c->d_group);
+    pool_free(c->C.state); pool_free(c->C.isg); pool_free(c->C.igm); pool_free(c->C.ipf); pool_free(c->C.E);
+    pool_free(c->C.accepted); pool_free(c->C.sep); pool_free(c->C.state_counts); pool_free(c->C.param_counts);
+    pool_free(c->d_traj_E); pool_free(c->d_traj_state); pool_free(c->d_traj_accept); pool_free(c->d_traj_idx);
+    pool_free(c->d_trace);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_chunk) cudaEventDestroy(c->ev_chunk);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     bcp_handle* h = c->h;
@@ -580,7 +619,10 @@ static cudaError_t launch_mcmc(const SamplerTables& T, const ChainBuffers& C, co
 // counters far from overflow
 static const long long kMaxStepsPerLaunch = 1ll << 22;
 
-extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void* stream) {
+// Launches the Metropolis kernel(s) for one sample() call.  pipe != nullptr (host-buffer API with
+// page-locked trajectory buffers): the call is cut into a few launches and the snapshots a launch
+// completed are copied to the host on a second stream while the next launch runs.
+static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* stream, const bcp_sample_out* pipe) {
     BCP_REQUIRE(c && cfg, "bcp_sample_launch: NULL argument");
     BCP_REQUIRE(cfg->n_steps > 0 && cfg->burn >= 0 && cfg->traj_every >= 0,
                 "bcp_sample_launch: n_steps must be > 0, burn and traj_every >= 0");
@@ -592,19 +634,19 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
 
     const long long n_snap = cfg->traj_every > 0 ? (cfg->n_steps + cfg->traj_every - 1) / cfg->traj_every : 0;
     if ((size_t)n_snap * n > c->cap_snap) {
-        cudaFree(c->d_traj_E); cudaFree(c->d_traj_state); cudaFree(c->d_traj_accept); cudaFree(c->d_traj_idx);
+        pool_free(c->d_traj_E); pool_free(c->d_traj_state); pool_free(c->d_traj_accept); pool_free(c->d_traj_idx);
         c->d_traj_E = nullptr; c->d_traj_state = nullptr; c->d_traj_accept = nullptr; c->d_traj_idx = nullptr;
         c->cap_snap = 0;
-        BCP_CUDA(dev_alloc(&c->d_traj_E, (size_t)n_snap * n));
-        BCP_CUDA(dev_alloc(&c->d_traj_state, (size_t)n_snap * n));
-        BCP_CUDA(dev_alloc(&c->d_traj_accept, (size_t)n_snap * n));
-        BCP_CUDA(dev_alloc(&c->d_traj_idx, (size_t)n_snap * n * T.P));
+        BCP_CUDA(pool_alloc(&c->d_traj_E, (size_t)n_snap * n));
+        BCP_CUDA(pool_alloc(&c->d_traj_state, (size_t)n_snap * n));
+        BCP_CUDA(pool_alloc(&c->d_traj_accept, (size_t)n_snap * n));
+        BCP_CUDA(pool_alloc(&c->d_traj_idx, (size_t)n_snap * n * T.P));
         c->cap_snap = (size_t)n_snap * n;
     }
     const long long n_trace = cfg->record_state_trace ? cfg->n_steps : 0;
     if ((size_t)n_trace * n > c->cap_trace) {
-        cudaFree(c->d_trace); c->d_trace = nullptr; c->cap_trace = 0;
-        BCP_CUDA(dev_alloc(&c->d_trace, (size_t)n_trace * n));
+        pool_free(c->d_trace); c->d_trace = nullptr; c->cap_trace = 0;
+        BCP_CUDA(pool_alloc(&c->d_trace, (size_t)n_trace * n));
         c->cap_trace = (size_t)n_trace * n;
     }
     c->n_snap = n_snap; c->n_trace = n_trace;
@@ -646,9 +688,21 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
     }
     BCP_CUDA(cudaEventRecord(c->ev0, st));
     int launches = 0;
-    for (long long s0 = 0; s0 < total; s0 += kMaxStepsPerLaunch) {
+    long long chunk = kMaxStepsPerLaunch;
+    if (pipe && n_snap >= 8) {
+        // ~4 launches, cut on snapshot boundaries
+        const long long te = cfg->traj_every;
+        long long per = ((total + 3) / 4 + te - 1) / te * te;
+        if (per < chunk) chunk = per;
+        if (!c->copy_stream) BCP_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        if (!c->ev_chunk) BCP_CUDA(cudaEventCreateWithFlags(&c->ev_chunk, cudaEventDisableTiming));
+    } else {
+        pipe = nullptr;
+    }
+    long long snaps_copied = 0;
+    for (long long s0 = 0; s0 < total; s0 += chunk) {
         A.s_begin = s0;
-        A.s_end = s0 + kMaxStepsPerLaunch < total ? s0 + kMaxStepsPerLaunch : total;
+        A.s_end = s0 + chunk < total ? s0 + chunk : total;
         cudaError_t e;
         if (T.pf.q >= 0) e = launch_mcmc_pf(T, c->C, A, st);
         else if (which == 3) {
@@ -669,7 +723,23 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
         }
         if (e != cudaSuccess) { set_error("mcmc_kernel launch failed: %s", cudaGetErrorString(e)); return BCP_ERR_CUDA; }
         ++launches;
+        if (pipe) {
+            // snapshots m with burn + m * traj_every < s_end are final once this launch has finished
+            long long done = A.s_end <= cfg->burn ? 0 : (A.s_end - cfg->burn + cfg->traj_every - 1) / cfg->traj_every;
+            if (done > n_snap) done = n_snap;
+            if (done > snaps_copied) {
+                const size_t lo = (size_t)snaps_copied * n, cnt = (size_t)(done - snaps_copied) * n;
+                BCP_CUDA(cudaEventRecord(c->ev_chunk, st));
+                BCP_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk, 0));
+                if (pipe->traj_energy) BCP_CUDA(cudaMemcpyAsync(pipe->traj_energy + lo, c->d_traj_E + lo, cnt * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+                if (pipe->traj_state) BCP_CUDA(cudaMemcpyAsync(pipe->traj_state + lo, c->d_traj_state + lo, cnt * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+                if (pipe->traj_accept) BCP_CUDA(cudaMemcpyAsync(pipe->traj_accept + lo, c->d_traj_accept + lo, cnt, cudaMemcpyDeviceToHost, c->copy_stream));
+                if (pipe->traj_indices) BCP_CUDA(cudaMemcpyAsync(pipe->traj_indices + lo * T.P, c->d_traj_idx + lo * T.P, cnt * T.P * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+                snaps_copied = done;
+            }
+        }
     }
+    c->snaps_piped = pipe ? snaps_copied : 0;
     BCP_LAUNCHED(launches);
     BCP_CUDA(cudaEventRecord(c->ev1, st));
     c->steps_done += (unsigned long long)total;
@@ -677,6 +747,10 @@ extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void*
     c->last_launches = launches;
     c->sampled = true;
     return BCP_OK;
+}
+
+extern "C" int bcp_sample_launch(bcp_chains* c, const bcp_sample_cfg* cfg, void* stream) {
+    return sample_launch_impl(c, cfg, stream, nullptr);
 }
 
 extern "C" int bcp_chains_sync(bcp_chains* c) {
@@ -782,11 +856,31 @@ extern "C" int bcp_chains_set_state(bcp_chains* c, const int32_t* state, const i
     return BCP_OK;
 }
 
+static bool is_pinned(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int bcp_sample(bcp_chains* c, const bcp_sample_cfg* cfg, bcp_sample_out* out) {
-    int rc = bcp_sample_launch(c, cfg, nullptr);
+    const bool pipe = out && cfg && cfg->traj_every > 0 && out->traj_energy && is_pinned(out->traj_energy) &&
+                      is_pinned(out->traj_state) && is_pinned(out->traj_accept) && is_pinned(out->traj_indices);
+    int rc = sample_launch_impl(c, cfg, nullptr, pipe ? out : nullptr);
     if (rc != BCP_OK) return rc;
-    if (out) return bcp_chains_fetch(c, out);
-    return bcp_chains_sync(c);
+    if (!out) return bcp_chains_sync(c);
+    if (c->snaps_piped > 0) {
+        // the trajectory went out chunk by chunk on the copy stream; fetch everything else
+        DeviceGuard guard(c->h->device);
+        bcp_sample_out rest = *out;
+        BCP_REQUIRE(c->snaps_piped == c->n_snap, "bcp_sample: internal error, %lld of %lld snapshots copied",
+                    c->snaps_piped, c->n_snap);
+        rest.traj_energy = nullptr; rest.traj_state = nullptr; rest.traj_accept = nullptr; rest.traj_indices = nullptr;
+        rc = bcp_chains_fetch(c, &rest);
+        BCP_CUDA(cudaStreamSynchronize(c->copy_stream));
+        return rc;
+    }
+    return bcp_chains_fetch(c, out);
 }
 
 extern "C" int bcp_neglogp(bcp_handle* h, int64_t n, const int32_t* lam, const int32_t* state,

@@ -27,10 +27,12 @@
 //     spread over the L steps of the batch D batches earlier (software pipelined by hand).
 //   * The sigma vectors {Ndof ln sigma, 2 sigma^2, 1/(2 sigma^2)} of all restraints are staged once per
 //     CTA by a 1-D TMA bulk copy (UBLKCP).
-//   * One step is ONE basic block: histogram flushes are predicated REDs, and everything rare (guard band
-//     of the accept test, an accepted state move = record copy + gamma row reload, a gamma index that
-//     drifted out of a prefetched window, a trajectory snapshot / state-trace store) sits behind a single
-//     warp-uniform, out-of-line branch that re-does the step's commit exactly.
+//   * One step is ONE basic block.  ptxas turns every predicated RED into a divergent branch, so the
+//     run-length histogram flushes are not issued in the step: a lane appends {bin, count} to a per-warp
+//     queue in shared memory (ballot + popc, predicated STS) and the queue is drained by one RED per
+//     batch.  Everything rare (guard band of the accept test, an accepted state move = record copy +
+//     gamma row reload, a gamma index that drifted out of a prefetched window, a trajectory snapshot /
+//     state-trace store) sits behind a single warp-uniform branch that re-does the step's commit exactly.
 // Same RNG stream, same fp64 operation order and the same outputs as the other kernels (parity with the
 // oracle is bit for bit); canonical restraint layout only (tables.cuh).
 #include "exp_det.cuh"
@@ -79,19 +81,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// predicated histogram flush without a branch (keeps the step a single basic block)
-__device__ __forceinline__ void red_add_if(unsigned long long* p, unsigned int v, bool pred) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        ".reg .u64 w;\n"
-        "setp.ne.b32 p, %2, 0;\n"
-        "cvt.u64.u32 w, %1;\n"
-        "@p red.global.add.u64 [%0], w;\n"
-        "}\n" ::"l"(p), "r"(v), "r"((int)pred)
-        : "memory");
-}
-
 // Metropolis uniform (2k+1) * 2^-53, k = (w2 << 20) | (w3 >> 12)  (== philox.cuh:u2_from_words)
 __device__ __forceinline__ double spec_u2(uint32_t w2, uint32_t w3) {
     const uint32_t hi = 0x3FF00000u | (w2 >> 12);
@@ -100,11 +89,14 @@ __device__ __forceinline__ double spec_u2(uint32_t w2, uint32_t w3) {
     return __dadd_rn(__dadd_rn(one_k, -1.0), 1.1102230246251565e-16);
 }
 
-// One generated step: the proposal packed in 32 bits, ln(u) in fp32 and u itself (guard band only).
-//   nuisance move: bit 31 | restraint (bits 0-3) | dsigma + 1 (bits 4-5) | dgamma + 1 (bits 6-7)
-//   state move:    proposed state (< 2^31)
+// One generated step.  dw, the word every lane of the group reads:
+//   bit 31       nuisance move (else state move)
+//   bits 20+r    restraint r is the one that moves (null moves included: they count as accepted)
+//   bits 2q+1:2q dsigma + 1 of restraint q (1 = unchanged), bits 17:16 dgamma + 1 (1 = unchanged)
+// istate = proposed state of a state move, lu = ln(u) in fp32, u itself is only needed inside the guard band.
+#define SPEC_DW_IDLE 0x00015555u
 struct SpecGen {
-    uint32_t desc;
+    uint32_t dw, istate;
     float lu;
     double u;
 };
@@ -115,7 +107,7 @@ struct SpecLayout {          // byte offsets inside a chain's shared-memory bloc
 
 template <int L>
 struct SpecCfg {
-    static constexpr int D = L == 2 ? 3 : 2;     // batches between the generation of a step and its batch
+    static constexpr int D = 3;                  // batches between the generation of a step and its batch
     static constexpr int NSLOT = 4 * L;          // proposal slots per chain (4 batches, power of two)
 };
 
@@ -154,7 +146,10 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     const bool owner = live && q < R;
     const bool lead = live && q == 0;
     const bool glane = HG && q == R - 1;                    // lane of the gamma restraint
-    const uint32_t own_tag = q < R ? (0x80000000u | (uint32_t)q) : 0xFFFFFFFFu;
+    const uint32_t own_mask = q < R ? (1u << (20 + q)) : 0u;   // this lane's restraint moves
+    const int fsh = 2 * qr;                                  // position of this lane's dsigma field
+    constexpr int GL = R < L ? R : 0;                        // lane that keeps the gamma histogram (an idle lane if any)
+    const bool ghist = HG && live && q == GL;
 
     const int lam = C.lam[c];
     const int grp = C.group[c];
@@ -166,8 +161,8 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     const int G = HG ? T.r[R - 1].n_gamma : 1;
     const int GS = HG ? T.gh4_stride : 0;
     unsigned long long* g_state_counts = C.state_counts + (size_t)grp * T.S;
-    unsigned long long* g_sigma_hist = C.param_counts + (size_t)grp * T.HB + T.r[qr].hist_sigma;
-    unsigned long long* g_gamma_hist = C.param_counts + (size_t)grp * T.HB + (HG ? T.r[R - 1].hist_gamma : 0);
+    const uint32_t sbin0 = (uint32_t)grp * (uint32_t)T.HB + (uint32_t)T.r[qr].hist_sigma;      // bins of C.param_counts
+    const uint32_t gbin0 = (uint32_t)grp * (uint32_t)T.HB + (uint32_t)(HG ? T.r[R - 1].hist_gamma : 0);
     const uint32_t S = (uint32_t)T.S;
     const uint32_t thresh = T.nuis_thresh;
     const int s_end = (int)(A.s_end - A.s_begin);
@@ -183,6 +178,10 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     const uint32_t cur_rec = chain_base + ly.cur_rec + 16 * qr;
     const uint32_t cur_row = chain_base + ly.cur_row;
     const uint32_t slots = chain_base + ly.slot0;
+    // per-warp queue of histogram events {bin, count}: at most 2 per chain and step, 64 per batch
+    const uint32_t evq = smem0 + (uint32_t)T.sig4_bytes + (uint32_t)(blockDim.x / L) * (uint32_t)ly.chain_bytes +
+                         (uint32_t)(threadIdx.x >> 5) * 512u;
+    const uint32_t lane_lt = (1u << (threadIdx.x & 31)) - 1u;
     const int nsig = T.r[qr].n_sigma;
     const uint32_t ent_base = smem0 + (uint32_t)SPEC_ENT_BYTES * (uint32_t)(T.ent_off[qr] + 2);   // entry of sigma index 0
     const double cnorm = T.r[qr].cnorm;
@@ -191,7 +190,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     int state = C.state[c];
     double E = C.E[c];
     int sg = C.isg[(size_t)qr * n + c];
-    int gm = glane ? C.igm[(size_t)(R - 1) * n + c] : 0;
+    int gm = HG ? C.igm[(size_t)(R - 1) * n + c] : 0;        // replicated in every lane of the group
     int pg = gm;                                             // unwrapped gamma position (window bookkeeping)
     // lane 0 adds energy + logZ to its term (reference order (C + t_0) + t_1 ...); x + (-0.0) == x bitwise
     double Cst = q == 0 ? __dadd_rn(energy[state], logZ) : -0.0;
@@ -237,7 +236,9 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         const uint32_t a = (uint32_t)(z1 >> 32);
         const uint32_t b = (HG && hi == (uint32_t)(R - 1)) ? (uint32_t)(z2 >> 32) : 1u;
         SpecGen g;
-        g.desc = nuis ? (0x80000000u | hi | (a << 4) | (b << 6)) : hi;
+        g.dw = nuis ? ((0x80000000u | SPEC_DW_IDLE | (0x00100000u << hi)) ^ ((a ^ 1u) << (2 * hi)) ^ ((b ^ 1u) << 16))
+                    : SPEC_DW_IDLE;
+        g.istate = hi;
         g.u = spec_u2(pc2, pc3);
         // steps past the end of the launch are executed as padding of the last batch: never accepted
         g.lu = s < s_end ? __logf((float)g.u) : __int_as_float(0x7f800000);
@@ -245,8 +246,8 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     };
     // cp.async of the proposed state's words for a generated state move into the step's slot
     auto prefetch = [&](const SpecGen& g, int s, int gm_now) {
-        if (!((int)g.desc < 0)) {
-            const uint32_t i2 = g.desc;
+        if (!((int)g.dw < 0)) {
+            const uint32_t i2 = g.istate;
             const uint32_t slot = slots + (uint32_t)(s & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
             const double* r2 = rec + (size_t)i2 * (2 * R);
 #pragma unroll
@@ -259,40 +260,39 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
             }
         }
     };
-    auto bcast_i = [&](int v, int src) { return __shfl_sync(SPEC_FULL, v, src, L); };
     auto bcast_u = [&](uint32_t v, int src) { return __shfl_sync(SPEC_FULL, v, src, L); };
     auto bcast_f = [&](float v, int src) { return __shfl_sync(SPEC_FULL, v, src, L); };
     auto bcast_d = [&](double v, int src) { return __shfl_sync(SPEC_FULL, v, src, L); };
     // window offset of a batch prefetched now: smem window index of unwrapped position p is wofs + p
-    auto window_ofs = [&](int gm_now) { return (gm_now & 1) + 4 - pg; };
+    auto window_ofs = [&]() { return (gm & 1) + 4 - pg; };
 
-    // ---- this lane's contribution to the energy of step `sn` (descriptor dn): its restraint term, plus
+    // ---- this lane's contribution to the energy of step `sn` (word dn): its restraint term, plus
     //      energy + logZ in lane 0.  A: on the committed state, B: on the committed state shifted by the
     //      pending step (d0, g0).  Window misses are only flagged here (out-of-line path re-evaluates).
     struct Cand { double xA, xB; int d1, g1; bool own, miss; };
     auto evaluate = [&](uint32_t dn, int sn, int wofs, int d0_, int g0_) {
         Cand k;
         const bool nuis_n = (int)dn < 0;
-        k.own = (dn & 0x8000000Fu) == own_tag;
-        k.d1 = k.own ? (int)((dn >> 4) & 3u) - 1 : 0;
-        k.g1 = k.own ? (int)((dn >> 6) & 3u) - 1 : 0;
+        k.own = (dn & own_mask) != 0u;
+        k.d1 = (int)((dn >> fsh) & 3u) - 1;
+        k.g1 = (int)((dn >> 16) & 3u) - 1;
         const uint32_t eA = ent_base + (uint32_t)(SPEC_ENT_BYTES * (sg + k.d1));   // unwrapped: entries carry a halo of 2
         const uint32_t eB = eA + (uint32_t)(SPEC_ENT_BYTES * d0_);
         const double nlA = lds64(eA), dvA = lds64(eA + 8), yA = lds64(eA + 16);
         const double nlB = lds64(eB), dvB = lds64(eB + 8), yB = lds64(eB + 16);
         const uint32_t slot = slots + (uint32_t)(sn & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
-        const double2 rv = lds128(nuis_n ? cur_rec : slot + 16 * qr);
+        const uint32_t recaddr = nuis_n ? cur_rec : slot + 16 * qr;
+        const double2 rv = lds128(recaddr);
         double numA = rv.x, numB = rv.x;
         k.miss = false;
         if (HG) {
+            // branch-free: the other lanes re-read their own sse word (the address of rv.x, stride 0)
             const int wi = wofs + pg;                        // window index of the current position (state move)
             const bool out = (unsigned)(wi - 1) > 7u;        // wi +- 1 must stay inside the 10-wide window
             const int ia = nuis_n ? gm + 4 + k.g1 : (out ? 4 : wi);
-            const uint32_t na = (nuis_n ? cur_row : slot + ly.slot_win) + 8u * (uint32_t)ia;
-            if (glane) {
-                numA = lds64(na);
-                numB = lds64(na + (uint32_t)(8 * g0_));
-            }
+            const uint32_t na = glane ? (nuis_n ? cur_row : slot + ly.slot_win) + 8u * (uint32_t)ia : recaddr;
+            numA = lds64(na);
+            numB = lds64(na + (uint32_t)(glane ? 8 * g0_ : 0));
             k.miss = glane && !nuis_n && out;
         }
         double Cn = Cst;
@@ -307,16 +307,17 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         k.xB = __dadd_rn(t, Cn);
         return k;
     };
-    // the same on the committed state only, gamma value of a proposed state read from global memory
-    auto evaluate_exact = [&](uint32_t dn, int sn, int d1, int g1) {
+    // the same on the committed state only; the gamma value of a proposed state (i2) is read from global memory
+    auto evaluate_exact = [&](uint32_t dn, int sn, uint32_t i2) {
         const bool nuis_n = (int)dn < 0;
+        const int d1 = (int)((dn >> fsh) & 3u) - 1, g1 = (int)((dn >> 16) & 3u) - 1;
         const uint32_t eA = ent_base + (uint32_t)(SPEC_ENT_BYTES * (sg + d1));
         const double nlA = lds64(eA), dvA = lds64(eA + 8), yA = lds64(eA + 16);
         const uint32_t slot = slots + (uint32_t)(sn & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
         const double2 rv = lds128(nuis_n ? cur_rec : slot + 16 * qr);
         double num = rv.x;
         if (HG) {
-            if (glane) num = nuis_n ? lds64(cur_row + 8u * (uint32_t)(gm + 4 + g1)) : __ldg(gh4 + (size_t)dn * GS + (gm + 4));
+            if (glane) num = nuis_n ? lds64(cur_row + 8u * (uint32_t)(gm + 4 + g1)) : __ldg(gh4 + (size_t)i2 * GS + (gm + 4));
         }
         double Cn = Cst;
         if (!nuis_n && q == 0) Cn = __dadd_rn(lds64(slot + ly.slot_c), logZ);
@@ -327,120 +328,160 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     };
 
     // ---- pending step (to be resolved next) and the commit of a decision ---------------------------
-    uint32_t desc_s;
+    uint32_t dw_s;
     float lu_s;
     double x_prop;
-    int d0, g0;
+    int d0, g0;          // this lane's sigma shift and the group's gamma shift if the pending step is accepted
     bool own_s;
-    auto commit = [&](bool acc, int s, double En) {
-        const bool accown = acc && own_s;
+    // commit of step s; returns this lane's histogram event {bin, run length} (count 0 = none)
+    auto commit = [&](bool acc, int s, double En, uint32_t& ev_bin, uint32_t& ev_cnt) {
         const bool rec_on = s > burn;
         E = acc ? En : E;
         acc_total += acc ? 1u : 0u;
-        acc_own += accown ? 1u : 0u;
-        {
-            int v = sg + d0;
-            v += v < 0 ? nsig : 0;
-            v -= v >= nsig ? nsig : 0;
-            const int sg_new = accown ? v : sg;
-            const bool ch = rec_on && sg_new != sg;
-            red_add_if(g_sigma_hist + sg, (unsigned int)(s - since_sg), ch && owner);
-            since_sg = ch ? s : since_sg;
-            sg = sg_new;
-        }
+        acc_own += (acc && own_s) ? 1u : 0u;
+        int v = sg + d0;                                      // d0 == 0 unless this lane's restraint moves
+        v += v < 0 ? nsig : 0;
+        v -= v >= nsig ? nsig : 0;
+        const int sg_new = acc ? v : sg;
+        const bool chs = rec_on && sg_new != sg;
+        uint32_t bin = sbin0 + (uint32_t)sg;
+        int since = since_sg;
+        bool ev = chs && owner;
+        since_sg = chs ? s : since_sg;
+        sg = sg_new;
         if (HG) {
-            int v = gm + g0;
-            v += v < 0 ? G : 0;
-            v -= v >= G ? G : 0;
-            const int gm_new = accown ? v : gm;
-            const bool ch = rec_on && gm_new != gm;
-            red_add_if(g_gamma_hist + gm, (unsigned int)(s - since_gm), ch && live);
-            since_gm = ch ? s : since_gm;
+            int w = gm + g0;                                  // replicated: every lane follows the gamma index
+            w += w < 0 ? G : 0;
+            w -= w >= G ? G : 0;
+            const int gm_new = acc ? w : gm;
+            const bool chg = rec_on && gm_new != gm;
+            const bool evg = chg && ghist;
+            bin = evg ? gbin0 + (uint32_t)gm : bin;
+            since = evg ? since_gm : since;
+            ev = ev || evg;
+            since_gm = chg ? s : since_gm;
             gm = gm_new;
-            pg += accown ? g0 : 0;
+            pg += acc ? g0 : 0;
         }
+        ev_bin = bin;
+        ev_cnt = ev ? (uint32_t)(s - since) : 0u;
     };
 
     // ---- prologue: batches 0 .. D-1 generated and prefetched, contribution of step 0 ----------------
     SpecGen gen[D];
     int wofs[D + 1];
     {
-        const int gm_b = HG ? bcast_i(gm, R - 1) : 0;
 #pragma unroll
         for (int b = 0; b < D; ++b) {
             philox_begin(b * L + q);
 #pragma unroll
             for (int r = 0; r < 10; ++r) philox_round();
             gen[b] = philox_finish(b * L + q);
-            prefetch(gen[b], b * L + q, gm_b);
-            wofs[b] = window_ofs(gm_b);
+            prefetch(gen[b], b * L + q, gm);
+            wofs[b] = window_ofs();
         }
         wofs[D] = wofs[0];
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
-        desc_s = bcast_u(gen[0].desc, 0);
+        dw_s = bcast_u(gen[0].dw, 0);
         lu_s = bcast_f(gen[0].lu, 0);
-        own_s = (desc_s & 0x8000000Fu) == own_tag;
-        d0 = own_s ? (int)((desc_s >> 4) & 3u) - 1 : 0;
-        g0 = own_s ? (int)((desc_s >> 6) & 3u) - 1 : 0;
-        x_prop = evaluate_exact(desc_s, 0, d0, g0);
+        own_s = (dw_s & own_mask) != 0u;
+        d0 = (int)((dw_s >> fsh) & 3u) - 1;
+        g0 = (int)((dw_s >> 16) & 3u) - 1;
+        x_prop = evaluate_exact(dw_s, 0, bcast_u(gen[0].istate, 0));
     }
 
     for (int s0 = 0; s0 < s_end; s0 += L) {
-        philox_begin(s0 + D * L + q);                        // the batch generated during this one
+        // everything this batch reads from the proposal slots has landed (issued >= one batch ago)
+        cp_async_wait<D - 2>();
+        __syncwarp();
+        uint32_t ev_bin[L], ev_cnt[L];
 #pragma unroll
-        for (int j = 0; j < L; ++j) {
-            const int s = s0 + j;
-            // Philox rounds scheduled into this step
+        for (int j = 0; j < L; ++j) { ev_bin[j] = 0; ev_cnt[j] = 0; }
+
+        // ---- fast batch: L steps as ONE basic block on registers only (shared memory is read, never
+        //      written); anything rare only raises a flag and the batch is then redone carefully -------
+        bool careful = (unsigned)(next_ev - s0) < (unsigned)L;          // a snapshot / trace store falls into it
+        if (!careful) {
+            const double sv_E = E, sv_x = x_prop;
+            const int sv_sg = sg, sv_gm = gm, sv_pg = pg, sv_ssg = since_sg, sv_sgm = since_gm, sv_d0 = d0, sv_g0 = g0;
+            const unsigned int sv_at = acc_total, sv_ao = acc_own;
+            const uint32_t sv_dw = dw_s;
+            const float sv_lu = lu_s;
+            const bool sv_own = own_s;
+            bool rare = false;
+            philox_begin(s0 + D * L + q);                    // the batch generated during this one
 #pragma unroll
-            for (int r = 0; r < 10; ++r)
-                if (r * L / 10 == j) philox_round();
-            // the proposals of the next batch are first read by the last step of this one
-            if (j == L - 1) {
-                cp_async_wait<D - 2>();
-                __syncwarp();
+            for (int j = 0; j < L; ++j) {
+                const int s = s0 + j;
+#pragma unroll
+                for (int r = 0; r < 10; ++r)
+                    if (r * L / 10 == j) philox_round();
+                const bool nb = j + 1 == L;
+                const uint32_t dw_n = bcast_u(nb ? gen[1].dw : gen[0].dw, (j + 1) & (L - 1));
+                const float lu_n = bcast_f(nb ? gen[1].lu : gen[0].lu, (j + 1) & (L - 1));
+                // (1) resolve step s: energy in the reference's summation order, accept in the log domain
+                double En = bcast_d(x_prop, 0);
+#pragma unroll
+                for (int r = 1; r < R; ++r) En = __dadd_rn(En, bcast_d(x_prop, r));
+                const double d = __dsub_rn(E, En);
+                const float tt = (float)d - lu_s;
+                const bool acc = tt > SPEC_MARGIN;
+                const bool unsure = !acc && !(tt < -SPEC_MARGIN);        // guard band, also NaN
+                // (2) contributions to step s+1 under both outcomes of step s
+                const Cand k = evaluate(dw_n, s + 1, nb ? wofs[1] : wofs[0], d0, g0);
+                rare = rare || unsure || (acc && (int)dw_s >= 0) || k.miss;
+                // (3) commit
+                commit(acc, s, En, ev_bin[j], ev_cnt[j]);
+                x_prop = acc ? k.xB : k.xA;
+                dw_s = dw_n; lu_s = lu_n; d0 = k.d1; g0 = k.g1; own_s = k.own;
             }
-            // descriptor of step s+1 (from this batch's or the next batch's generating lane)
-            constexpr int dummy = 0; (void)dummy;
-            const bool nb = j + 1 == L;
-            const uint32_t desc_n = bcast_u(nb ? gen[1].desc : gen[0].desc, (j + 1) & (L - 1));
-            const float lu_n = bcast_f(nb ? gen[1].lu : gen[0].lu, (j + 1) & (L - 1));
-
-            // (1) resolve step s: energy in the reference's summation order, accept in the log domain
-            double En = bcast_d(x_prop, 0);
+            if (__any_sync(SPEC_FULL, rare)) {               // roll the batch back
+                E = sv_E; x_prop = sv_x; sg = sv_sg; gm = sv_gm; pg = sv_pg; since_sg = sv_ssg; since_gm = sv_sgm;
+                d0 = sv_d0; g0 = sv_g0; acc_total = sv_at; acc_own = sv_ao; dw_s = sv_dw; lu_s = sv_lu; own_s = sv_own;
 #pragma unroll
-            for (int r = 1; r < R; ++r) En = __dadd_rn(En, bcast_d(x_prop, r));
-            const double d = __dsub_rn(E, En);
-            const float tt = (float)d - lu_s;
-            const bool acc_f = tt > SPEC_MARGIN;
-            const bool unsure = !acc_f && !(tt < -SPEC_MARGIN);          // guard band, also NaN
-            const bool state_s = (int)desc_s >= 0;
+                for (int j = 0; j < L; ++j) ev_cnt[j] = 0;
+                careful = true;
+            }
+        }
 
-            // (2) contributions to step s+1 under both outcomes of step s
-            const Cand k = evaluate(desc_n, s + 1, nb ? wofs[1] : wofs[0], d0, g0);
-
-            // (3) commit; everything rare goes through one out-of-line path
-            const bool rare = __any_sync(SPEC_FULL, unsure || (acc_f && state_s) || k.miss) || s == next_ev;
-            if (__builtin_expect(rare, 0)) {
+        // ---- careful batch: step by step, every rare case handled exactly -----------------------------
+        if (careful) {
+#pragma unroll 1
+            for (int j = 0; j < L; ++j) {
+                const int s = s0 + j;
+                const bool nb = j + 1 == L;
+                const int jn = (j + 1) & (L - 1);
+                const uint32_t dw_n = bcast_u(nb ? gen[1].dw : gen[0].dw, jn);
+                const float lu_n = bcast_f(nb ? gen[1].lu : gen[0].lu, jn);
+                const uint32_t i2n = bcast_u(nb ? gen[1].istate : gen[0].istate, jn);
+                const uint32_t i2 = bcast_u(gen[0].istate, j);
                 const double u = bcast_d(gen[0].u, j);
+                double En = bcast_d(x_prop, 0);
+#pragma unroll
+                for (int r = 1; r < R; ++r) En = __dadd_rn(En, bcast_d(x_prop, r));
+                const double d = __dsub_rn(E, En);
+                const float tt = (float)d - lu_s;
+                const bool unsure = !(tt > SPEC_MARGIN) && !(tt < -SPEC_MARGIN);
                 const bool exact = s < s_end && ((En < E) || (d >= BCP_ACCEPT_CUTOFF && u < exp_det(d)));
-                const bool acc = unsure ? exact : acc_f;
-                commit(acc, s, En);
+                const bool acc = unsure ? exact : tt > SPEC_MARGIN;
+                const bool state_s = (int)dw_s >= 0;
+                uint32_t eb, ec;
+                commit(acc, s, En, eb, ec);
+                if (ec) atomicAdd(C.param_counts + eb, (unsigned long long)ec);
                 const bool accst = acc && state_s;
-                const bool redo = __any_sync(SPEC_FULL, accst || k.miss);
                 if (__any_sync(SPEC_FULL, accst)) {
                     if (accst) {       // adopt the slot as the current state, reload the gamma row
-                        const int i2 = (int)desc_s;
                         const uint32_t slot = slots + (uint32_t)(s & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
                         if (q < R) sts128(cur_rec, lds128(slot + 16 * qr));
                         if (q == 0) Cst = __dadd_rn(lds64(slot + ly.slot_c), logZ);
                         ++acc_state;
-                        if (i2 != state) {
+                        if ((int)i2 != state) {
                             if (s > burn && lead)
                                 atomicAdd(g_state_counts + state, (unsigned long long)(s - since_state));
                             if (s > burn) since_state = s;
-                            state = i2;
+                            state = (int)i2;
                         }
                         if (HG) {
                             const double2* src = reinterpret_cast<const double2*>(gh4 + (size_t)i2 * GS);
@@ -449,7 +490,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                     }
                     __syncwarp();
                 }
-                x_prop = redo ? evaluate_exact(desc_n, s + 1, k.d1, k.g1) : (acc ? k.xB : k.xA);
+                x_prop = evaluate_exact(dw_n, s + 1, i2n);
                 if (s >= burn && s < s_end) {
                     if (A.state_trace && lead) A.state_trace[(size_t)(A.s_begin + s - A.burn) * n + c] = state;
                     if (s == next_snap) {
@@ -466,21 +507,40 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                         next_snap = ns < s_end ? (int)ns : -1;
                     }
                 }
-                next_ev = A.state_trace ? s + 1 : next_snap;
-            } else {
-                commit(acc_f, s, En);
-                x_prop = acc_f ? k.xB : k.xA;
+                dw_s = dw_n; lu_s = lu_n; own_s = (dw_n & own_mask) != 0u;
+                d0 = (int)((dw_n >> fsh) & 3u) - 1;
+                g0 = (int)((dw_n >> 16) & 3u) - 1;
             }
-            desc_s = desc_n; lu_s = lu_n; d0 = k.d1; g0 = k.g1; own_s = k.own;
+            next_ev = A.state_trace ? s0 + L : next_snap;
+            philox_begin(s0 + D * L + q);
+#pragma unroll
+            for (int r = 0; r < 10; ++r) philox_round();
         }
-        // end of batch: finish the generated batch, prefetch its state moves, rotate
+
+        // ---- end of batch: compact the histogram events of the warp into its queue and flush them with
+        //      one RED per 32 events; finish the generated batch, prefetch its state moves, rotate -------
         {
+            uint32_t evn = 0;
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+                const uint32_t m = __ballot_sync(SPEC_FULL, ev_cnt[j] != 0u);
+                if (ev_cnt[j] != 0u) {
+                    const uint32_t at = evq + 8u * (evn + (uint32_t)__popc(m & lane_lt));
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(at), "r"(ev_bin[j]), "r"(ev_cnt[j]) : "memory");
+                }
+                evn += (uint32_t)__popc(m);
+            }
+            __syncwarp();
+            for (uint32_t k = threadIdx.x & 31; k < evn; k += 32) {
+                uint32_t bin, cnt;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bin), "=r"(cnt) : "r"(evq + 8u * k));
+                atomicAdd(C.param_counts + bin, (unsigned long long)cnt);
+            }
             const int sb = s0 + D * L + q;
             const SpecGen g = philox_finish(sb);
-            const int gm_now = HG ? bcast_i(gm, R - 1) : 0;
-            prefetch(g, sb, gm_now);
+            prefetch(g, sb, gm);
             cp_async_commit();
-            wofs[D] = window_ofs(gm_now);
+            wofs[D] = window_ofs();
 #pragma unroll
             for (int b = 0; b + 1 < D; ++b) gen[b] = gen[b + 1];
             gen[D - 1] = g;
@@ -499,12 +559,12 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         C.sep[(size_t)R * n + c] += acc_state;
     }
     if (owner) {
-        if (s_end > since_sg) atomicAdd(g_sigma_hist + sg, (unsigned long long)(s_end - since_sg));
+        if (s_end > since_sg) atomicAdd(C.param_counts + sbin0 + sg, (unsigned long long)(s_end - since_sg));
         C.isg[(size_t)q * n + c] = sg;
         C.sep[(size_t)q * n + c] += acc_own;
     }
-    if (HG && glane && live) {
-        if (s_end > since_gm) atomicAdd(g_gamma_hist + gm, (unsigned long long)(s_end - since_gm));
+    if (ghist) {
+        if (s_end > since_gm) atomicAdd(C.param_counts + gbin0 + gm, (unsigned long long)(s_end - since_gm));
         C.igm[(size_t)(R - 1) * n + c] = gm;
     }
 }
@@ -522,7 +582,7 @@ static cudaError_t launch_spec_one(const SamplerTables& T, const ChainBuffers& C
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     size_t smem = 0;
     for (; wpb >= 1; --wpb) {
-        smem = (size_t)T.sig4_bytes + (size_t)(wpb * 32 / L) * ly.chain_bytes + 128;
+        smem = (size_t)T.sig4_bytes + (size_t)(wpb * 32 / L) * ly.chain_bytes + (size_t)wpb * 512 + 128;
         if (smem + 64 <= (size_t)max_optin) break;
     }
     if (wpb < 1) return cudaErrorNotSupported;
