@@ -284,10 +284,14 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "bcp::mcmc_coop_kernel<4,true> (auto-selected for <= 8192 chains)", "kernel_ms_per_launch": k_ms,
+                "traffic": traffic, "kernel": "bcp::mcmc_spec_kernel<4,4,true> (auto-selected for <= 8192 chains)", "kernel_ms_per_launch": k_ms,
+                "cycles_per_chain_step": k_ms * 1e-3 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / N_MCMC,
                 "algorithmic_bytes_per_chain_step": bps, "peak_source": peak_src,
                 "note": "latency/issue-bound by construction (SURVEY 8d): the useful table words are L2-resident "
-                        "gathers; the HBM fraction is reported as required, the meaningful ceiling is instruction issue"}
+                        "gathers (measured L2 random-gather peak 2.9e11 8-B words/s, profiles/r01_microbench.json: "
+                        "this kernel needs 2.8 words per chain-step); the HBM fraction is reported as required, the "
+                        "meaningful ceiling is one warp's in-order instruction stream per step (4096 chains = 512 "
+                        "warps on 592 SM sub-partitions)"}
 
     # ---- CPU baseline beside it: the C oracle port on the host cores, bounded sample ----
     from oracle import cbind
