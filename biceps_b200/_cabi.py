@@ -188,6 +188,8 @@ _SIGS = {
                            C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
     "bcp_mbar_dev": (C.c_int, [C.c_void_p, c_int64_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int, C.c_void_p,
                                C.c_double, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
+    "bcp_chains_score": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, c_int64_p, c_double_p, c_double_p,
+                                   c_double_p, c_double_p, c_int32_p]),
     "bcp_mbar_pass_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, c_int64_p, c_double_p, C.c_int32, C.c_int,
                                     C.c_void_p, c_double_p, c_double_p]),
 }

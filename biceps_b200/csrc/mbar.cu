@@ -120,7 +120,10 @@ __global__ void mbar_finish_kernel(const double* __restrict__ partial, int n_blo
     out[p] = s;
 }
 
-// populations: P[l][s] += W_nl, Q[l][s] += W_nl^2 for the state s of sample n (fp64 atomics)
+// populations: P[l][s] += W_nl, Q[l][s] += W_nl^2 for the state s of sample n (fp64 atomics).
+// Consecutive samples are consecutive snapshots of one chain and mostly share their state, and a peaked
+// posterior sends almost every sample to a handful of states: a warp whose 32 samples agree reduces its
+// weights with shuffles first and issues one atomic per lambda instead of 32 colliding ones.
 __global__ void __launch_bounds__(MB_TILE)
 mbar_pop_kernel(const double* __restrict__ u, long long N, int K, const double* __restrict__ a_in,
                 const double* __restrict__ rn_in, const int* __restrict__ state, int S, double* __restrict__ P,
@@ -135,9 +138,27 @@ mbar_pop_kernel(const double* __restrict__ u, long long N, int K, const double* 
     const long long n_tiles = (N + MB_TILE - 1) / MB_TILE;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long n = tile * MB_TILE + t;
-        if (n < N) {
-            sample_weights(u, N, n, K, a, Ws, t);
-            const int s = state[n];
+        const bool valid = n < N;
+        if (valid) sample_weights(u, N, n, K, a, Ws, t);
+        const int s = valid ? state[n] : -1;
+        const int s0 = __shfl_sync(0xffffffffu, s, 0);
+        const bool uniform = __all_sync(0xffffffffu, s == s0 || !valid);
+        if (s0 < 0) continue;                               // the whole warp is past the end (warp-uniform)
+        if (uniform) {
+            for (int k = 0; k < K; ++k) {
+                double w = valid ? Ws[k * MB_LD + t] * rn[k] : 0.0;
+                double w2 = w * w;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    w += __shfl_xor_sync(0xffffffffu, w, off);
+                    w2 += __shfl_xor_sync(0xffffffffu, w2, off);
+                }
+                if ((t & 31) == 0) {
+                    atomicAdd(P + (size_t)k * S + s0, w);
+                    atomicAdd(Q + (size_t)k * S + s0, w2);
+                }
+            }
+        } else if (valid) {
             for (int k = 0; k < K; ++k) {
                 const double w = Ws[k * MB_LD + t] * rn[k];
                 atomicAdd(P + (size_t)k * S + s, w);

@@ -293,6 +293,44 @@ __global__ void build_layouts_kernel(const SamplerTables T, double* rec, double*
     if (flag) *bad = 1;
 }
 
+// K6 on the device-resident snapshots of a sample() call (bcp_chains_score): snapshot m of chain c is
+// sample pos0[c] + m of its lambda run (the chains of a run are concatenated, kln_to_kn order).  The
+// restraint terms do not depend on lambda: evaluated once, K energies written in
+// PosteriorSampler.neglogP order.  m is the fastest thread index, so the K * 8-byte writes coalesce.
+__global__ void __launch_bounds__(256)
+ukn_traj_kernel(const SamplerTables T, long long n_chains, long long n_snap, long long N, const long long* __restrict__ pos0,
+                const int* __restrict__ traj_state, const int* __restrict__ traj_idx, double* __restrict__ u,
+                int* __restrict__ state_n) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_chains * n_snap) return;
+    const long long c = idx / n_snap, m = idx - c * n_snap;
+    const long long nn = pos0[c] + m;
+    const int st = traj_state[m * n_chains + c];
+    double t[BCP_MAX_RESTRAINTS];
+    int p = 0;
+#pragma unroll
+    for (int q = 0; q < BCP_MAX_RESTRAINTS; ++q) {
+        if (q < T.R) {
+            const RestraintDev& rd = T.r[q];
+            const int sg = traj_idx[(m * T.P + p++) * n_chains + c];
+            const int gm = rd.has_gamma ? traj_idx[(m * T.P + p++) * n_chains + c] : 0;
+            const double* sig = T.sig_tab + rd.sig_off;
+            double v = __dadd_rn(sig[sg], __ddiv_rn(rd.sse[(size_t)st * rd.n_gamma + gm], sig[rd.n_sigma + sg]));
+            v = __dadd_rn(v, rd.cnorm);
+            if (rd.refsum) v = __dsub_rn(v, rd.refsum[st]);
+            t[q] = v;
+        }
+    }
+    for (int l = 0; l < T.K; ++l) {
+        double E = __dadd_rn(T.energy[(size_t)l * T.S + st], T.logZ[l]);
+#pragma unroll
+        for (int q = 0; q < BCP_MAX_RESTRAINTS; ++q)
+            if (q < T.R) E = __dadd_rn(E, t[q]);
+        u[(size_t)l * N + nn] = E;
+    }
+    state_n[nn] = st;
+}
+
 }  // namespace bcp
 
 using namespace bcp;
@@ -327,6 +365,7 @@ struct bcp_chains {
     size_t cap_snap = 0, cap_trace = 0;
     cudaStream_t last_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk = nullptr;
+    std::vector<int> h_lam;                 // lambda index of every chain (bcp_chains_score)
     cudaStream_t copy_stream = nullptr;     // device -> host copies of finished snapshots (bcp_sample)
     long long snaps_piped = 0;
     int last_launches = 0;
@@ -546,6 +585,7 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
     c->h = h;
     ++h->refs;
     c->n_groups = n_groups;
+    c->h_lam = lam;
     ChainBuffers& C = c->C;
     C.n_chains = n; C.seed = cfg->seed; C.chain_id0 = cfg->chain_id0;
     auto fail = [&](int code) { bcp_chains_destroy(c); return code; };
@@ -881,6 +921,45 @@ extern "C" int bcp_sample(bcp_chains* c, const bcp_sample_cfg* cfg, bcp_sample_o
         return rc;
     }
     return bcp_chains_fetch(c, out);
+}
+
+extern "C" int bcp_chains_score(bcp_chains* c, int32_t want_pops, double tol, int32_t max_iter, int64_t* N_k_out,
+                                double* f_k, double* theta, double* pops, double* dpops, int32_t* iters) {
+    BCP_REQUIRE(c && f_k && theta, "bcp_chains_score: NULL argument");
+    BCP_REQUIRE(c->sampled && c->n_snap > 0, "bcp_chains_score: no snapshots (sample with traj_every > 0 first)");
+    bcp_handle* h = c->h;
+    const SamplerTables& T = h->T;
+    BCP_REQUIRE(T.pf.q < 0, "bcp_chains_score: ensembles with a PFGRID restraint go through bcp_ukn + bcp_mbar");
+    DeviceGuard guard(h->device);
+    const long long n = c->C.n_chains, ns = c->n_snap;
+    const int K = T.K;
+    std::vector<long long> cnt(K, 0), off(K + 1, 0), pos0(n);
+    for (long long i = 0; i < n; ++i) ++cnt[c->h_lam[i]];
+    for (int k = 0; k < K; ++k) off[k + 1] = off[k] + cnt[k] * ns;
+    std::vector<long long> seen(K, 0);
+    for (long long i = 0; i < n; ++i) { const int k = c->h_lam[i]; pos0[i] = off[k] + seen[k] * ns; ++seen[k]; }
+    std::vector<int64_t> N_k(K);
+    for (int k = 0; k < K; ++k) { N_k[k] = cnt[k] * ns; if (N_k_out) N_k_out[k] = N_k[k]; }
+    const long long N = off[K];
+    cudaStream_t st = c->last_stream;
+    long long* d_pos = nullptr; double* d_u = nullptr; int* d_sn = nullptr;
+    int rc = BCP_OK;
+    do {
+#define STEP(x) if ((x) != cudaSuccess) { set_error("bcp_chains_score: %s: %s", #x, cudaGetErrorString(cudaGetLastError())); rc = BCP_ERR_CUDA; break; }
+        STEP(pool_alloc(&d_pos, (size_t)n));
+        STEP(pool_alloc(&d_u, (size_t)K * N));
+        STEP(pool_alloc(&d_sn, (size_t)N));
+        STEP(cudaMemcpyAsync(d_pos, pos0.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        ukn_traj_kernel<<<(unsigned)((n * ns + 255) / 256), 256, 0, st>>>(T, n, ns, N, d_pos, c->d_traj_state, c->d_traj_idx, d_u, d_sn);
+        BCP_LAUNCHED(1);
+        STEP(cudaGetLastError());
+#undef STEP
+        rc = bcp_mbar_dev(d_u, N_k.data(), K, N, want_pops ? d_sn : nullptr, want_pops ? T.S : 0, h->device, st, tol, max_iter,
+                          f_k, theta, pops, dpops, iters);
+    } while (0);
+    cudaStreamSynchronize(st);
+    pool_free(d_pos); pool_free(d_u); pool_free(d_sn);
+    return rc;
 }
 
 extern "C" int bcp_neglogp(bcp_handle* h, int64_t n, const int32_t* lam, const int32_t* state,

@@ -136,6 +136,23 @@ class ChainBlock(object):
         A.check(self._lib.bcp_chains_fetch(self._c, C.byref(s)), "bcp_chains_fetch")
         return o
 
+    def score(self, populations=True, tol=0.0, max_iter=0):
+        """BICePs scores straight from the device-resident snapshots of the last sample()/launch() call
+        (bcp_chains_score): u_kn by rescoring under every lambda, then MBAR; no file or host round trip.
+        Several chains per lambda (seeds) are concatenated in chain order.  Returns dict(f, theta, Delta_f,
+        dDelta_f, P, dP, iters, N_k) like mbar.mbar."""
+        T = self.tables
+        K, S = T.n_lambda, T.n_states
+        f = np.zeros(K); theta = np.zeros((K, K)); N_k = np.zeros(K, np.int64)
+        P = np.zeros((S, K)) if populations else None
+        dP = np.zeros((S, K)) if populations else None
+        it = C.c_int32(0)
+        A.check(self._lib.bcp_chains_score(self._c, int(bool(populations)), float(tol), int(max_iter), A.i64ptr(N_k),
+                                           A.dptr(f), A.dptr(theta), A.dptr(P), A.dptr(dP), C.byref(it)), "bcp_chains_score")
+        d = np.diag(theta)
+        return dict(f=f, theta=theta, Delta_f=f[None, :] - f[:, None],
+                    dDelta_f=np.sqrt(np.abs(d[:, None] + d[None, :] - 2.0 * theta)), P=P, dP=dP, iters=int(it.value), N_k=N_k)
+
     def set_state(self, state=None, indices=None, energy=None):
         """Overwrite chain state / indices [n][P] / energy (None = keep): checkpoint restart."""
         st = None if state is None else A.i32(state)

@@ -234,6 +234,13 @@ int bcp_mbar(const double* u_kn, const int64_t* N_k, int32_t K, int64_t N, const
 int bcp_mbar_dev(const double* d_u_kn, const int64_t* N_k, int32_t K, int64_t N, const int32_t* d_state_n, int32_t S,
                  int device, void* stream, double tol, int32_t max_iter, double* f_k, double* theta, double* pops,
                  double* dpops, int32_t* iters);
+/* The whole Analysis step on the device-resident snapshots of the chains' last sample() call (no file or
+ * host round trip): every chain's snapshots are samples of its lambda run
+ * (chains of one run concatenated in chain order = Analysis.py:214 kln_to_kn order, several seeds per
+ * lambda allowed), u_kn by rescoring under every lambda (Analysis.py:165-183), then MBAR as bcp_mbar.
+ * N_k_out [K] (may be NULL) receives the samples per run; pops / dpops [S][K] only if want_pops.  */
+int bcp_chains_score(bcp_chains* c, int32_t want_pops, double tol, int32_t max_iter, int64_t* N_k_out,
+                     double* f_k, double* theta, double* pops, double* dpops, int32_t* iters);
 /* One streaming reduction over a local shard of samples (multi-GPU MBAR: the caller all-reduces
  * s and M across ranks between passes): s[K] = sum_n W_nk, M[K][K] = sum_n W_nk W_nl.        */
 int bcp_mbar_pass_dev(const double* d_u_kn, int64_t n_local, int32_t K, const int64_t* N_k_global,

@@ -63,3 +63,40 @@ def test_mbar_rejects_bad_input():
         mbar.mbar(np.zeros((2, 10)), [5, 4])            # sum(N_k) != N
     with pytest.raises(RuntimeError):
         mbar.mbar(np.zeros((2, 10)), [5, 5], np.full(10, 3), 3)   # state out of range
+
+
+def test_device_resident_score_pipeline_equals_the_host_route():
+    """bcp_chains_score (snapshots stay in HBM: rescoring + MBAR) against the host route
+    fetch -> concatenate per lambda in chain order -> bcp_ukn -> bcp_mbar, and against the numpy MBAR.
+    Three lambdas, several seeds per lambda, chains interleaved over the lambdas."""
+    from biceps_b200 import engine, mbar, synthetic
+    from oracle import precompute_oracle as PO
+    ens = synthetic.make_ensemble("C2", seed=4, n_states=60, n_lambda=3)
+    tabs = PO.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], exact_pow=False)
+    T = engine.DeviceTables(tabs)
+    n = 3 * 5 + 2                                           # ragged: lambda 0 and 1 get one more seed
+    lam = (np.arange(n) % 3).astype(np.int32)
+    blk = T.chains(n, 11, chain_lambda=lam)
+    o = blk.sample(4000, burn=200, traj_every=10)
+    got = blk.score(populations=True)
+    ns = o["traj_state"].shape[0]
+    order = [c for k in range(3) for c in range(n) if lam[c] == k]
+    state = np.concatenate([o["traj_state"][:, c] for c in order])
+    idx = np.concatenate([o["traj_indices"][:, :, c] for c in order])
+    N_k = np.array([ns * int((lam == k).sum()) for k in range(3)])
+    assert np.array_equal(got["N_k"], N_k)
+    u = mbar.ukn(T, state, idx)
+    # the stored energies are the diagonal of u_kln (Analysis.py:170) -- same bits as rescoring
+    o2 = 0
+    for k in range(3):
+        e = np.concatenate([o["traj_energy"][:, c] for c in order if lam[c] == k])
+        assert np.array_equal(u[k, o2:o2 + N_k[k]], e)
+        o2 += N_k[k]
+    want = mbar.mbar(u, N_k, state, 60)
+    assert np.allclose(got["f"], want["f"], atol=1e-12)
+    assert np.allclose(got["theta"], want["theta"], rtol=1e-10, atol=1e-15)
+    assert np.allclose(got["P"], want["P"], rtol=1e-10, atol=1e-15)
+    f, W, it = M.mbar_solve(u, N_k)
+    assert np.allclose(got["f"], f, atol=1e-9)
+    with pytest.raises(RuntimeError):
+        T.chains(4, 1).score()                              # nothing sampled yet
