@@ -744,7 +744,12 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
         A.s_begin = s0;
         A.s_end = s0 + chunk < total ? s0 + chunk : total;
         cudaError_t e;
-        if (T.pf.q >= 0) e = launch_mcmc_pf(T, c->C, A, st);
+        if (T.pf.q >= 0) {
+            // BCP_PF_KERNEL=generic forces the general warp-per-chain kernel (tests run both)
+            const char* pk = getenv("BCP_PF_KERNEL");
+            e = (pk && !strcmp(pk, "generic")) ? cudaErrorNotSupported : launch_mcmc_pf2(T, c->C, A, st);
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_pf(T, c->C, A, st); }
+        }
         else if (which == 3) {
             e = launch_mcmc_spec(T, c->C, A, st, sms);
             if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); }

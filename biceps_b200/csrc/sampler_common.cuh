@@ -88,6 +88,8 @@ cudaError_t launch_mcmc_coop(const SamplerTables& T, const ChainBuffers& C, cons
 cudaError_t launch_mcmc_spec(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms);
 // warp-per-chain kernel for ensembles with a PFGRID restraint (sampler_pf.cu); any layout
 cudaError_t launch_mcmc_pf(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st);
+// tuned variant for scalar restraints + one PFGRID restraint (sampler_pf2.cu); cudaErrorNotSupported otherwise
+cudaError_t launch_mcmc_pf2(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st);
 // -log P of explicit configurations when the ensemble has a PFGRID restraint (warp per configuration)
 cudaError_t launch_energy_pf(const SamplerTables& T, long long N, const int* d_lam, const int* d_state,
                              const int* d_indices, double* d_out, int all_lambdas, cudaStream_t st);

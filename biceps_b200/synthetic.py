@@ -61,3 +61,30 @@ def make_ensemble(config="C3", seed=0, n_states=None, n_lambda=None):
     restraints = [_restraint(rng, S, J, fl) for fl, J in layout]
     lambdas = np.linspace(0.0, 1.0, K) if K > 1 else np.array([1.0])
     return dict(config=config, n_states=S, energies=energies, lambdas=lambdas, restraints=restraints)
+
+
+def make_pf_tables(n_states=100000, n_obs=107, seed=0, n_lambda=1, dtype=np.float64):
+    """C4 (BASELINE configs[3]): HDX protection factors on the default 6-D nuisance grid
+    (beta_c 20 x beta_h 26 x beta_0 50 x x_c 7 x x_h 8 x b 1), raw <N_c>[S][7][1][J] ~ U(0,60) increasing in
+    x_c, <N_h>[S][8][1][J] ~ U(0,4) increasing in x_h, ln PF_exp ~ U(0,10), exponential reference, zero
+    prior.  Returns sampler tables (kind "pfgrid": the term is evaluated on the fly by the sampler)."""
+    from .precompute import sigma_vectors
+    rng = np.random.default_rng(seed)
+    grids = [np.arange(0.05, 0.25, 0.01), np.arange(0.0, 5.2, 0.2), np.arange(-10.0, 0.0, 0.2),
+             np.arange(5.0, 8.5, 0.5), np.arange(2.0, 2.7, 0.1), np.arange(15.0, 16.0, 1.0)]
+    nxc, nxh, nb = len(grids[3]), len(grids[4]), len(grids[5])
+    Nc = np.sort(rng.uniform(0.0, 60.0, (n_states, nxc, nb, n_obs)), axis=1)
+    Nh = np.sort(rng.uniform(0.0, 4.0, (n_states, nxh, nb, n_obs)), axis=1)
+    exp = rng.uniform(0.0, 10.0, n_obs)
+    weight = np.ones(n_obs)
+    ndof = float(np.sum(weight))
+    sigma = np.exp(np.arange(np.log(0.05), np.log(20.0), np.log(1.02)))
+    nlsig, two, cnorm = sigma_vectors(ndof, sigma)
+    energies = 3.0 * np.abs(rng.standard_normal(n_states))
+    energies -= energies.min()
+    lambdas = np.linspace(0.0, 1.0, n_lambda) if n_lambda > 1 else np.array([1.0])
+    en = lambdas[:, None] * energies[None, :]
+    logZ = np.log(np.sum(np.exp(-en), axis=1))
+    rt = dict(kind="pfgrid", name="pf", ref="exponential", ndof=ndof, sigma=sigma, nlsig=nlsig, two_sig2=two,
+              cnorm=cnorm, grids=grids, prior=None, pf=dict(Nc=Nc, Nh=Nh, exp=exp, weight=weight), refsum=None, sse=None)
+    return dict(n_states=n_states, energy=en, logZ=logZ, restraints=[rt])

@@ -8,6 +8,14 @@ from helpers import load_npz, tables_from_npz, pf_raw_tables, assert_outputs_equ
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["tuned", "generic"], autouse=True)
+def pf_kernel(request, monkeypatch):
+    """Every case runs through the tuned kernel (sampler_pf2.cu: scalar restraints + one PF restraint) and the
+    general one (sampler_pf.cu); BCP_PF_KERNEL is read at each launch."""
+    monkeypatch.setenv("BCP_PF_KERNEL", request.param)
+    return request.param
+
+
 def both(tabs, n, seed, steps, **kw):
     from biceps_b200 import engine
     from oracle import cbind
