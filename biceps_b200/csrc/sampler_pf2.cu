@@ -8,7 +8,8 @@
 //   * R and the residues per lane (NJ = ceil(J / 32) <= 4) are template parameters, the chain state is a
 //     handful of scalars: 2-3x fewer registers than the generic kernel's 235 -> 4+ warps per sub-partition;
 //   * the rows of step s+1's proposal are requested while step s is still being evaluated, assuming step s
-//     is rejected (PF acceptance is a few per cent); an accepted step simply re-requests them;
+//     is rejected (PF acceptance is a few per cent); an accepted step simply re-requests them.  They travel
+//     by cp.async into a per-warp double buffer in shared memory, so data in flight holds no registers;
 //   * lane j generates the Philox block of step s0 + j for a batch of 32 steps (1/32 block per step and
 //     lane instead of a whole one).
 // The summation order of the PF sums (strided partials per lane, then the 16-8-4-2-1 xor butterfly) and
@@ -24,6 +25,10 @@ __device__ __forceinline__ int p2wrap(int v, int n) {      // v in [-1, n]
     return v < 0 ? v + n : (v >= n ? v - n : v);
 }
 
+#ifndef PF2_MIN_BLOCKS
+#define PF2_MIN_BLOCKS 4
+#endif
+
 struct Pf2Prop {            // proposal of one step, decoded from its Philox block (warp-uniform)
     bool nuis;
     int pick;               // restraint that moves (nuisance move)
@@ -33,13 +38,23 @@ struct Pf2Prop {            // proposal of one step, decoded from its Philox blo
 };
 
 template <int R, int NJ>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, PF2_MIN_BLOCKS)
 mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                 const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_sig = reinterpret_cast<double*>(smem_raw);
     __shared__ __align__(8) uint64_t mbar;
     stage_sigma_table(s_sig, T.sig_tab, T.sig_bytes, &mbar);
+    // experimental values and weights of the residues, padded with zero weight up to 32 NJ
+    double* s_ex = s_sig + T.sig_bytes / 8;
+    double* s_wt = s_ex + 32 * NJ;
+    double* s_rows = s_wt + 32 * NJ;                        // [warps][2 buffers][nc | nh][32 NJ], zero past J
+    for (int k = threadIdx.x; k < 32 * NJ; k += blockDim.x) {
+        s_ex[k] = k < T.pf.J ? T.pf.exp[k] : 0.0;
+        s_wt[k] = k < T.pf.J ? T.pf.weight[k] : 0.0;
+    }
+    for (int k = threadIdx.x; k < (int)(blockDim.x >> 5) * 4 * 32 * NJ; k += blockDim.x) s_rows[k] = 0.0;
+    __syncthreads();
 
     const long long n = C.n_chains;
     const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -66,27 +81,26 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
 
     const int n0 = pf.n[0], n1 = pf.n[1], n2 = pf.n[2], n3 = pf.n[3], n4 = pf.n[4], n5 = pf.n[5];
     const int nk[BCP_PF_NGRID] = {n0, n1, n2, n3, n4, n5};
-    // per-lane residues: experimental values and weights stay in registers (zero weight past J)
-    double ex[NJ], wt[NJ];
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) {
-        const int j = lane + 32 * i;
-        ex[i] = j < J ? __ldg(pf.exp + j) : 0.0;
-        wt[i] = j < J ? __ldg(pf.weight + j) : 0.0;
-    }
-
     // ---- the two rows of counts of (state, grid indices), and the PF sums over them ----------------
-    auto load_rows = [&](int st, const int* ci, double* nc, double* nh) {
+    double* my_rows = s_rows + (size_t)(threadIdx.x >> 5) * 4 * 32 * NJ;
+    const uint32_t my_rows_u32 = smem_u32(my_rows);
+    // cp.async of the two rows into buffer `buf`; each lane copies (and later reads) its own residues
+    auto request_rows = [&](int st, const int* ci, int buf) {
         const double* __restrict__ Nc = pf.Nc + (size_t)((unsigned)((st * n3 + ci[3]) * n5 + ci[5])) * (unsigned)J;
         const double* __restrict__ Nh = pf.Nh + (size_t)((unsigned)((st * n4 + ci[4]) * n5 + ci[5])) * (unsigned)J;
+        const uint32_t dst = my_rows_u32 + (uint32_t)buf * (2u * 32u * NJ * 8u) + 8u * (uint32_t)lane;
 #pragma unroll
         for (int i = 0; i < NJ; ++i) {
             const int j = lane + 32 * i;
-            nc[i] = j < J ? __ldg(Nc + j) : 0.0;
-            nh[i] = j < J ? __ldg(Nh + j) : 0.0;
+            if (j < J) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 256u * i), "l"(Nc + j) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 256u * (NJ + i)), "l"(Nh + j) : "memory");
+            }
         }
     };
-    auto pf_sums = [&](const int* ci, const double* nc, const double* nh, double& sse, double& ref) {
+    auto pf_sums = [&](const int* ci, int buf, double& sse, double& ref) {
+        const double* nc = my_rows + (size_t)buf * (2 * 32 * NJ) + lane;
+        const double* nh = nc + 32 * NJ;
         const double bc = __ldg(pf.grid + ci[0]);
         const double bh = __ldg(pf.grid + n0 + ci[1]);
         const double b0 = __ldg(pf.grid + n0 + n1 + ci[2]);
@@ -94,11 +108,12 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         // residues past J carry weight 0 and counts 0: they add +0.0, which changes no bit of ps / pr
 #pragma unroll
         for (int i = 0; i < NJ; ++i) {
-            const double model = __dadd_rn(__dadd_rn(__dmul_rn(bc, nc[i]), __dmul_rn(bh, nh[i])), b0);
-            const double err = __dsub_rn(model, ex[i]);
-            ps = __dadd_rn(ps, __dmul_rn(wt[i], __dmul_rn(err, err)));
+            const double model = __dadd_rn(__dadd_rn(__dmul_rn(bc, nc[32 * i]), __dmul_rn(bh, nh[32 * i])), b0);
+            const double err = __dsub_rn(model, s_ex[lane + 32 * i]);
+            const double wi = s_wt[lane + 32 * i];
+            ps = __dadd_rn(ps, __dmul_rn(wi, __dmul_rn(err, err)));
             const double neg = __dmul_rn(-1.0, model);
-            pr = __dadd_rn(pr, __dmul_rn(wt[i], neg > 0.0 ? neg : 0.0));
+            pr = __dadd_rn(pr, __dmul_rn(wi, neg > 0.0 ? neg : 0.0));
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
@@ -141,8 +156,9 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
 #pragma unroll
     for (int k = 0; k < BCP_PF_NGRID; ++k) { ipf[k] = C.ipf[(size_t)k * n + c]; since_pf[k] = burn; }
     {
-        double nc[NJ], nh[NJ];
-        load_rows(state, ipf, nc, nh);
+        request_rows(state, ipf, 0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             isg[q] = C.isg[(size_t)q * n + c];
@@ -151,7 +167,7 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             csse[q] = 0.0; cref[q] = 0.0;
             if (q == QP) {
                 double sse, ref;
-                pf_sums(ipf, nc, nh, sse, ref);
+                pf_sums(ipf, 0, sse, ref);
                 t[q] = pf_term(isg[q], ipf, sse, ref);
             } else {
                 csse[q] = __ldg(T.r[q].sse + state);
@@ -217,9 +233,10 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         return p;
     };
     // what a proposal reads from global memory (requested one step ahead)
-    struct Pre { double nc[NJ], nh[NJ], C, sse[R], ref[R]; };
-    auto request = [&](const Pf2Prop& p, Pre& x) {
-        if (!p.nuis || p.pick == QP) load_rows(p.nstate, p.npf, x.nc, x.nh);
+    struct Pre { double C, sse[R], ref[R]; };
+    auto request = [&](const Pf2Prop& p, Pre& x, int buf) {
+        if (!p.nuis || p.pick == QP) request_rows(p.nstate, p.npf, buf);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         if (!p.nuis) {
             x.C = __ldg(energy + p.nstate);
 #pragma unroll
@@ -242,7 +259,8 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         wn = (j == 31) ? bcast(gnxt, 0) : bcast(gcur, j + 1);
         if (j == 31) { gcur = gnxt; gnxt = block_of(s + 1 + 32 + lane); }
         pn = decode(wn);
-        request(pn, pren);
+        request(pn, pren, (s + 1) & 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");          // step s's rows have landed
 
         double tn[R];
         const double Cn = prop.nuis ? Cst : __dadd_rn(pre.C, logZ);
@@ -254,7 +272,7 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 const int sg = prop.nuis ? prop.nsg : isg[q];
                 if (q == QP) {
                     double sse, ref;
-                    pf_sums(prop.npf, pre.nc, pre.nh, sse, ref);
+                    pf_sums(prop.npf, s & 1, sse, ref);
                     tn[q] = pf_term(sg, prop.npf, sse, ref);
                 } else {
                     tn[q] = scalar_term(q, sg, prop.nuis ? csse[q] : pre.sse[q], prop.nuis ? cref[q] : pre.ref[q]);
@@ -300,9 +318,11 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                     }
                 }
             }
-            // the request for step s+1 assumed the old state: decode and request again
+            // the request for step s+1 assumed the old state: decode and request again (the stale copies
+            // must have landed before the same buffer is written again)
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             pn = decode(wn);
-            request(pn, pren);
+            request(pn, pren, (s + 1) & 1);
         }
 
         if (s >= burn && lead) {
@@ -333,7 +353,7 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     Philox4 wA = bcast(gcur, 0), wB;
     Pf2Prop pA = decode(wA), pB;
     Pre xA, xB;
-    request(pA, xA);
+    request(pA, xA, 0);
     for (int s = 0; s < s_end; s += 2) {
         step(s, wA, pA, xA, wB, pB, xB);
         if (s + 1 < s_end) step(s + 1, wB, pB, xB, wA, pA, xA);
@@ -363,12 +383,12 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
 
 template <int R, int NJ>
 static cudaError_t launch_pf2_one(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(mcmc_pf2_kernel<R, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.sig_bytes);
+    cudaError_t e = cudaFuncSetAttribute(mcmc_pf2_kernel<R, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.sig_bytes + 512 * NJ + 4 * 4 * 256 * NJ);
     if (e != cudaSuccess) return e;
     const int block = 128;                                   // 4 chains per CTA
     const long long threads = C.n_chains * 32;
     const int grid = (int)((threads + block - 1) / block);
-    mcmc_pf2_kernel<R, NJ><<<grid, block, T.sig_bytes, st>>>(T, C, A);
+    mcmc_pf2_kernel<R, NJ><<<grid, block, T.sig_bytes + 512 * NJ + 4 * 4 * 256 * NJ, st>>>(T, C, A);
     return cudaGetLastError();
 }
 
