@@ -300,6 +300,33 @@ def run_ours(args, rank, world, local_rank):
                  "biceps_score_lambda1": float(r5["f"][-1] - r5["f"][0]), "d_score": float(r5["dDelta_f"][0, -1]),
                  "chain_steps_per_s": n5 * steps5 / best[1], "note": "best of 2; tables resident, results on the host"}
 
+    # ---- C4 (BASELINE configs[3]): HDX protection factors on the 6-D grid, 1e5 states (1.3 GB of <N_c>/<N_h>
+    #      counts in HBM), warp-per-chain kernel evaluating the term on the fly: the one HBM-bound sampler ----
+    pf_c4 = None
+    if world == 1:
+        tabs4 = synthetic.make_pf_tables(n_states=100000)
+        T4 = engine.DeviceTables(tabs4, device=dev)
+        n4, steps4 = 32768, 500
+        b4 = T4.chains(n4, SEED + 20)
+        b4.launch(100, stream=stream)
+        ms4 = []
+        for _ in range(3):
+            b4.launch(steps4, stream=stream)
+            b4.sync()
+            ms4.append(b4.last_kernel_ms()[0])
+        b4.close(); T4.close()
+        rate4 = n4 * steps4 / (min(ms4) * 1e-3)
+        row_bytes = 16.0 * 107                      # two 8 J-byte rows per evaluated proposal
+        peak4, _src = measured_peak_hbm()
+        pf_c4 = {"workload": "C4: 100000 states x 107 residues, default 6-D grid (20x26x50x7x8x1), 32768 chains x 500 steps",
+                 "value": rate4, "unit": "chain-steps/s", "kernel": "bcp::mcmc_pf2_kernel<1,4>",
+                 "roofline": {"bound": "hbm", "achieved": rate4 * row_bytes / 1e9, "peak": peak4, "unit": "GB/s",
+                              "frac": rate4 * row_bytes / 1e9 / peak4, "algorithmic_bytes_per_chain_step": row_bytes,
+                              "traffic": 14.467e9 + 8.3e6,
+                              "note": "algorithmic = the two rows of counts every proposal reads; ncu (profiles/"
+                                      "r01_mcmc_pf2_32k.summary.txt, same launch): 14.5 GB of DRAM reads = 883 B per "
+                                      "chain-step, L2 serves the rest (a nuisance move re-reads rows of the chain's state)"}}
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----
@@ -346,7 +373,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "mcmc_steps_per_chain": N_MCMC_E2E, "traj_every": 100},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "saturated": saturated,
-            "score_pipeline": score}
+            "score_pipeline": score, "pf_c4": pf_c4}
     emit(line)
 
 

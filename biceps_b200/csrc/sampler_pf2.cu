@@ -112,8 +112,9 @@ mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             const double err = __dsub_rn(model, s_ex[lane + 32 * i]);
             const double wi = s_wt[lane + 32 * i];
             ps = __dadd_rn(ps, __dmul_rn(wi, __dmul_rn(err, err)));
-            const double neg = __dmul_rn(-1.0, model);
-            pr = __dadd_rn(pr, __dmul_rn(wi, neg > 0.0 ? neg : 0.0));
+            // reference: pr += w * max(-model, 0).  For model >= 0 (or -0.0, NaN) that adds w * 0.0 = +0.0, which
+            // leaves every bit of pr unchanged (pr is never -0.0), so the add is skipped
+            if (model < 0.0) pr = __dadd_rn(pr, __dmul_rn(wi, __dmul_rn(-1.0, model)));
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
