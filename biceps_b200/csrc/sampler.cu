@@ -711,10 +711,13 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     // kernel choice: BCP_KERNEL=generic|fast|coop overrides (BCP_FORCE_GENERIC=1 == generic)
     const char* force = getenv("BCP_FORCE_GENERIC");
     const char* kern = getenv("BCP_KERNEL");
-    // auto: few chains -> the step time is one warp's instruction stream: spread a chain over L lanes
-    // (coop); many chains -> issue-bound: one thread per chain (fast).  Crossover measured on B200
-    // (profiles/README.md): coop wins at 4096 chains (5.6e9 vs 4.2e9 steps/s), fast from ~16k up.
-    int which = !T.canonical ? 0 : (n <= 8192 ? 3 : 1);              // 0 generic, 1 fast, 2 coop, 3 spec
+    // auto: few chains -> the step time is one warp's instruction stream: spread a chain over L lanes and
+    // speculate (spec); many chains -> issue-bound: one thread per chain (fast).  The spec kernel holds one
+    // CTA of 128 threads per SM (shared-memory chain blocks) and is flat beyond ~one wave; measured on B200
+    // (scripts/probe_sampler.py, probe_c2.py): C3 (L = 4) 1.5e10 steps/s at 4096 chains, 1.7e10 at 32768 vs
+    // fast 4.2e9 / 2.9e10; C2 (L = 8) spec 3.7e9 / 7.3e9 at 1024 / 8192 chains vs fast 1.1e9 / 8.5e9.
+    const int lanes = T.R <= 2 ? 2 : (T.R <= 4 ? 4 : 8);
+    int which = !T.canonical ? 0 : (n * lanes <= 2ll * sms * 128 ? 3 : 1);      // 0 generic, 1 fast, 2 coop, 3 spec
     if (kern && T.canonical)
         which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : 2));
     if (force && force[0] == '1') which = 0;
