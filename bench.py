@@ -343,6 +343,12 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "bcp::mcmc_spec_kernel<4,4,true> (auto-selected for <= 8192 chains)", "kernel_ms_per_launch": k_ms,
                 "cycles_per_chain_step": k_ms * 1e-3 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / N_MCMC,
+                "latency_floor_cycles_per_chain_step": 110,
+                "latency_floor_note": "a chain is serial: select -> 8 SHFL (26 cycles) -> 3+1 DADD (8.4 each) -> F2F/FADD/"
+                                      "FSETP for the accept, overlapped with the next candidate's LDS (31.5) + 5-op "
+                                      "division (40) + 4 DADD; measured latencies in profiles/r01_microbench.json. The "
+                                      "kernel issues 209 warp instructions per step at 0.40 IPC (profiles/"
+                                      "r01_mcmc_spec_4096.summary.txt)",
                 "algorithmic_bytes_per_chain_step": bps, "peak_source": peak_src,
                 "note": "latency/issue-bound by construction (SURVEY 8d): the useful table words are L2-resident "
                         "gathers (measured L2 random-gather peak 2.9e11 8-B words/s, profiles/r01_microbench.json: "
