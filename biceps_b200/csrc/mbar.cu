@@ -112,12 +112,155 @@ mbar_pass_kernel(const double* __restrict__ u, long long N, int K, const double*
     }
 }
 
+// Streaming pass for small K (the BICePs case: a handful of lambda values): the K reduced potentials of a
+// sample, its log-sum-exp and weights stay in registers, and every thread accumulates its own partial s_k
+// and (HESS) upper triangle of W^T W over its samples -- no barrier inside the stream.  The accumulators
+// (77 doubles at K = 11) leave room for only 8 warps per SM, far too few plain loads in flight for HBM, so
+// u_kn is staged through shared memory with cp.async: every thread copies the K x 16 bytes of ITS two
+// samples for MB_STAGES tiles ahead (data in flight holds no registers: 3 x 256 x K x 16 B = 135 KB per SM
+// at K = 11) and later reads back what it copied itself, so no block-level synchronisation is needed.
+// u_kn is read exactly once.  The partials are reduced once at the end: xor butterfly inside the warp,
+// fixed-order sum over the warps.  Same arithmetic per sample as sample_weights().
+constexpr int MB_REGK = 12;
+constexpr int MB_STAGES = 3;
+
+template <int K, bool HESS>
+__global__ void __launch_bounds__(256)
+mbar_pass_reg_kernel(const double* __restrict__ u, long long N, const double* __restrict__ a_in,
+                     const double* __restrict__ rn_in, double* __restrict__ partial) {
+    constexpr int NP = HESS ? K * (K + 1) / 2 : 0;
+    extern __shared__ __align__(16) double stage_buf[];          // [MB_STAGES][K][256] x double2
+    __shared__ double red[8][K + (HESS ? K * (K + 1) / 2 : 0)];
+    double a[K], rn[K], accs[K], accm[NP > 0 ? NP : 1];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { a[k] = a_in[k]; rn[k] = rn_in[k]; accs[k] = 0.0; }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) accm[p] = 0.0;
+
+    auto one_sample = [&](const double* x) {                     // x[k] = u_kn of one sample
+        double w[K];
+        double mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            w[k] = a[k] - x[k];
+            mx = fmax(mx, w[k]);
+        }
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            w[k] = exp(w[k] - mx);
+            sum += w[k];
+        }
+        const double inv = 1.0 / sum;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            w[k] = (w[k] * inv) * rn[k];
+            accs[k] += w[k];
+        }
+        if (HESS) {
+            int p = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int l = k; l < K; ++l) accm[p++] += w[k] * w[l];
+        }
+    };
+
+    // tiles of 512 samples (2 per thread); rows of u_kn are 16-byte aligned for every k only if N is even
+    const long long n_tiles = N / 512;
+    const bool aligned = (N & 1) == 0;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage_buf) + 16u * threadIdx.x;
+    auto issue = [&](long long tile, int st) {
+        if (tile < n_tiles) {
+            const double* src = u + tile * 512 + 2 * threadIdx.x;
+            const uint32_t dst = sbase + (uint32_t)st * (K * 256u * 16u);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (aligned) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * 4096u), "l"(src + (size_t)k * N) : "memory");
+                } else {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + k * 4096u), "l"(src + (size_t)k * N) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + k * 4096u + 8u), "l"(src + (size_t)k * N + 1) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    long long tile = blockIdx.x;
+#pragma unroll
+    for (int st = 0; st < MB_STAGES - 1; ++st) issue(tile + (long long)st * gridDim.x, st);
+    int st = 0;
+    for (; tile < n_tiles; tile += gridDim.x) {
+        issue(tile + (long long)(MB_STAGES - 1) * gridDim.x, (st + MB_STAGES - 1) % MB_STAGES);
+        asm volatile("cp.async.wait_group %0;" ::"n"(MB_STAGES - 1) : "memory");
+        const double2* buf = reinterpret_cast<const double2*>(stage_buf) + (size_t)st * (K * 256) + threadIdx.x;
+        double x0[K], x1[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double2 v = buf[k * 256];
+            x0[k] = v.x; x1[k] = v.y;
+        }
+        one_sample(x0);
+        one_sample(x1);
+        st = (st + 1) % MB_STAGES;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // the last N % 512 samples: plain streaming loads
+    for (long long n = n_tiles * 512 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+        double x[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = __ldcs(u + (size_t)k * N + n);
+        one_sample(x);
+    }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double v = accs[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][k] = v;
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        double v = accm[p];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][K + p] = v;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < K + NP; p += blockDim.x) {
+        double v = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) v += red[wv][p];
+        partial[(size_t)blockIdx.x * (K + NP) + p] = v;
+    }
+}
+
+template <int K>
+static void launch_pass_reg(bool hess, int grid, cudaStream_t st, const double* u, long long N, const double* a, const double* rn,
+                            double* partial) {
+    const int smem = MB_STAGES * K * 256 * 16;
+    if (hess) {
+        cudaFuncSetAttribute(mbar_pass_reg_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        mbar_pass_reg_kernel<K, true><<<grid, 256, smem, st>>>(u, N, a, rn, partial);
+    } else {
+        cudaFuncSetAttribute(mbar_pass_reg_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        mbar_pass_reg_kernel<K, false><<<grid, 256, smem, st>>>(u, N, a, rn, partial);
+    }
+}
+
+// fixed-order reduction of the per-CTA partials: one warp per accumulator (lane-strided partial sums, then
+// the xor butterfly) -- deterministic for a given grid
 __global__ void mbar_finish_kernel(const double* __restrict__ partial, int n_blocks, int n_acc, double* __restrict__ out) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (p >= n_acc) return;
     double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += partial[(size_t)b * n_acc + p];
-    out[p] = s;
+    for (int b = lane; b < n_blocks; b += 32) s += partial[(size_t)b * n_acc + p];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[p] = s;
 }
 
 // populations: P[l][s] += W_nl, Q[l][s] += W_nl^2 for the state s of sample n (fp64 atomics).
@@ -163,6 +306,66 @@ mbar_pop_kernel(const double* __restrict__ u, long long N, int K, const double* 
                 const double w = Ws[k * MB_LD + t] * rn[k];
                 atomicAdd(P + (size_t)k * S + s, w);
                 atomicAdd(Q + (size_t)k * S + s, w * w);
+            }
+        }
+    }
+}
+
+// populations for small K: the weights of a sample stay in registers (same arithmetic as sample_weights), a
+// warp whose 32 samples share their state reduces with shuffles and issues one atomic pair per lambda
+template <int K>
+__global__ void __launch_bounds__(256)
+mbar_pop_reg_kernel(const double* __restrict__ u, long long N, const double* __restrict__ a_in,
+                    const double* __restrict__ rn_in, const int* __restrict__ state, int S, double* __restrict__ P,
+                    double* __restrict__ Q) {
+    double a[K], rn[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { a[k] = a_in[k]; rn[k] = rn_in[k]; }
+    const long long n_warp_tiles = (N + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long wt = warp0; wt < n_warp_tiles; wt += n_warps) {
+        const long long n = wt * 32 + lane;
+        const bool valid = n < N;
+        double w[K];
+        double mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            w[k] = valid ? a[k] - __ldcs(u + (size_t)k * N + n) : 0.0;
+            mx = fmax(mx, w[k]);
+        }
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            w[k] = exp(w[k] - mx);
+            sum += w[k];
+        }
+        const double inv = 1.0 / sum;
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[k] = valid ? (w[k] * inv) * rn[k] : 0.0;
+        const int s = valid ? state[n] : -1;
+        const int s0 = __shfl_sync(0xffffffffu, s, 0);
+        const bool uniform = __all_sync(0xffffffffu, s == s0 || !valid);
+        if (uniform) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double x = w[k], x2 = w[k] * w[k];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    x += __shfl_xor_sync(0xffffffffu, x, off);
+                    x2 += __shfl_xor_sync(0xffffffffu, x2, off);
+                }
+                if (lane == 0) {
+                    atomicAdd(P + (size_t)k * S + s0, x);
+                    atomicAdd(Q + (size_t)k * S + s0, x2);
+                }
+            }
+        } else if (valid) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                atomicAdd(P + (size_t)k * S + s, w[k]);
+                atomicAdd(Q + (size_t)k * S + s, w[k] * w[k]);
             }
         }
     }
@@ -218,6 +421,11 @@ static int mbar_work_init(MbarWork& w, int device, int K, long long N, const int
     w.n_acc_h = K + K * (K + 1) / 2;
     const long long tiles = (N + MB_TILE - 1) / MB_TILE;
     w.grid = (int)std::min<long long>(tiles, (long long)w.sms * 4);
+    if (K <= MB_REGK) {      // persistent CTAs of the staged small-K kernel: as many per SM as their shared memory allows
+        const int smem = MB_STAGES * K * 256 * 16;
+        const int per_sm = std::max(1, std::min(4, 220 * 1024 / smem));
+        w.grid = (int)std::min<long long>((N + 511) / 512, (long long)w.sms * per_sm);
+    }
     if (w.grid < 1) w.grid = 1;
     w.lnN.resize(K); w.rn.resize(K);
     for (int k = 0; k < K; ++k) {
@@ -243,9 +451,17 @@ static int mbar_pass(MbarWork& w, const double* d_u, const double* f, bool hess,
     BCP_CUDA(cudaMemcpyAsync(w.d_a, a.data(), K * 8, cudaMemcpyHostToDevice, st));
     const int n_acc = hess ? w.n_acc_h : K;
     const size_t sm = pass_smem(K, n_acc);
-    if (hess) mbar_pass_kernel<true><<<w.grid, MB_TILE, sm, st>>>(d_u, w.N, K, w.d_a, w.d_rn, w.d_partial, n_acc);
+    if (K <= MB_REGK) {
+        switch (K) {
+#define BCP_PASS(k) case k: launch_pass_reg<k>(hess, w.grid, st, d_u, w.N, w.d_a, w.d_rn, w.d_partial); break;
+            BCP_PASS(1) BCP_PASS(2) BCP_PASS(3) BCP_PASS(4) BCP_PASS(5) BCP_PASS(6)
+            BCP_PASS(7) BCP_PASS(8) BCP_PASS(9) BCP_PASS(10) BCP_PASS(11) BCP_PASS(12)
+#undef BCP_PASS
+        }
+    }
+    else if (hess) mbar_pass_kernel<true><<<w.grid, MB_TILE, sm, st>>>(d_u, w.N, K, w.d_a, w.d_rn, w.d_partial, n_acc);
     else mbar_pass_kernel<false><<<w.grid, MB_TILE, sm, st>>>(d_u, w.N, K, w.d_a, w.d_rn, w.d_partial, n_acc);
-    mbar_finish_kernel<<<(n_acc + 127) / 128, 128, 0, st>>>(w.d_partial, w.grid, n_acc, w.d_out);
+    mbar_finish_kernel<<<(n_acc * 32 + 127) / 128, 128, 0, st>>>(w.d_partial, w.grid, n_acc, w.d_out);
     BCP_LAUNCHED(2);
     BCP_CUDA(cudaGetLastError());
     std::vector<double> out(n_acc);
@@ -348,7 +564,16 @@ static int mbar_populations(MbarWork& w, const double* d_u, const double* f, con
     BCP_CUDA(cudaMemcpyAsync(w.d_a, a.data(), K * 8, cudaMemcpyHostToDevice, st));
     BCP_CUDA(cudaMemsetAsync(d_P, 0, (size_t)K * S * 8, st));
     BCP_CUDA(cudaMemsetAsync(d_Q, 0, (size_t)K * S * 8, st));
-    mbar_pop_kernel<<<w.grid, MB_TILE, pass_smem(K, 0), st>>>(d_u, w.N, K, w.d_a, w.d_rn, d_state, S, d_P, d_Q);
+    if (K <= MB_REGK) {
+        const int pgrid = (int)std::min<long long>((w.N + 255) / 256, (long long)w.sms * 8);
+        switch (K) {
+#define BCP_POP(k) case k: mbar_pop_reg_kernel<k><<<pgrid, 256, 0, st>>>(d_u, w.N, w.d_a, w.d_rn, d_state, S, d_P, d_Q); break;
+            BCP_POP(1) BCP_POP(2) BCP_POP(3) BCP_POP(4) BCP_POP(5) BCP_POP(6)
+            BCP_POP(7) BCP_POP(8) BCP_POP(9) BCP_POP(10) BCP_POP(11) BCP_POP(12)
+#undef BCP_POP
+        }
+    } else
+        mbar_pop_kernel<<<w.grid, MB_TILE, pass_smem(K, 0), st>>>(d_u, w.N, K, w.d_a, w.d_rn, d_state, S, d_P, d_Q);
     BCP_LAUNCHED(1);
     BCP_CUDA(cudaGetLastError());
     return BCP_OK;
@@ -434,9 +659,9 @@ static int mbar_impl(const double* d_u, const int32_t* d_state, const int64_t* N
     if (rc != BCP_OK) return rc;
     if (d_state && S > 0 && (pops || dpops)) {
         double *d_P = nullptr, *d_Q = nullptr;
-        BCP_CUDA(dev_alloc(&d_P, (size_t)K * S));
-        cudaError_t e = dev_alloc(&d_Q, (size_t)K * S);
-        if (e != cudaSuccess) { cudaFree(d_P); set_error("bcp_mbar: cudaMalloc: %s", cudaGetErrorString(e)); return BCP_ERR_CUDA; }
+        BCP_CUDA(cudaMallocAsync((void**)&d_P, (size_t)K * S * 8, st));          // stream-ordered pool, no device sync
+        cudaError_t e = cudaMallocAsync((void**)&d_Q, (size_t)K * S * 8, st);
+        if (e != cudaSuccess) { cudaFreeAsync(d_P, st); set_error("bcp_mbar: cudaMallocAsync: %s", cudaGetErrorString(e)); return BCP_ERR_CUDA; }
         rc = mbar_populations(w, d_u, f_k, d_state, S, d_P, d_Q, st);
         std::vector<double> P((size_t)K * S), Q((size_t)K * S);
         if (rc == BCP_OK) {
@@ -445,7 +670,7 @@ static int mbar_impl(const double* d_u, const int32_t* d_state, const int64_t* N
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) { set_error("bcp_mbar: copy back: %s", cudaGetErrorString(e)); rc = BCP_ERR_CUDA; }
         }
-        cudaFree(d_P); cudaFree(d_Q);
+        cudaFreeAsync(d_P, st); cudaFreeAsync(d_Q, st);
         if (rc != BCP_OK) return rc;
         mbar_finish_outputs(K, S, f_k, th.data(), P.data(), Q.data(), pops, dpops);
     }
