@@ -100,3 +100,28 @@ def test_device_resident_score_pipeline_equals_the_host_route():
     assert np.allclose(got["f"], f, atol=1e-9)
     with pytest.raises(RuntimeError):
         T.chains(4, 1).score()                              # nothing sampled yet
+
+
+def test_independent_runs_agree_with_the_reference_tutorial_score():
+    """north_star tolerances for independent runs: |delta score| < 0.05 kT against the score the reference stored
+    for its tutorial (docs/examples/Tutorials/Prep_Rest_Post_Ana/results/BS.dat: 0.3028 +- 0.0399, from its own
+    MT-seeded CPU run of 2 x 200 snapshots) and KL < 1e-3 between the populations of two of our runs."""
+    from biceps_b200 import engine
+    z, tabs, trajs = tutorial()
+    T = engine.DeviceTables(stack_lambdas(tabs))
+    n = 4096
+    lam = (np.arange(n) % 2).astype(np.int32)
+    runs = []
+    for seed in (1, 2):
+        blk = T.chains(n, seed, chain_lambda=lam)
+        blk.launch(20000, burn=2000, traj_every=100)
+        runs.append(blk.score(populations=True))
+        blk.close()
+    for r in runs:
+        assert abs((r["f"][1] - r["f"][0]) - z["BS"][1, 0]) < 0.05
+    assert abs(runs[0]["f"][1] - runs[1]["f"][1]) < 0.05
+    p, q = runs[0]["P"][:, 1], runs[1]["P"][:, 1]
+    m = (p > 0) & (q > 0)
+    assert float(np.sum(p[m] * np.log(p[m] / q[m]))) < 1e-3
+    # the most populated states are the reference's
+    assert list(np.argsort(-p)[:5]) == list(np.argsort(-z["populations"][:, 1])[:5])
