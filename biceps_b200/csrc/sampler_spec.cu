@@ -127,7 +127,7 @@ __host__ __device__ inline SpecLayout spec_layout(int L, int R, bool hg, int gh4
 }
 
 template <int L, int R, bool HG>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 1)
 mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                  const __grid_constant__ LaunchArgs A) {
     constexpr int D = SpecCfg<L>::D;
@@ -214,18 +214,26 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     int next_ev = A.state_trace ? 0 : next_snap;             // next step that must take the out-of-line path
 
     // ---- Philox block of one step, generated by the lane whose index is the step's batch position ----
-    uint32_t pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0, pk0 = 0, pk1 = 0;
+    // the 20 round keys are the same for every block of the launch: kept in registers (made opaque, so that
+    // the compiler does not re-derive them from the seed in every round)
+    uint32_t rk0[10], rk1[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        rk0[i] = seed_lo + (uint32_t)i * BCP_PHILOX_W0;
+        rk1[i] = seed_hi + (uint32_t)i * BCP_PHILOX_W1;
+        asm volatile("" : "+r"(rk0[i]), "+r"(rk1[i]));
+    }
+    uint32_t pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0;
     auto philox_begin = [&](int s) {
         const unsigned long long ctr = ctr0 + (unsigned long long)s;
-        pc0 = (uint32_t)ctr; pc1 = (uint32_t)(ctr >> 32); pc2 = ch_lo; pc3 = ch_hi; pk0 = seed_lo; pk1 = seed_hi;
+        pc0 = (uint32_t)ctr; pc1 = (uint32_t)(ctr >> 32); pc2 = ch_lo; pc3 = ch_hi;
     };
-    auto philox_round = [&]() {
+    auto philox_round = [&](int i) {
         const uint64_t p0 = (uint64_t)BCP_PHILOX_M0 * pc0;
         const uint64_t p1 = (uint64_t)BCP_PHILOX_M1 * pc2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ pc1 ^ pk0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ pc3 ^ pk1;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ pc1 ^ rk0[i];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ pc3 ^ rk1[i];
         pc1 = (uint32_t)p1; pc3 = (uint32_t)p0; pc0 = n0; pc2 = n2;
-        pk0 += BCP_PHILOX_W0; pk1 += BCP_PHILOX_W1;
     };
     auto philox_finish = [&](int s) {
         const bool nuis = pc0 < thresh;
@@ -375,7 +383,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         for (int b = 0; b < D; ++b) {
             philox_begin(b * L + q);
 #pragma unroll
-            for (int r = 0; r < 10; ++r) philox_round();
+            for (int r = 0; r < 10; ++r) philox_round(r);
             gen[b] = philox_finish(b * L + q);
             prefetch(gen[b], b * L + q, gm);
             wofs[b] = window_ofs();
@@ -417,7 +425,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 const int s = s0 + j;
 #pragma unroll
                 for (int r = 0; r < 10; ++r)
-                    if (r * L / 10 == j) philox_round();
+                    if (r * L / 10 == j) philox_round(r);
                 const bool nb = j + 1 == L;
                 const uint32_t dw_n = bcast_u(nb ? gen[1].dw : gen[0].dw, (j + 1) & (L - 1));
                 const float lu_n = bcast_f(nb ? gen[1].lu : gen[0].lu, (j + 1) & (L - 1));
@@ -514,7 +522,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
             next_ev = A.state_trace ? s0 + L : next_snap;
             philox_begin(s0 + D * L + q);
 #pragma unroll
-            for (int r = 0; r < 10; ++r) philox_round();
+            for (int r = 0; r < 10; ++r) philox_round(r);
         }
 
         // ---- end of batch: compact the histogram events of the warp into its queue and flush them with
