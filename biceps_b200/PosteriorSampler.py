@@ -164,7 +164,8 @@ class PosteriorSampler(object):
             start = [int(i) for R in self.ensemble[0] for i in R._param_start()]
             blk.set_state(indices=np.tile(np.array(start, np.int32), (self.nchains, 1)))
         every = int(self.traj_every)
-        o = blk.sample(int(nsteps), burn=int(burn), traj_every=every, record_state_trace=True)
+        # the reference keeps one state trace per sampler: chain 0 stands for it
+        o = blk.sample(int(nsteps), burn=int(burn), traj_every=every, record_state_trace=True, trace_chains=1)
         self._calls += 1
 
         # chain 0 -> the reference's attribute layout

@@ -46,7 +46,7 @@ class bcp_chain_cfg(C.Structure):
 
 class bcp_sample_cfg(C.Structure):
     _fields_ = [("n_steps", C.c_int64), ("burn", C.c_int64), ("traj_every", C.c_int64),
-                ("record_state_trace", C.c_int32), ("reserved", C.c_int32)]
+                ("record_state_trace", C.c_int32), ("trace_chains", C.c_int32)]
 
 
 class bcp_sample_out(C.Structure):

@@ -170,7 +170,7 @@ mcmc_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ Cha
         }
 
         if (s >= A.burn) {
-            if (A.state_trace) A.state_trace[(size_t)(s - A.burn) * n + c] = state;
+            if (A.state_trace && c < A.trace_n) A.state_trace[(size_t)(s - A.burn) * A.trace_n + c] = state;
             if (s == next_snap) {
                 const size_t o = (size_t)snap_idx * n + c;
                 A.traj_E[o] = E;
@@ -356,7 +356,7 @@ struct bcp_chains {
     int* d_lam = nullptr;
     int* d_group = nullptr;
     // outputs of the last sample() call
-    long long n_snap = 0, n_trace = 0;
+    long long n_snap = 0, n_trace = 0, trace_n = 0;
     double* d_traj_E = nullptr;
     int* d_traj_state = nullptr;
     unsigned char* d_traj_accept = nullptr;
@@ -684,12 +684,13 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
         c->cap_snap = (size_t)n_snap * n;
     }
     const long long n_trace = cfg->record_state_trace ? cfg->n_steps : 0;
-    if ((size_t)n_trace * n > c->cap_trace) {
+    const long long trace_n = (cfg->trace_chains > 0 && cfg->trace_chains < n) ? cfg->trace_chains : n;
+    if ((size_t)n_trace * trace_n > c->cap_trace) {
         pool_free(c->d_trace); c->d_trace = nullptr; c->cap_trace = 0;
-        BCP_CUDA(pool_alloc(&c->d_trace, (size_t)n_trace * n));
-        c->cap_trace = (size_t)n_trace * n;
+        BCP_CUDA(pool_alloc(&c->d_trace, (size_t)n_trace * trace_n));
+        c->cap_trace = (size_t)n_trace * trace_n;
     }
-    c->n_snap = n_snap; c->n_trace = n_trace;
+    c->n_snap = n_snap; c->n_trace = n_trace; c->trace_n = trace_n;
     // sep_accepted is per sample() call (PosteriorSampler.py:287)
     BCP_CUDA(cudaMemsetAsync(c->C.sep, 0, (size_t)(T.R + 1) * n * sizeof(unsigned long long), st));
 
@@ -705,7 +706,7 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     A.step0 = c->steps_done;
     A.burn = cfg->burn; A.traj_every = cfg->traj_every; A.n_snap = n_snap;
     A.traj_E = c->d_traj_E; A.traj_state = c->d_traj_state; A.traj_accept = c->d_traj_accept;
-    A.traj_idx = c->d_traj_idx; A.state_trace = n_trace ? c->d_trace : nullptr;
+    A.traj_idx = c->d_traj_idx; A.state_trace = n_trace ? c->d_trace : nullptr; A.trace_n = trace_n;
     const long long total = cfg->n_steps + cfg->burn;
     // the specialised kernel covers the canonical layout; BCP_FORCE_GENERIC=1 selects the generic one
     // kernel choice: BCP_KERNEL=generic|fast|coop overrides (BCP_FORCE_GENERIC=1 == generic)
@@ -867,7 +868,7 @@ extern "C" int bcp_chains_fetch(bcp_chains* c, bcp_sample_out* o) {
         D2H(o->traj_indices, c->d_traj_idx, (size_t)c->n_snap * n * T.P * 4);
         if (o->state_trace) {
             if (!c->n_trace) { set_error("bcp_chains_fetch: state_trace requested but not recorded"); return BCP_ERR_STATE; }
-            D2H(o->state_trace, c->d_trace, (size_t)c->n_trace * n * 4);
+            D2H(o->state_trace, c->d_trace, (size_t)c->n_trace * c->trace_n * 4);
         }
     }
 #undef D2H

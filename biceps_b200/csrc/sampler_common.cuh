@@ -31,7 +31,8 @@ struct LaunchArgs {
     int* traj_state;            // [n_snap][n]
     unsigned char* traj_accept; // [n_snap][n]
     int* traj_idx;              // [n_snap][P][n]
-    int* state_trace;           // [n_steps][n] or nullptr
+    int* state_trace;           // [n_steps][trace_n] or nullptr
+    long long trace_n;          // chains 0 .. trace_n-1 are traced
 };
 
 // number of recorded steps in [a, b): those with local step >= burn

@@ -227,7 +227,7 @@ mcmc_coop_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         }
 
         if (s >= burn) {
-            if (A.state_trace && lead) A.state_trace[(size_t)(A.s_begin + s - A.burn) * n + c] = state;
+            if (A.state_trace && lead && c < A.trace_n) A.state_trace[(size_t)(A.s_begin + s - A.burn) * A.trace_n + c] = state;
             if (s == next_snap) {
                 const size_t o = (size_t)snap_idx * n + c;
                 if (lead) {

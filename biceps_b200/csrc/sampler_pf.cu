@@ -219,7 +219,7 @@ mcmc_pf_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
         }
 
         if (s >= A.burn && lead) {
-            if (A.state_trace) A.state_trace[(size_t)(s - A.burn) * n + c] = state;
+            if (A.state_trace && c < A.trace_n) A.state_trace[(size_t)(s - A.burn) * A.trace_n + c] = state;
             if (s == next_snap) {
                 const size_t o = (size_t)snap_idx * n + c;
                 A.traj_E[o] = E;

@@ -126,7 +126,7 @@ __host__ __device__ inline SpecLayout spec_layout(int L, int R, bool hg, int gh4
     return o;
 }
 
-template <int L, int R, bool HG>
+template <int L, int R, bool HG, bool TRACE>
 __global__ void __launch_bounds__(128, 1)
 mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                  const __grid_constant__ LaunchArgs A) {
@@ -211,7 +211,10 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         const long long ns = A.burn + m * A.traj_every - A.s_begin;
         next_snap = ns < s_end ? (int)ns : -1;
     }
-    int next_ev = A.state_trace ? 0 : next_snap;             // next step that must take the out-of-line path
+    // the state only changes in the careful path, so a fast batch traces L copies of it at its end (TRACE
+    // kernels only: the extra code costs the untraced kernel ~6 % through ptxas' schedule)
+    const bool traced = TRACE && lead && c < A.trace_n;
+    int next_ev = next_snap;                                 // next step that must take the careful path
 
     // ---- Philox block of one step, generated by the lane whose index is the step's batch position ----
     // the 20 round keys are the same for every block of the launch: kept in registers (made opaque, so that
@@ -500,7 +503,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 }
                 x_prop = evaluate_exact(dw_n, s + 1, i2n);
                 if (s >= burn && s < s_end) {
-                    if (A.state_trace && lead) A.state_trace[(size_t)(A.s_begin + s - A.burn) * n + c] = state;
+                    if (TRACE && traced) A.state_trace[(size_t)(A.s_begin + s - A.burn) * A.trace_n + c] = state;
                     if (s == next_snap) {
                         const size_t o = (size_t)snap_idx * n + c;
                         if (lead) {
@@ -519,12 +522,17 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 d0 = (int)((dw_n >> fsh) & 3u) - 1;
                 g0 = (int)((dw_n >> 16) & 3u) - 1;
             }
-            next_ev = A.state_trace ? s0 + L : next_snap;
+            next_ev = next_snap;
             philox_begin(s0 + D * L + q);
 #pragma unroll
             for (int r = 0; r < 10; ++r) philox_round(r);
         }
 
+        if (TRACE && !careful && traced) {                    // fast batch: the state did not change
+#pragma unroll
+            for (int j = 0; j < L; ++j)
+                if (s0 + j >= burn && s0 + j < s_end) A.state_trace[(size_t)(A.s_begin + s0 + j - A.burn) * A.trace_n + c] = state;
+        }
         // ---- end of batch: compact the histogram events of the warp into its queue and flush them with
         //      one RED per 32 events; finish the generated batch, prefetch its state moves, rotate -------
         {
@@ -577,7 +585,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     }
 }
 
-template <int L, int R, bool HG>
+template <int L, int R, bool HG, bool TRACE>
 static cudaError_t launch_spec_one(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st,
                                    int sms) {
     const SpecLayout ly = spec_layout(L, R, HG, T.gh4_stride);
@@ -594,20 +602,22 @@ static cudaError_t launch_spec_one(const SamplerTables& T, const ChainBuffers& C
         if (smem + 64 <= (size_t)max_optin) break;
     }
     if (wpb < 1) return cudaErrorNotSupported;
-    cudaError_t e = cudaFuncSetAttribute(mcmc_spec_kernel<L, R, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mcmc_spec_kernel<L, R, HG, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int block = wpb * 32;
     const int grid = (int)((threads + block - 1) / block);
-    mcmc_spec_kernel<L, R, HG><<<grid, block, smem, st>>>(T, C, A);
+    mcmc_spec_kernel<L, R, HG, TRACE><<<grid, block, smem, st>>>(T, C, A);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mcmc_spec(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms) {
     if (!T.canonical || !T.div_safe || T.R < 1 || T.R > 8 || T.S < 1) return cudaErrorNotSupported;
     const bool hg = T.r[T.R - 1].has_gamma != 0;
+    const bool tr = A.state_trace != nullptr;
 #define BCP_SPEC(l, r)                                                                              \
     case r:                                                                                         \
-        return hg ? launch_spec_one<l, r, true>(T, C, A, st, sms) : launch_spec_one<l, r, false>(T, C, A, st, sms);
+        return tr ? (hg ? launch_spec_one<l, r, true, true>(T, C, A, st, sms) : launch_spec_one<l, r, false, true>(T, C, A, st, sms)) \
+                  : (hg ? launch_spec_one<l, r, true, false>(T, C, A, st, sms) : launch_spec_one<l, r, false, false>(T, C, A, st, sms));
     switch (T.R) {          // L = smallest of 2, 4, 8 that holds one lane per restraint
         BCP_SPEC(2, 1) BCP_SPEC(2, 2) BCP_SPEC(4, 3) BCP_SPEC(4, 4)
         BCP_SPEC(8, 5) BCP_SPEC(8, 6) BCP_SPEC(8, 7) BCP_SPEC(8, 8)

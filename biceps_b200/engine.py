@@ -12,7 +12,8 @@ def n_snapshots(n_steps, traj_every):
     return (n_steps + traj_every - 1) // traj_every if traj_every > 0 else 0
 
 
-def alloc_outputs(n_chains, n_groups, S, P, HB, n_steps, traj_every, record_state_trace, pool=None, reuse=None):
+def alloc_outputs(n_chains, n_groups, S, P, HB, n_steps, traj_every, record_state_trace, pool=None, reuse=None,
+                  trace_chains=0):
     """numpy buffers + the bcp_sample_out struct pointing at them.  With a PinnedPool the big
     trajectory buffers are page-locked (the returned dict keeps the pool alive under "_pool");
     `reuse` = a dict returned earlier for the same sizes: its buffers are used again."""
@@ -25,7 +26,8 @@ def alloc_outputs(n_chains, n_groups, S, P, HB, n_steps, traj_every, record_stat
              energy=np.zeros(n_chains, np.float64),
              traj_energy=big((ns, n_chains), np.float64), traj_state=big((ns, n_chains), np.int32),
              traj_accept=big((ns, n_chains), np.uint8), traj_indices=big((ns, P, n_chains), np.int32),
-             state_trace=big((n_steps if record_state_trace else 0, n_chains), np.int32))
+             state_trace=big((n_steps if record_state_trace else 0,
+                              trace_chains if 0 < trace_chains < n_chains else n_chains), np.int32))
     s = A.bcp_sample_out(A.i64ptr(o["state_counts"]), A.i64ptr(o["param_counts"]), A.i64ptr(o["accepted"]),
                          A.i64ptr(o["total"]), A.i64ptr(o["sep_accepted"]), A.i32ptr(o["state"]),
                          A.i32ptr(o["indices"]), A.dptr(o["energy"]),
@@ -102,9 +104,9 @@ class ChainBlock(object):
         A.check(self._lib.bcp_chains_create(tables._h, C.byref(cfg), C.byref(c)), "bcp_chains_create")
         self._c = c
 
-    def sample(self, n_steps, burn=0, traj_every=0, record_state_trace=False, pinned=False, out=None):
+    def sample(self, n_steps, burn=0, traj_every=0, record_state_trace=False, pinned=False, out=None, trace_chains=0):
         """Synchronous bcp_sample with host output buffers; returns a dict of numpy arrays
-        (pinned=True: page-locked trajectory buffers, owned by the returned dict's "_pool";
+        (trace_chains=k: only chains 0..k-1 are traced; pinned=True: page-locked trajectory buffers, owned by the returned dict's "_pool";
         out=<dict of an earlier call with the same sizes>: reuse its buffers)."""
         T = self.tables
         pool = A.PinnedPool() if (pinned and out is None) else None
@@ -113,16 +115,16 @@ class ChainBlock(object):
             if out["traj_energy"].shape != (ns, self.n_chains) or out["state_counts"].shape != (self.n_groups, T.n_states):
                 raise ValueError("out= buffers do not match this call's sizes")
         o, s = alloc_outputs(self.n_chains, self.n_groups, T.n_states, T.n_params, T.param_bins, int(n_steps),
-                             int(traj_every), bool(record_state_trace), pool, reuse=out)
+                             int(traj_every), bool(record_state_trace), pool, reuse=out, trace_chains=int(trace_chains))
         if pool is not None:
             o["_pool"] = pool
-        cfg = A.bcp_sample_cfg(int(n_steps), int(burn), int(traj_every), int(bool(record_state_trace)), 0)
+        cfg = A.bcp_sample_cfg(int(n_steps), int(burn), int(traj_every), int(bool(record_state_trace)), int(trace_chains))
         A.check(self._lib.bcp_sample(self._c, C.byref(cfg), C.byref(s)), "bcp_sample")
         return o
 
-    def launch(self, n_steps, burn=0, traj_every=0, record_state_trace=False, stream=None):
-        cfg = A.bcp_sample_cfg(int(n_steps), int(burn), int(traj_every), int(bool(record_state_trace)), 0)
-        self._last = (int(n_steps), int(traj_every), bool(record_state_trace))
+    def launch(self, n_steps, burn=0, traj_every=0, record_state_trace=False, stream=None, trace_chains=0):
+        cfg = A.bcp_sample_cfg(int(n_steps), int(burn), int(traj_every), int(bool(record_state_trace)), int(trace_chains))
+        self._last = (int(n_steps), int(traj_every), bool(record_state_trace), int(trace_chains))
         A.check(self._lib.bcp_sample_launch(self._c, C.byref(cfg), C.c_void_p(stream or 0)), "bcp_sample_launch")
 
     def sync(self):
@@ -130,9 +132,9 @@ class ChainBlock(object):
 
     def fetch(self):
         T = self.tables
-        n_steps, traj_every, rec = getattr(self, "_last", (0, 0, False))
+        n_steps, traj_every, rec, tc = getattr(self, "_last", (0, 0, False, 0))
         o, s = alloc_outputs(self.n_chains, self.n_groups, T.n_states, T.n_params, T.param_bins, n_steps,
-                             traj_every, rec)
+                             traj_every, rec, trace_chains=tc)
         A.check(self._lib.bcp_chains_fetch(self._c, C.byref(s)), "bcp_chains_fetch")
         return o
 

@@ -134,7 +134,8 @@ typedef struct bcp_sample_cfg {
     int64_t burn;
     int64_t traj_every;             /* 0: no snapshots */
     int32_t record_state_trace;     /* 1: keep state_trace (4 B/step/chain, :345) */
-    int32_t reserved;
+    int32_t trace_chains;           /* 0: trace every chain; k > 0: only chains 0 .. k-1 (the reference keeps one
+                                       trace per sampler; a drop-in sampler with many chains traces chain 0) */
 } bcp_sample_cfg;
 
 /* Host output buffers; any pointer may be NULL to skip that output.
@@ -156,7 +157,7 @@ typedef struct bcp_sample_out {
     int32_t* traj_state;        /* [n_snap][n_chains] */
     uint8_t* traj_accept;       /* [n_snap][n_chains] */
     int32_t* traj_indices;      /* [n_snap][P][n_chains] */
-    int32_t* state_trace;       /* [n_steps][n_chains] if record_state_trace */
+    int32_t* state_trace;       /* [n_steps][traced chains] if record_state_trace (traced chains = trace_chains or n_chains) */
 } bcp_sample_out;
 
 /* synchronous: launch, wait, copy results to the host buffers */

@@ -58,6 +58,20 @@ def test_given_initial_states_and_ragged_chain_count(cin):
     assert_outputs_equal(got, want)
 
 
+def test_state_trace_of_the_first_chains_only(cin):
+    """trace_chains = k keeps the state trace of chains 0..k-1 only ([n_steps][k]); everything else unchanged."""
+    from biceps_b200 import engine
+    from oracle import cbind
+    T = engine.DeviceTables(cin, device=0)
+    lam = (np.arange(50) % 2).astype(np.int32)
+    want = cbind.sample(cin, 50, 21, 3000, burn=7, traj_every=9, record_state_trace=True, chain_lambda=lam, n_threads=4)
+    for k in (1, 3):
+        got = T.chains(50, 21, chain_lambda=lam).sample(3000, burn=7, traj_every=9, record_state_trace=True, trace_chains=k)
+        assert got["state_trace"].shape == (3000, k)
+        assert np.array_equal(got["state_trace"], want["state_trace"][:, :k])
+        assert_outputs_equal({x: got[x] for x in got if x != "state_trace"}, {x: want[x] for x in want if x != "state_trace"})
+
+
 def test_no_snapshots_no_trace(cin):
     got, want = run_both(cin, 64, 5, 2000)
     assert_outputs_equal(got, want)
