@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbiceps_b200.so")
+# BCP_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("BCP_LIB") or os.path.join(_HERE, "lib", "libbiceps_b200.so")
 
 BCP_KIND_SCALAR, BCP_KIND_GAMMA, BCP_KIND_PFGRID = 0, 1, 2
 BCP_MAX_RESTRAINTS = 8

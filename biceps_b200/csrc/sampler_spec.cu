@@ -41,6 +41,21 @@
 
 namespace bcp {
 
+// tuning knobs (scripts/tune_spec.sh builds variants; the defaults are the measured best)
+#ifndef SPEC_EVAL_FIRST
+#define SPEC_EVAL_FIRST 0          // source order inside a step: candidates of step s+1 before / after resolving step s
+#endif
+#ifndef SPEC_MINBLOCKS
+#define SPEC_MINBLOCKS 1           // __launch_bounds__ second argument (register cap)
+#endif
+#ifndef SPEC_LDS_VOLATILE
+#define SPEC_LDS_VOLATILE 1        // shared-memory loads as volatile asm (pins their order in the PTX)
+#endif
+#if SPEC_LDS_VOLATILE
+#define SPEC_ASM asm volatile
+#else
+#define SPEC_ASM asm
+#endif
 #define SPEC_FULL 0xffffffffu
 #define SPEC_MARGIN 1.220703125e-4f      // 2^-13: >> fp32 error of ln(u) (< 1e-5) + rounding of (float)d (< 3e-6)
 constexpr int SPEC_WIN_BYTES = 80;       // 10 doubles
@@ -60,12 +75,12 @@ __device__ __forceinline__ double div_markstein(double a, double b, double y) {
 
 __device__ __forceinline__ double lds64(uint32_t addr) {
     double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    SPEC_ASM("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
     double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    SPEC_ASM("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, double2 v) {
@@ -127,7 +142,7 @@ __host__ __device__ inline SpecLayout spec_layout(int L, int R, bool hg, int gh4
 }
 
 template <int L, int R, bool HG, bool TRACE>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, SPEC_MINBLOCKS)
 mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                  const __grid_constant__ LaunchArgs A) {
     constexpr int D = SpecCfg<L>::D;
@@ -432,6 +447,9 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 const bool nb = j + 1 == L;
                 const uint32_t dw_n = bcast_u(nb ? gen[1].dw : gen[0].dw, (j + 1) & (L - 1));
                 const float lu_n = bcast_f(nb ? gen[1].lu : gen[0].lu, (j + 1) & (L - 1));
+#if SPEC_EVAL_FIRST
+                const Cand k = evaluate(dw_n, s + 1, nb ? wofs[1] : wofs[0], d0, g0);
+#endif
                 // (1) resolve step s: energy in the reference's summation order, accept in the log domain
                 double En = bcast_d(x_prop, 0);
 #pragma unroll
@@ -441,7 +459,9 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 const bool acc = tt > SPEC_MARGIN;
                 const bool unsure = !acc && !(tt < -SPEC_MARGIN);        // guard band, also NaN
                 // (2) contributions to step s+1 under both outcomes of step s
+#if !SPEC_EVAL_FIRST
                 const Cand k = evaluate(dw_n, s + 1, nb ? wofs[1] : wofs[0], d0, g0);
+#endif
                 rare = rare || unsure || (acc && (int)dw_s >= 0) || k.miss;
                 // (3) commit
                 commit(acc, s, En, ev_bin[j], ev_cnt[j]);
