@@ -37,7 +37,17 @@ struct Prefetch {
     double W[5];
 };
 
-template <int R, bool HG>
+// a / b with y = RN(1/b): bit-identical to IEEE division for the magnitudes SamplerTables::div_safe admits
+// (sampler_spec.cu:div_markstein); 5 dependent FMA-class operations instead of the ~20-instruction sequence
+__device__ __forceinline__ double fast_div(double a, double b, double y) {
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-q, b, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-q, b, a);
+    return __fma_rn(r, y, q);
+}
+
+template <int R, bool HG, bool MK>
 __global__ void __launch_bounds__(128)
 mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                  const __grid_constant__ LaunchArgs A) {
@@ -49,6 +59,12 @@ mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     if (threadIdx.x < R)
         s_meta[threadIdx.x] = make_int4(T.r[threadIdx.x].n_sigma, T.r[threadIdx.x].sig_off, T.r[threadIdx.x].hist_sigma, 0);
     stage_sigma_table(s_sig, T.sig_tab, T.sig_bytes, &mbar);        // contains a __syncthreads
+    // correctly rounded reciprocals of the staged words (used for the 2 sigma^2 entries only)
+    double* s_rcp = s_sig + T.sig_bytes / 8;
+    if (MK) {
+        for (int k = threadIdx.x; k < T.sig_bytes / 8; k += blockDim.x) s_rcp[k] = __drcp_rn(s_sig[k]);
+        __syncthreads();
+    }
 
     const long long n = C.n_chains;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,6 +89,30 @@ mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     const unsigned long long ctr0 = A.step0 + (unsigned long long)A.s_begin;
     const uint32_t seed_lo = (uint32_t)C.seed, seed_hi = (uint32_t)(C.seed >> 32);
     const uint32_t ch_lo = (uint32_t)chain_id, ch_hi = (uint32_t)(chain_id >> 32);
+
+    // the 20 Philox round keys are launch constants: kept in registers (opaque to the compiler, which would
+    // otherwise re-derive them from the seed in every round)
+    uint32_t rk0[10], rk1[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        rk0[i] = seed_lo + (uint32_t)i * BCP_PHILOX_W0;
+        rk1[i] = seed_hi + (uint32_t)i * BCP_PHILOX_W1;
+        asm volatile("" : "+r"(rk0[i]), "+r"(rk1[i]));
+    }
+    auto philox = [&](unsigned long long ctr) {
+        uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = ch_lo, c3 = ch_hi;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const uint64_t p0 = (uint64_t)BCP_PHILOX_M0 * c0;
+            const uint64_t p1 = (uint64_t)BCP_PHILOX_M1 * c2;
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk0[i];
+            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk1[i];
+            c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        }
+        Philox4 r;
+        r.w0 = c0; r.w1 = c1; r.w2 = c2; r.w3 = c3;
+        return r;
+    };
 
     // ---- chain state -------------------------------------------------------------------
     int state = C.state[c];
@@ -151,12 +191,13 @@ mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         const int gmn = HG ? wrap1(igm + dgm, G) : 0;
 
         // ---- operands of the R terms -----------------------------------------------------
-        double num[R], ref[R], av[R], dv[R];
+        double num[R], ref[R], av[R], dv[R], yv[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) {
             const int sq = (q == pick) ? sgn : isg[q];
             av[q] = s_sig[T.r[q].sig_off + sq];
             dv[q] = s_sig[T.r[q].sig_off + T.r[q].n_sigma + sq];
+            yv[q] = MK ? s_rcp[T.r[q].sig_off + T.r[q].n_sigma + sq] : 0.0;
             num[q] = nuis ? csse[q] : use.rec[q].x;
             ref[q] = nuis ? cref[q] : use.rec[q].y;
         }
@@ -171,7 +212,7 @@ mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         // ---- next step: RNG and, if it is a state move, its table words -------------------
         {
             const unsigned long long ctr = ctr0 + (unsigned long long)(s + 1);
-            wn = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), ch_lo, ch_hi, seed_lo, seed_hi);
+            wn = philox(ctr);
             if (!(wn.w0 < thresh)) prefetch(fill, (int)(((uint64_t)wn.w1 * (uint32_t)S) >> 32));
         }
 
@@ -179,7 +220,7 @@ mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         double En = Cn;
 #pragma unroll
         for (int q = 0; q < R; ++q) {
-            double t = __dadd_rn(av[q], __ddiv_rn(num[q], dv[q]));
+            double t = __dadd_rn(av[q], MK ? fast_div(num[q], dv[q], yv[q]) : __ddiv_rn(num[q], dv[q]));
             t = __dadd_rn(t, T.r[q].cnorm);
             t = __dsub_rn(t, ref[q]);
             En = __dadd_rn(En, t);
@@ -249,7 +290,7 @@ mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     };
 
     // ---- software pipeline: prologue, then two steps per iteration (ping-pong buffers) ------
-    Philox4 wa = philox4x32_10((uint32_t)ctr0, (uint32_t)(ctr0 >> 32), ch_lo, ch_hi, seed_lo, seed_hi), wb;
+    Philox4 wa = philox(ctr0), wb;
     Prefetch<R> pa, pb;
     pa.C = 0.0; pb.C = 0.0;
 #pragma unroll
@@ -287,13 +328,20 @@ mcmc_fast_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     }
 }
 
+template <int R, bool HG, bool MK>
+static cudaError_t launch_one_mk(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, int grid, int block,
+                                 cudaStream_t st) {
+    const int smem = T.sig_bytes * (MK ? 2 : 1);
+    cudaError_t e = cudaFuncSetAttribute(mcmc_fast_kernel<R, HG, MK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    mcmc_fast_kernel<R, HG, MK><<<grid, block, smem, st>>>(T, C, A);
+    return cudaGetLastError();
+}
 template <int R, bool HG>
 static cudaError_t launch_one(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, int grid, int block,
                               cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(mcmc_fast_kernel<R, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.sig_bytes);
-    if (e != cudaSuccess) return e;
-    mcmc_fast_kernel<R, HG><<<grid, block, T.sig_bytes, st>>>(T, C, A);
-    return cudaGetLastError();
+    // the reciprocal-table division needs every operand in the safe range checked by bcp_create
+    return T.div_safe ? launch_one_mk<R, HG, true>(T, C, A, grid, block, st) : launch_one_mk<R, HG, false>(T, C, A, grid, block, st);
 }
 
 cudaError_t launch_mcmc_fast(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, int grid, int block,
