@@ -300,6 +300,25 @@ def run_ours(args, rank, world, local_rank):
                  "biceps_score_lambda1": float(r5["f"][-1] - r5["f"][0]), "d_score": float(r5["dDelta_f"][0, -1]),
                  "chain_steps_per_s": n5 * steps5 / best[1], "note": "best of 2; tables resident, results on the host"}
 
+    # ---- C2 (BASELINE configs[1]): chignolin-scale, 1000 states, cs_H/cs_Ca/cs_N/J/NOE, 8 lambdas x 1024 chains ----
+    c2 = None
+    if world == 1:
+        ens2 = synthetic.make_ensemble("C2", seed=0, n_lambda=N_LAMBDA)
+        tabs2 = precompute.build_tables(ens2["energies"], ens2["lambdas"], ens2["restraints"], device=dev)
+        T2c = engine.DeviceTables(tabs2, device=dev)
+        n2, steps2 = 8 * 1024, 20000
+        b2c = T2c.chains(n2, SEED + 30, chain_lambda=(np.arange(n2) % N_LAMBDA).astype(np.int32))
+        b2c.launch(200, stream=stream)
+        ms2 = []
+        for _ in range(3):
+            b2c.launch(steps2, stream=stream)
+            b2c.sync()
+            ms2.append(b2c.last_kernel_ms()[0])
+        b2c.close(); T2c.close()
+        c2 = {"workload": "C2: 1000 states, R=5 (cs_H, cs_Ca, cs_N, J, NOE), 8 lambdas x 1024 chains, 20000 steps",
+              "value": n2 * steps2 / (min(ms2) * 1e-3), "unit": "chain-steps/s",
+              "kernel": "auto-selected (thread-per-chain kernel above one wave of the speculative kernel)"}
+
     # ---- C4 (BASELINE configs[3]): HDX protection factors on the 6-D grid, 1e5 states (1.3 GB of <N_c>/<N_h>
     #      counts in HBM), warp-per-chain kernel evaluating the term on the fly: the one HBM-bound sampler ----
     pf_c4 = None
@@ -379,7 +398,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "mcmc_steps_per_chain": N_MCMC_E2E, "traj_every": 100},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "saturated": saturated,
-            "score_pipeline": score, "pf_c4": pf_c4}
+            "score_pipeline": score, "c2": c2, "pf_c4": pf_c4}
     emit(line)
 
 
