@@ -21,10 +21,12 @@
 //   * All state-dependent words of a chain live in shared memory: the current state's record and its
 //     whole gamma row (periodic halo, so index +-2 needs no wrap), and, for the state moves of the
 //     next batches, the proposed state's record + a 10-wide gamma window, fetched with cp.async
-//     D batches (D L steps) ahead by the lane that generated that step's Philox block.  Chain blocks are
-//     laid out 16 B apart modulo the 128-B bank period, so the 8 chains of a warp never collide.
-//   * Lane j of a group generates the Philox block of position j of a batch of L steps; the 10 rounds are
-//     spread over the L steps of the batch D batches earlier (software pipelined by hand).
+//     two batches ahead by the lane that generated that step's Philox block (three batches of slots are
+//     alive: the current one, the next one, the one being generated).  Chain blocks are laid out 16 B apart
+//     modulo the 128-B bank period, so the 8 chains of a warp never collide.
+//   * Lane q of a group generates the Philox blocks of positions q, q + L, ... of a batch of BL steps
+//     (BL = 4 for L <= 4, 8 for L = 8; 8 was measured slower at L = 4); the 10 rounds of a block are spread
+//     over L steps of the batch two batches earlier (software pipelined by hand).
 //   * The sigma vectors {Ndof ln sigma, 2 sigma^2, 1/(2 sigma^2)} of all restraints are staged once per
 //     CTA by a 1-D TMA bulk copy (UBLKCP).
 //   * One step is ONE basic block.  ptxas turns every predicated RED into a divergent branch, so the
@@ -44,6 +46,9 @@ namespace bcp {
 // tuning knobs (scripts/tune_spec.sh builds variants; the defaults are the measured best)
 #ifndef SPEC_EVAL_FIRST
 #define SPEC_EVAL_FIRST 0          // source order inside a step: candidates of step s+1 before / after resolving step s
+#endif
+#ifndef SPEC_BL
+#define SPEC_BL(L) ((L) == 8 ? 8 : 4)     // steps per batch as a function of the lanes per chain
 #endif
 #ifndef SPEC_MINBLOCKS
 #define SPEC_MINBLOCKS 1           // __launch_bounds__ second argument (register cap)
@@ -122,11 +127,14 @@ struct SpecLayout {          // byte offsets inside a chain's shared-memory bloc
 
 template <int L>
 struct SpecCfg {
-    static constexpr int D = 3;                  // batches between the generation of a step and its batch
-    static constexpr int NSLOT = 4 * L;          // proposal slots per chain (4 batches, power of two)
+    static constexpr int BL = SPEC_BL(L);        // steps per batch (one basic block, one rollback unit)
+    static constexpr int NB = BL / L;            // Philox blocks a lane generates per batch
+    static constexpr int D = 2;                  // batches between the generation of a step and its batch
+    static constexpr int NBATCH = 3;             // batches whose proposal slots are alive (this, next, generated)
+    static constexpr int NSLOT = NBATCH * BL;    // proposal slots per chain
 };
 
-__host__ __device__ inline SpecLayout spec_layout(int L, int R, bool hg, int gh4_stride) {
+__host__ __device__ inline SpecLayout spec_layout(int nslot, int R, bool hg, int gh4_stride) {
     SpecLayout o;
     o.cur_rec = 0;
     o.cur_row = 16 * R;
@@ -134,7 +142,7 @@ __host__ __device__ inline SpecLayout spec_layout(int L, int R, bool hg, int gh4
     o.slot_c = 16 * R;
     o.slot_win = 16 * R + 16;
     o.slot_bytes = o.slot_win + (hg ? SPEC_WIN_BYTES : 0);
-    int b = o.slot0 + 4 * L * o.slot_bytes;
+    int b = o.slot0 + nslot * o.slot_bytes;
     b = (b + 15) & ~15;
     while ((b & 127) != 16) b += 16;      // consecutive chains start 16 B apart modulo the 128-B bank period
     o.chain_bytes = b;
@@ -146,6 +154,8 @@ __global__ void __launch_bounds__(128, SPEC_MINBLOCKS)
 mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                  const __grid_constant__ LaunchArgs A) {
     constexpr int D = SpecCfg<L>::D;
+    constexpr int BL = SpecCfg<L>::BL;
+    constexpr int NB = SpecCfg<L>::NB;
     constexpr int NSLOT = SpecCfg<L>::NSLOT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
@@ -187,15 +197,15 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     const uint32_t seed_lo = (uint32_t)C.seed, seed_hi = (uint32_t)(C.seed >> 32);
     const uint32_t ch_lo = (uint32_t)chain_id, ch_hi = (uint32_t)(chain_id >> 32);
 
-    const SpecLayout ly = spec_layout(L, R, HG, GS);
+    const SpecLayout ly = spec_layout(NSLOT, R, HG, GS);
     const uint32_t smem0 = smem_u32(smem_raw);
     const uint32_t chain_base = smem0 + (uint32_t)T.sig4_bytes + (uint32_t)(threadIdx.x / L) * (uint32_t)ly.chain_bytes;
     const uint32_t cur_rec = chain_base + ly.cur_rec + 16 * qr;
     const uint32_t cur_row = chain_base + ly.cur_row;
     const uint32_t slots = chain_base + ly.slot0;
-    // per-warp queue of histogram events {bin, count}: at most 2 per chain and step, 64 per batch
+    // per-warp queue of histogram events {bin, count}: at most 2 per chain and step, 128 per batch
     const uint32_t evq = smem0 + (uint32_t)T.sig4_bytes + (uint32_t)(blockDim.x / L) * (uint32_t)ly.chain_bytes +
-                         (uint32_t)(threadIdx.x >> 5) * 512u;
+                         (uint32_t)(threadIdx.x >> 5) * 1024u;
     const uint32_t lane_lt = (1u << (threadIdx.x & 31)) - 1u;
     const int nsig = T.r[qr].n_sigma;
     const uint32_t ent_base = smem0 + (uint32_t)SPEC_ENT_BYTES * (uint32_t)(T.ent_off[qr] + 2);   // entry of sigma index 0
@@ -271,10 +281,10 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         return g;
     };
     // cp.async of the proposed state's words for a generated state move into the step's slot
-    auto prefetch = [&](const SpecGen& g, int s, int gm_now) {
+    auto slot_of = [&](int sbatch, int j) { return slots + (uint32_t)(sbatch * BL + j) * (uint32_t)ly.slot_bytes; };
+    auto prefetch = [&](const SpecGen& g, uint32_t slot, int gm_now) {
         if (!((int)g.dw < 0)) {
             const uint32_t i2 = g.istate;
-            const uint32_t slot = slots + (uint32_t)(s & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
             const double* r2 = rec + (size_t)i2 * (2 * R);
 #pragma unroll
             for (int k = 0; k < R; ++k) cp_async16(slot + 16 * k, r2 + 2 * k);
@@ -296,7 +306,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     //      energy + logZ in lane 0.  A: on the committed state, B: on the committed state shifted by the
     //      pending step (d0, g0).  Window misses are only flagged here (out-of-line path re-evaluates).
     struct Cand { double xA, xB; int d1, g1; bool own, miss; };
-    auto evaluate = [&](uint32_t dn, int sn, int wofs, int d0_, int g0_) {
+    auto evaluate = [&](uint32_t dn, uint32_t slot, int wofs, int d0_, int g0_) {
         Cand k;
         const bool nuis_n = (int)dn < 0;
         k.own = (dn & own_mask) != 0u;
@@ -306,7 +316,6 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         const uint32_t eB = eA + (uint32_t)(SPEC_ENT_BYTES * d0_);
         const double nlA = lds64(eA), dvA = lds64(eA + 8), yA = lds64(eA + 16);
         const double nlB = lds64(eB), dvB = lds64(eB + 8), yB = lds64(eB + 16);
-        const uint32_t slot = slots + (uint32_t)(sn & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
         const uint32_t recaddr = nuis_n ? cur_rec : slot + 16 * qr;
         const double2 rv = lds128(recaddr);
         double numA = rv.x, numB = rv.x;
@@ -334,12 +343,11 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         return k;
     };
     // the same on the committed state only; the gamma value of a proposed state (i2) is read from global memory
-    auto evaluate_exact = [&](uint32_t dn, int sn, uint32_t i2) {
+    auto evaluate_exact = [&](uint32_t dn, uint32_t slot, uint32_t i2) {
         const bool nuis_n = (int)dn < 0;
         const int d1 = (int)((dn >> fsh) & 3u) - 1, g1 = (int)((dn >> 16) & 3u) - 1;
         const uint32_t eA = ent_base + (uint32_t)(SPEC_ENT_BYTES * (sg + d1));
         const double nlA = lds64(eA), dvA = lds64(eA + 8), yA = lds64(eA + 16);
-        const uint32_t slot = slots + (uint32_t)(sn & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
         const double2 rv = lds128(nuis_n ? cur_rec : slot + 16 * qr);
         double num = rv.x;
         if (HG) {
@@ -394,41 +402,47 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     };
 
     // ---- prologue: batches 0 .. D-1 generated and prefetched, contribution of step 0 ----------------
-    SpecGen gen[D];
+    // lane q generates positions q, q + L, ... of a batch: gen[b][m] = step (batch b) * BL + m * L + q
+    SpecGen gen[D][NB];
     int wofs[D + 1];
+    int sb0 = 0;                                             // slot batch of the current batch (0 .. NBATCH-1)
     {
 #pragma unroll
         for (int b = 0; b < D; ++b) {
-            philox_begin(b * L + q);
 #pragma unroll
-            for (int r = 0; r < 10; ++r) philox_round(r);
-            gen[b] = philox_finish(b * L + q);
-            prefetch(gen[b], b * L + q, gm);
+            for (int m = 0; m < NB; ++m) {
+                const int sp = b * BL + m * L + q;
+                philox_begin(sp);
+#pragma unroll
+                for (int r = 0; r < 10; ++r) philox_round(r);
+                gen[b][m] = philox_finish(sp);
+                prefetch(gen[b][m], slot_of(b, m * L + q), gm);
+            }
             wofs[b] = window_ofs();
         }
         wofs[D] = wofs[0];
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
-        dw_s = bcast_u(gen[0].dw, 0);
-        lu_s = bcast_f(gen[0].lu, 0);
+        dw_s = bcast_u(gen[0][0].dw, 0);
+        lu_s = bcast_f(gen[0][0].lu, 0);
         own_s = (dw_s & own_mask) != 0u;
         d0 = (int)((dw_s >> fsh) & 3u) - 1;
         g0 = (int)((dw_s >> 16) & 3u) - 1;
-        x_prop = evaluate_exact(dw_s, 0, bcast_u(gen[0].istate, 0));
+        x_prop = evaluate_exact(dw_s, slot_of(0, 0), bcast_u(gen[0][0].istate, 0));
     }
 
-    for (int s0 = 0; s0 < s_end; s0 += L) {
-        // everything this batch reads from the proposal slots has landed (issued >= one batch ago)
-        cp_async_wait<D - 2>();
-        __syncwarp();
-        uint32_t ev_bin[L], ev_cnt[L];
+    for (int s0 = 0; s0 < s_end; s0 += BL) {
+        const int sb1 = sb0 + 1 == SpecCfg<L>::NBATCH ? 0 : sb0 + 1;         // slot batch of the next batch
+        const int sb2 = sb1 + 1 == SpecCfg<L>::NBATCH ? 0 : sb1 + 1;         // ... of the batch generated now
+        uint32_t ev_bin[BL], ev_cnt[BL];
 #pragma unroll
-        for (int j = 0; j < L; ++j) { ev_bin[j] = 0; ev_cnt[j] = 0; }
+        for (int j = 0; j < BL; ++j) { ev_bin[j] = 0; ev_cnt[j] = 0; }
+        SpecGen gnew[NB];
 
-        // ---- fast batch: L steps as ONE basic block on registers only (shared memory is read, never
+        // ---- fast batch: BL steps as ONE basic block on registers only (shared memory is read, never
         //      written); anything rare only raises a flag and the batch is then redone carefully -------
-        bool careful = (unsigned)(next_ev - s0) < (unsigned)L;          // a snapshot / trace store falls into it
+        bool careful = (unsigned)(next_ev - s0) < (unsigned)BL;         // a snapshot falls into it
         if (!careful) {
             const double sv_E = E, sv_x = x_prop;
             const int sv_sg = sg, sv_gm = gm, sv_pg = pg, sv_ssg = since_sg, sv_sgm = since_gm, sv_d0 = d0, sv_g0 = g0;
@@ -437,18 +451,26 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
             const float sv_lu = lu_s;
             const bool sv_own = own_s;
             bool rare = false;
-            philox_begin(s0 + D * L + q);                    // the batch generated during this one
 #pragma unroll
-            for (int j = 0; j < L; ++j) {
+            for (int j = 0; j < BL; ++j) {
                 const int s = s0 + j;
+                // Philox: block m of the batch generated now runs its 10 rounds during steps m L .. m L + L - 1
+                if (j % L == 0) philox_begin(s0 + D * BL + j + q);
 #pragma unroll
                 for (int r = 0; r < 10; ++r)
-                    if (r * L / 10 == j) philox_round(r);
-                const bool nb = j + 1 == L;
-                const uint32_t dw_n = bcast_u(nb ? gen[1].dw : gen[0].dw, (j + 1) & (L - 1));
-                const float lu_n = bcast_f(nb ? gen[1].lu : gen[0].lu, (j + 1) & (L - 1));
+                    if (r * L / 10 == j % L) philox_round(r);
+                if (j % L == L - 1) gnew[j / L] = philox_finish(s0 + D * BL + (j / L) * L + q);
+                // the proposals of the next batch (requested one batch ago) are first read by the last step
+                if (j == BL - 1) {
+                    cp_async_wait<0>();
+                    __syncwarp();
+                }
+                const bool nb = j + 1 == BL;
+                const int jn = nb ? 0 : j + 1;
+                const uint32_t dw_n = bcast_u(nb ? gen[1][0].dw : gen[0][jn / L].dw, jn % L);
+                const float lu_n = bcast_f(nb ? gen[1][0].lu : gen[0][jn / L].lu, jn % L);
 #if SPEC_EVAL_FIRST
-                const Cand k = evaluate(dw_n, s + 1, nb ? wofs[1] : wofs[0], d0, g0);
+                const Cand k = evaluate(dw_n, slot_of(nb ? sb1 : sb0, jn), nb ? wofs[1] : wofs[0], d0, g0);
 #endif
                 // (1) resolve step s: energy in the reference's summation order, accept in the log domain
                 double En = bcast_d(x_prop, 0);
@@ -460,7 +482,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 const bool unsure = !acc && !(tt < -SPEC_MARGIN);        // guard band, also NaN
                 // (2) contributions to step s+1 under both outcomes of step s
 #if !SPEC_EVAL_FIRST
-                const Cand k = evaluate(dw_n, s + 1, nb ? wofs[1] : wofs[0], d0, g0);
+                const Cand k = evaluate(dw_n, slot_of(nb ? sb1 : sb0, jn), nb ? wofs[1] : wofs[0], d0, g0);
 #endif
                 rare = rare || unsure || (acc && (int)dw_s >= 0) || k.miss;
                 // (3) commit
@@ -472,23 +494,32 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 E = sv_E; x_prop = sv_x; sg = sv_sg; gm = sv_gm; pg = sv_pg; since_sg = sv_ssg; since_gm = sv_sgm;
                 d0 = sv_d0; g0 = sv_g0; acc_total = sv_at; acc_own = sv_ao; dw_s = sv_dw; lu_s = sv_lu; own_s = sv_own;
 #pragma unroll
-                for (int j = 0; j < L; ++j) ev_cnt[j] = 0;
+                for (int j = 0; j < BL; ++j) ev_cnt[j] = 0;
                 careful = true;
             }
         }
 
         // ---- careful batch: step by step, every rare case handled exactly -----------------------------
         if (careful) {
+            // generating lane and block of batch position jj (compile-time select chain: no dynamic register index)
+            auto g_dw = [&](int jj) { uint32_t v = gen[0][0].dw; _Pragma("unroll") for (int m = 1; m < NB; ++m) v = jj / L == m ? gen[0][m].dw : v; return v; };
+            auto g_lu = [&](int jj) { float v = gen[0][0].lu; _Pragma("unroll") for (int m = 1; m < NB; ++m) v = jj / L == m ? gen[0][m].lu : v; return v; };
+            auto g_is = [&](int jj) { uint32_t v = gen[0][0].istate; _Pragma("unroll") for (int m = 1; m < NB; ++m) v = jj / L == m ? gen[0][m].istate : v; return v; };
+            auto g_u = [&](int jj) { double v = gen[0][0].u; _Pragma("unroll") for (int m = 1; m < NB; ++m) v = jj / L == m ? gen[0][m].u : v; return v; };
 #pragma unroll 1
-            for (int j = 0; j < L; ++j) {
+            for (int j = 0; j < BL; ++j) {
                 const int s = s0 + j;
-                const bool nb = j + 1 == L;
-                const int jn = (j + 1) & (L - 1);
-                const uint32_t dw_n = bcast_u(nb ? gen[1].dw : gen[0].dw, jn);
-                const float lu_n = bcast_f(nb ? gen[1].lu : gen[0].lu, jn);
-                const uint32_t i2n = bcast_u(nb ? gen[1].istate : gen[0].istate, jn);
-                const uint32_t i2 = bcast_u(gen[0].istate, j);
-                const double u = bcast_d(gen[0].u, j);
+                if (j == BL - 1) {
+                    cp_async_wait<0>();
+                    __syncwarp();
+                }
+                const bool nb = j + 1 == BL;
+                const int jn = nb ? 0 : j + 1;
+                const uint32_t dw_n = bcast_u(nb ? gen[1][0].dw : g_dw(jn), jn % L);
+                const float lu_n = bcast_f(nb ? gen[1][0].lu : g_lu(jn), jn % L);
+                const uint32_t i2n = bcast_u(nb ? gen[1][0].istate : g_is(jn), jn % L);
+                const uint32_t i2 = bcast_u(g_is(j), j % L);
+                const double u = bcast_d(g_u(j), j % L);
                 double En = bcast_d(x_prop, 0);
 #pragma unroll
                 for (int r = 1; r < R; ++r) En = __dadd_rn(En, bcast_d(x_prop, r));
@@ -504,7 +535,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 const bool accst = acc && state_s;
                 if (__any_sync(SPEC_FULL, accst)) {
                     if (accst) {       // adopt the slot as the current state, reload the gamma row
-                        const uint32_t slot = slots + (uint32_t)(s & (NSLOT - 1)) * (uint32_t)ly.slot_bytes;
+                        const uint32_t slot = slot_of(sb0, j);
                         if (q < R) sts128(cur_rec, lds128(slot + 16 * qr));
                         if (q == 0) Cst = __dadd_rn(lds64(slot + ly.slot_c), logZ);
                         ++acc_state;
@@ -521,7 +552,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                     }
                     __syncwarp();
                 }
-                x_prop = evaluate_exact(dw_n, s + 1, i2n);
+                x_prop = evaluate_exact(dw_n, slot_of(nb ? sb1 : sb0, jn), i2n);
                 if (s >= burn && s < s_end) {
                     if (TRACE && traced) A.state_trace[(size_t)(A.s_begin + s - A.burn) * A.trace_n + c] = state;
                     if (s == next_snap) {
@@ -543,22 +574,27 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 g0 = (int)((dw_n >> 16) & 3u) - 1;
             }
             next_ev = next_snap;
-            philox_begin(s0 + D * L + q);
 #pragma unroll
-            for (int r = 0; r < 10; ++r) philox_round(r);
+            for (int m = 0; m < NB; ++m) {
+                const int sp = s0 + D * BL + m * L + q;
+                philox_begin(sp);
+#pragma unroll
+                for (int r = 0; r < 10; ++r) philox_round(r);
+                gnew[m] = philox_finish(sp);
+            }
         }
 
         if (TRACE && !careful && traced) {                    // fast batch: the state did not change
 #pragma unroll
-            for (int j = 0; j < L; ++j)
+            for (int j = 0; j < BL; ++j)
                 if (s0 + j >= burn && s0 + j < s_end) A.state_trace[(size_t)(A.s_begin + s0 + j - A.burn) * A.trace_n + c] = state;
         }
         // ---- end of batch: compact the histogram events of the warp into its queue and flush them with
-        //      one RED per 32 events; finish the generated batch, prefetch its state moves, rotate -------
+        //      one RED per 32 events; prefetch the state moves of the generated batch, rotate ---------------
         {
             uint32_t evn = 0;
 #pragma unroll
-            for (int j = 0; j < L; ++j) {
+            for (int j = 0; j < BL; ++j) {
                 const uint32_t m = __ballot_sync(SPEC_FULL, ev_cnt[j] != 0u);
                 if (ev_cnt[j] != 0u) {
                     const uint32_t at = evq + 8u * (evn + (uint32_t)__popc(m & lane_lt));
@@ -572,16 +608,19 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bin), "=r"(cnt) : "r"(evq + 8u * k));
                 atomicAdd(C.param_counts + bin, (unsigned long long)cnt);
             }
-            const int sb = s0 + D * L + q;
-            const SpecGen g = philox_finish(sb);
-            prefetch(g, sb, gm);
+#pragma unroll
+            for (int m = 0; m < NB; ++m) prefetch(gnew[m], slot_of(sb2, m * L + q), gm);
             cp_async_commit();
             wofs[D] = window_ofs();
 #pragma unroll
-            for (int b = 0; b + 1 < D; ++b) gen[b] = gen[b + 1];
-            gen[D - 1] = g;
+            for (int b = 0; b + 1 < D; ++b)
+#pragma unroll
+                for (int m = 0; m < NB; ++m) gen[b][m] = gen[b + 1][m];
+#pragma unroll
+            for (int m = 0; m < NB; ++m) gen[D - 1][m] = gnew[m];
 #pragma unroll
             for (int b = 0; b < D; ++b) wofs[b] = wofs[b + 1];
+            sb0 = sb1;
         }
     }
     cp_async_wait<0>();
@@ -608,7 +647,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
 template <int L, int R, bool HG, bool TRACE>
 static cudaError_t launch_spec_one(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st,
                                    int sms) {
-    const SpecLayout ly = spec_layout(L, R, HG, T.gh4_stride);
+    const SpecLayout ly = spec_layout(SpecCfg<L>::NSLOT, R, HG, T.gh4_stride);
     const long long threads = C.n_chains * L;
     const long long n_warps = (threads + 31) / 32;
     int wpb = (int)((n_warps + sms - 1) / sms);
@@ -618,7 +657,7 @@ static cudaError_t launch_spec_one(const SamplerTables& T, const ChainBuffers& C
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     size_t smem = 0;
     for (; wpb >= 1; --wpb) {
-        smem = (size_t)T.sig4_bytes + (size_t)(wpb * 32 / L) * ly.chain_bytes + (size_t)wpb * 512 + 128;
+        smem = (size_t)T.sig4_bytes + (size_t)(wpb * 32 / L) * ly.chain_bytes + (size_t)wpb * 1024 + 128;
         if (smem + 64 <= (size_t)max_optin) break;
     }
     if (wpb < 1) return cudaErrorNotSupported;
