@@ -526,8 +526,11 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 const double d = __dsub_rn(E, En);
                 const float tt = (float)d - lu_s;
                 const bool unsure = !(tt > SPEC_MARGIN) && !(tt < -SPEC_MARGIN);
-                const bool exact = s < s_end && ((En < E) || (d >= BCP_ACCEPT_CUTOFF && u < exp_det(d)));
-                const bool acc = unsure ? exact : tt > SPEC_MARGIN;
+                bool acc = tt > SPEC_MARGIN;
+                if (__any_sync(SPEC_FULL, unsure)) {                      // the specified exact rule, inside the guard band only
+                    const bool exact = s < s_end && ((En < E) || (d >= BCP_ACCEPT_CUTOFF && u < exp_det(d)));
+                    acc = unsure ? exact : acc;
+                }
                 const bool state_s = (int)dw_s >= 0;
                 uint32_t eb, ec;
                 commit(acc, s, En, eb, ec);
