@@ -59,6 +59,53 @@ class Analysis(object):
             raise ValueError("State number cannot be zero.")
         self.MBAR_analysis()
 
+    @classmethod
+    def from_samplers(cls, samplers, nstates, device=0, verbose=False):
+        """File-free route: BICePs scores and populations straight from sampler
+        objects that have been sampled in this process, one per lambda in ascending lambda order.  The
+        columnar snapshot arrays of EVERY chain of a sampler (`traj.chains`, nchains seeds) are the samples of
+        its lambda run (chain-major = Analysis.py:214 kln_to_kn order); no traj_lambda*.npz / .pkl round trip
+        and no Python list-of-lists.  Fills lam, K, N_k, u_kn, f_df, P_dP, Deltaf_ij, dDeltaf_ij like
+        MBAR_analysis (u_kln / states_kn, whose [K][K][Nmax] layout only makes sense for the file route, are
+        not built)."""
+        self = cls.__new__(cls)
+        self.verbose, self.device, self.nstates = verbose, int(device), int(nstates)
+        if self.nstates == 0:
+            raise ValueError("State number cannot be zero.")
+        self.sampler = list(samplers)
+        self.traj = [s.traj for s in self.sampler]
+        self.lam = [float(s.lam) for s in self.sampler]
+        self.K = self.nlambda = K = len(self.sampler)
+        self.scheme = self.sampler[0].rest_type
+        tabs = dict(self.sampler[0].tables)
+        tabs["energy"] = np.array([s.tables["energy"][0] for s in self.sampler])
+        tabs["logZ"] = np.array([s.tables["logZ"][0] for s in self.sampler])
+        T = engine.DeviceTables(tabs, device=self.device)
+        state, idx, N_k = [], [], []
+        for s in self.sampler:
+            ch = getattr(s.traj, "chains", None)
+            if ch is None or ch["state"].shape[0] == 0:
+                raise ValueError("from_samplers: every sampler must have been sampled (traj.chains is empty)")
+            ns, n = ch["state"].shape
+            state.append(np.ascontiguousarray(ch["state"].T).reshape(-1))                    # chain-major
+            idx.append(np.ascontiguousarray(ch["indices"].transpose(2, 0, 1)).reshape(ns * n, -1))
+            N_k.append(ns * n)
+        state = np.concatenate(state).astype(np.int32)
+        idx = np.concatenate(idx).astype(np.int32)
+        self.N_k = np.array(N_k)
+        self.u_kn = mbar.ukn(T, state, idx)                                                  # K6
+        r = mbar.mbar(self.u_kn, self.N_k, state, self.nstates, device=self.device)          # K7
+        T.close()
+        self.Deltaf_ij, self.dDeltaf_ij = r["Delta_f"], r["dDelta_f"]
+        self.mbar_iterations = r["iters"]
+        self.f_df = np.zeros((K, 2))
+        self.f_df[:, 0] = self.Deltaf_ij[0, :]
+        self.f_df[:, 1] = self.dDeltaf_ij[0, :]
+        self.P_dP = np.zeros((self.nstates, 2 * K))
+        self.P_dP[:, 0:K] = r["P"]
+        self.P_dP[:, K:2 * K] = r["dP"]
+        return self
+
     def load_data(self):
         """Trajectories (*.npz), their samplers (*.pkl) and the lambda values parsed from the
         file names (Analysis.py:74-116)."""

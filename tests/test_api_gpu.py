@@ -150,6 +150,45 @@ def test_many_chains_and_second_sample_call(dataset):
     assert s1.total == 1500 and len(s1.traj.trajectory) == 15 and len(s1.traj.sep_accept) == 4
 
 
+def test_analysis_from_samplers_without_files(dataset, tmp_path):
+    """Analysis.from_samplers (no npz / pkl round trip) gives the file route's numbers for one chain per
+    lambda, and uses every chain of a many-chain sampler."""
+    import biceps_b200 as biceps
+    d, z, t0, t1 = dataset
+    input_data = biceps.toolbox.sort_data(d)
+    out = str(tmp_path)
+    samplers = []
+    for lam in (0.0, 1.0):
+        ens = biceps.Ensemble(lam, z["raw_energies"])
+        ens.initialize_restraints(input_data, OPTS)
+        s = biceps.PosteriorSampler(ens, seed=5)
+        s.sample(10000, burn=500)
+        s.traj.process_results(os.path.join(out, "traj_lambda%2.2f.npz" % lam))
+        samplers.append(s)
+    A = biceps.Analysis(out, nstates=100, precheck=False)
+    B = biceps.Analysis.from_samplers(samplers, nstates=100)
+    assert B.K == 2 and B.lam == [0.0, 1.0] and list(B.N_k) == list(A.N_k)
+    assert np.array_equal(B.u_kn, A.u_kn)
+    assert np.allclose(B.f_df, A.f_df, atol=1e-12)
+    ok = ~np.isnan(A.P_dP)
+    assert np.array_equal(np.isnan(B.P_dP), ~ok) and np.allclose(B.P_dP[ok], A.P_dP[ok], rtol=1e-10, atol=1e-15)
+    scores = []
+    for seed in (9, 10):                                     # two independent many-chain runs
+        many = []
+        for lam in (0.0, 1.0):
+            ens = biceps.Ensemble(lam, z["raw_energies"])
+            ens.initialize_restraints(input_data, OPTS)
+            s = biceps.PosteriorSampler(ens, nchains=512, seed=seed)
+            s.sample(10000, burn=1000)
+            many.append(s)
+        Cn = biceps.Analysis.from_samplers(many, nstates=100)
+        assert list(Cn.N_k) == [512 * 100, 512 * 100]
+        assert Cn.f_df[1, 1] < 0.01 and abs(Cn.P_dP[:, :2].sum(axis=0) - 1.0).max() < 1e-9
+        scores.append(Cn.f_df[1, 0])
+    assert abs(scores[0] - scores[1]) < 0.05                 # north_star tolerance for independent runs
+    assert abs(scores[0] - A.f_df[1, 0]) < 5 * A.f_df[1, 1] + 0.05   # and consistent with the one-chain file route
+
+
 def test_from_arrays_bulk_constructor(dataset):
     import biceps_b200 as biceps
     d, z, t0, t1 = dataset
