@@ -383,6 +383,9 @@ Dictionary keys for {R.__name__} are any of: {possible_args}")
             exp = np.asarray(rd["exp"], np.float64)
             J = exp.shape[0]
             ri = rd.get("restraint_index", list(range(J)))
+            if "weight" in rd:                                  # shared by every state: summed once (reference order)
+                w_given = np.asarray(rd["weight"], np.float64)
+                ndof_given = precompute.ndof(w_given)
             objs = []
             for i in range(S):
                 o = R(**a1)
@@ -397,8 +400,7 @@ Dictionary keys for {R.__name__} are any of: {possible_args}")
                 o._exp, o._model = exp, model[i]
                 o._weight_option = rd.get("options", {}).get("weight", 1)
                 if "weight" in rd:
-                    o._weights = np.asarray(rd["weight"], np.float64)
-                    o.Ndof = precompute.ndof(o._weights)
+                    o._weights, o.Ndof = w_given, ndof_given
                 if R is Restraint_noe:
                     g = a2.get("gamma", [0.2, 10.0, 1.01])
                     o.allowed_gamma = np.exp(np.arange(np.log(g[0]), np.log(g[1]), np.log(g[2])))

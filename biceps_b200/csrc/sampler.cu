@@ -366,6 +366,7 @@ struct bcp_chains {
     cudaStream_t last_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk = nullptr;
     std::vector<int> h_lam;                 // lambda index of every chain (bcp_chains_score)
+    int spec_verdict = 0;                   // 0 undecided, 1 keep the speculative kernel, -1 its batches roll back too often
     cudaStream_t copy_stream = nullptr;     // device -> host copies of finished snapshots (bcp_sample)
     long long snaps_piped = 0;
     int last_launches = 0;
@@ -605,6 +606,8 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
     TRY_CUDA(pool_alloc(&C.sep, (size_t)(T.R + 1) * n));
     TRY_CUDA(pool_alloc(&C.state_counts, (size_t)n_groups * T.S));
     TRY_CUDA(pool_alloc(&C.param_counts, (size_t)n_groups * T.HB));
+    TRY_CUDA(pool_alloc(&C.spec_stats, 2));
+    TRY_CUDA(cudaMemset(C.spec_stats, 0, 2 * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.accepted, 0, n * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.sep, 0, (size_t)(T.R + 1) * n * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.state_counts, 0, (size_t)n_groups * T.S * sizeof(unsigned long long)));
@@ -635,6 +638,7 @@ extern "C" void bcp_chains_destroy(bcp_chains* c) {
     pool_free(c->d_lam); pool_free(c->d_group);
     pool_free(c->C.state); pool_free(c->C.isg); pool_free(c->C.igm); pool_free(c->C.ipf); pool_free(c->C.E);
     pool_free(c->C.accepted); pool_free(c->C.sep); pool_free(c->C.state_counts); pool_free(c->C.param_counts);
+    pool_free(c->C.spec_stats);
     pool_free(c->d_traj_E); pool_free(c->d_traj_state); pool_free(c->d_traj_accept); pool_free(c->d_traj_idx);
     pool_free(c->d_trace);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -722,9 +726,8 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     if (kern && T.canonical)
         which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : 2));
     if (force && force[0] == '1') which = 0;
-    const bool fast = which == 1;
     int fgrid = grid, fblock = block;
-    if (fast) {
+    {                                                        // launch shape of the thread-per-chain kernel
         int w = (int)((n_warps + sms - 1) / sms);
         w = w < 1 ? 1 : (w > 4 ? 4 : w);
         fblock = w * 32;
@@ -744,9 +747,27 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
         pipe = nullptr;
     }
     long long snaps_copied = 0;
-    for (long long s0 = 0; s0 < total; s0 += chunk) {
+    // The speculative kernel redoes a whole batch when any chain of a warp accepts a state move: fine when
+    // that is rare (C3: 0.2 % of the batches), slower than the thread-per-chain kernel when it is not (a
+    // 100-state ensemble with 16 chains per warp: 28 %).  Acceptance is a property of the ensemble, so a
+    // long auto-selected run starts with a short pilot launch whose rollback fraction decides; the verdict
+    // sticks to the chain block.  Every kernel produces the same bits, so this is invisible in the results.
+    const bool spec_auto = which == 3 && !(kern && T.canonical) && T.pf.q < 0;
+    if (spec_auto && c->spec_verdict < 0) which = 1;
+    const long long pilot = (spec_auto && c->spec_verdict == 0 && total >= 8192) ? 1024 : 0;
+    for (long long s0 = 0, s1 = 0; s0 < total; s0 = s1) {
+        s1 = (pilot && s0 == 0) ? pilot : s0 + chunk;
+        if (s1 > total) s1 = total;
         A.s_begin = s0;
-        A.s_end = s0 + chunk < total ? s0 + chunk : total;
+        A.s_end = s1;
+        if (pilot && s0 == pilot) {
+            unsigned long long stats[2] = {0, 0};
+            BCP_CUDA(cudaMemcpyAsync(stats, c->C.spec_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+            BCP_CUDA(cudaStreamSynchronize(st));
+            c->spec_verdict = (stats[0] > 0 && (double)stats[1] > 0.15 * (double)stats[0]) ? -1 : 1;
+            if (c->spec_verdict < 0) which = 1;
+        }
+        const bool fast = which == 1;
         cudaError_t e;
         if (T.pf.q >= 0) {
             // BCP_PF_KERNEL=generic forces the general warp-per-chain kernel (tests run both)

@@ -19,6 +19,7 @@ struct ChainBuffers {
     unsigned long long* sep;          // [R+1][n]  (this sample() call)
     unsigned long long* state_counts; // [groups][S]
     unsigned long long* param_counts; // [groups][HB]
+    unsigned long long* spec_stats;   // [2]: batches run / batches rolled back by the speculative kernel (kernel choice)
 };
 
 struct LaunchArgs {

@@ -221,6 +221,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     double Cst = q == 0 ? __dadd_rn(energy[state], logZ) : -0.0;
     int since_sg = burn, since_gm = burn, since_state = burn;
     unsigned int acc_own = 0, acc_state = 0, acc_total = 0;
+    unsigned int n_batches = 0, n_rollbacks = 0;             // per warp, for the host's kernel choice
 
     if (q < R) sts128(cur_rec, *reinterpret_cast<const double2*>(rec + ((size_t)state * R + q) * 2));
     if (HG) {
@@ -496,7 +497,9 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < BL; ++j) ev_cnt[j] = 0;
                 careful = true;
+                ++n_rollbacks;
             }
+            ++n_batches;
         }
 
         // ---- careful batch: step by step, every rare case handled exactly -----------------------------
@@ -549,9 +552,15 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                             state = (int)i2;
                         }
                         if (HG) {
+                            // the whole row by cp.async: the copies of a lane are all in flight at once (a load /
+                            // store loop pays one L2 round trip per 16 bytes: 7 us for a 1.4 KB row at L = 2)
                             const double2* src = reinterpret_cast<const double2*>(gh4 + (size_t)i2 * GS);
-                            for (int kk = q; kk < GS / 2; kk += L) sts128(cur_row + 16 * kk, __ldg(src + kk));
+                            for (int kk = q; kk < GS / 2; kk += L) cp_async16(cur_row + 16 * kk, src + kk);
                         }
+                    }
+                    if (HG) {
+                        cp_async_commit();
+                        cp_async_wait<0>();
                     }
                     __syncwarp();
                 }
@@ -628,6 +637,10 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
     }
     cp_async_wait<0>();
 
+    if ((threadIdx.x & 31) == 0 && n_batches) {
+        atomicAdd(C.spec_stats, (unsigned long long)n_batches);
+        if (n_rollbacks) atomicAdd(C.spec_stats + 1, (unsigned long long)n_rollbacks);
+    }
     // ---- flush run-length counters, persist the chain -------------------------------------
     if (lead) {
         if (s_end > since_state) atomicAdd(g_state_counts + state, (unsigned long long)(s_end - since_state));
