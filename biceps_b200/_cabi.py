@@ -65,6 +65,11 @@ class bcp_obs(C.Structure):
                 ("model", c_double_p), ("exp", c_double_p), ("weight", c_double_p), ("gamma", c_double_p)]
 
 
+class bcp_jsd_task(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("n_total", C.c_int64), ("n_first", C.c_int64), ("sel_offset", C.c_int64),
+                ("stream", C.c_uint64), ("n_bins", C.c_int32), ("mode", C.c_int32)]
+
+
 def _ptr(a, ctype):
     if a is None:
         return C.cast(None, C.POINTER(ctype))
@@ -191,6 +196,13 @@ _SIGS = {
                                C.c_double, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
     "bcp_chains_score": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_int32, c_int64_p, c_double_p, c_double_p,
                                    c_double_p, c_double_p, c_int32_p]),
+    "bcp_autocorr": (C.c_int, [c_double_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int, c_double_p, c_double_p]),
+    "bcp_autocorr_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "bcp_jsd": (C.c_int, [c_int32_p, C.c_int64, c_int32_p, C.c_int64, C.POINTER(bcp_jsd_task), C.c_int64, C.c_uint64,
+                          C.c_int, c_double_p]),
+    "bcp_param_hist": (C.c_int, [c_int32_p, C.c_int64, C.POINTER(bcp_jsd_task), C.c_int64, C.c_int32, C.c_int,
+                                 c_int64_p]),
     "bcp_mbar_pass_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, c_int64_p, c_double_p, C.c_int32, C.c_int,
                                     C.c_void_p, c_double_p, c_double_p]),
 }

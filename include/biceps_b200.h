@@ -247,6 +247,40 @@ int bcp_chains_score(bcp_chains* c, int32_t want_pops, double tol, int32_t max_i
 int bcp_mbar_pass_dev(const double* d_u_kn, int64_t n_local, int32_t K, const int64_t* N_k_global,
                       const double* f_k, int32_t want_hess, int device, void* stream, double* s_out, double* M_out);
 
+/* ---------------------------------------------------------------------------------------
+ * Convergence diagnostics of the sampled traces.
+ * Autocorrelation curves of n_series time series of length T (row-major [n_series][T]):
+ *   curves[s][tau] = sum_{t=0}^{T-2-tau} z[t] z[t+tau] / (T - tau),  z = f - mean(f),  tau = 0 .. max_tau,
+ * divided by curves[s][0] if normalize (convergence.py:93-111, g(); the last sample is left out of both
+ * factors exactly like the reference does), and tau[s] = sum_tau curves[s][tau] (compute_autocorrelation_time,
+ * :114-125; may be NULL).  Host pointers; the *_dev variant takes device pointers and is asynchronous on
+ * `stream`.  Agrees with the reference's np.dot to ~1e-13 of curves[s][0] (summation order).            */
+int bcp_autocorr(const double* series, int32_t n_series, int64_t T, int32_t max_tau, int32_t normalize,
+                 int device, double* curves, double* tau);
+int bcp_autocorr_dev(const double* d_series, int32_t n_series, int64_t T, int32_t max_tau, int32_t normalize,
+                     int device, void* stream, double* d_curves, double* d_tau);
+
+/* One Jensen-Shannon divergence (compute_JSD, convergence.py:145-186) of a parameter-index series
+ * idx[offset .. offset + n_total) split into a first part of n_first samples and the rest:
+ *   mode 0  first part = the first n_first samples            (Convergence.process :503-507)
+ *   mode 1  first part = positions sel[sel_offset .. + n_first) (the caller's np.random.choice draw, :509)
+ *   mode 2  first part = the n_first positions with the smallest keys (w0 << 32 | position), w0 the first word
+ *           of Philox4x32-10(counter = (position, stream), key = seed): a device-side random half          */
+typedef struct bcp_jsd_task {
+    int64_t offset;
+    int64_t n_total;
+    int64_t n_first;
+    int64_t sel_offset;
+    uint64_t stream;
+    int32_t n_bins;             /* length of the parameter's grid (<= 2048) */
+    int32_t mode;
+} bcp_jsd_task;
+int bcp_jsd(const int32_t* idx, int64_t n_idx, const int32_t* sel, int64_t n_sel, const bcp_jsd_task* tasks,
+            int64_t n_tasks, uint64_t seed, int device, double* jsd_out);
+/* counts[task][max_bins] = histogram of idx[offset .. offset + n_total) (block averaging, :462-480) */
+int bcp_param_hist(const int32_t* idx, int64_t n_idx, const bcp_jsd_task* tasks, int64_t n_tasks,
+                   int32_t max_bins, int device, int64_t* counts);
+
 #ifdef __cplusplus
 }
 #endif
