@@ -305,6 +305,115 @@ class Restraint_pf(Restraint):
                 self.xhs_index, self.bs_index]
 
 
+class Preparation(object):
+    """Writes the per-state input files of Ensemble.initialize_restraints (Restraint.py:896-1152): same
+    constructor, prepare_{cs,noe,J,pf} arguments, error messages, file names (`<state>.<ext>`) and DataFrame
+    columns as the reference.  All S frames of a restraint type are built from one [S][J] array instead of
+    S*J list appends.
+
+    Extension: `write_as="columnar"` writes ONE file per restraint type,
+    `<outdir>/ensemble.<ext>` (an npz holding model[S][J], exp[J], restraint_index[J] and the atom indices),
+    which `Ensemble.from_columnar` feeds straight to the precompute kernels: no S*R small files."""
+
+    _N_ATOMS = {"cs": 1, "noe": 2, "J": 4, "pf": 1}
+
+    def __init__(self, nstates=0, top_file=None, outdir=None):
+        self.nstates = nstates
+        if top_file is not None:
+            try:
+                import mdtraj as md
+            except ImportError as e:       # residue / atom-name columns need a topology reader
+                raise ImportError("Preparation(top_file=...) needs mdtraj to read the topology") from e
+            self.topology = md.load(top_file).topology
+        else:
+            self.topology = None
+        self.outdir = outdir
+
+    def to_sorted_list(self):
+        return toolbox.sort_data(self.outdir)
+
+    def write_DataFrame(self, filename, As="pickle", verbose=False):
+        if verbose:
+            print('Writing %s as %s...' % (filename, As))
+        getattr(pd.DataFrame(self.biceps_df), "to_%s" % As)(filename)
+
+    def _prepare(self, kind, ext, exp_data, model_data, indices, write_as, verbose, with_model=True):
+        import os
+        n_at = self._N_ATOMS[kind]
+        self.ind = toolbox.check_indices(indices)
+        self.exp_data = toolbox.check_exp_data(exp_data)
+        self.model_data = toolbox.check_model_data(model_data)
+        if int(len(self.model_data)) != int(self.nstates):
+            raise ValueError("The number of states doesn't equal to file numbers")
+        exp_data = np.asarray(self.exp_data)
+        if self.ind.shape[0] != exp_data.shape[0]:
+            raise ValueError('The number of atom pairs (%d) does not match the number of restraints (%d)! Exiting.'
+                             % (self.ind.shape[0], exp_data.shape[0]))
+        J = self.ind.shape[0]
+        atoms = self.ind.reshape(J, -1)[:, :n_at] if (kind != "cs") else self.ind.reshape(J, 1)
+        model = np.stack([np.asarray(np.loadtxt(m) if isinstance(m, str) else m, dtype=np.float64).reshape(-1)[:J]
+                          for m in self.model_data]) if with_model else None
+        ridx = exp_data[:, 0].astype(int)
+        exp = exp_data[:, 1].astype(np.float64)
+        self.header = ("exp",) + (("model",) if with_model else ()) + ("restraint_index",)
+        names = {}
+        if self.topology is not None:
+            by_index = {a.index: a for a in self.topology.atoms}
+        cols_tail = []
+        for a in range(n_at):
+            cols_tail.append(("atom_index%d" % (a + 1), atoms[:, a].astype(int)))
+            if self.topology is not None:
+                cols_tail.append(("res%d" % (a + 1), [str(by_index[int(x)].residue) for x in atoms[:, a]]))
+                if kind != "pf":
+                    cols_tail.append(("atom_name%d" % (a + 1), [str(by_index[int(x)].name) for x in atoms[:, a]]))
+        self.header += tuple(c for c, _ in cols_tail)
+        if write_as == "columnar":
+            if self.outdir:
+                out = dict(exp=exp, restraint_index=ridx, atoms=atoms.astype(np.int64), kind=np.array(kind),
+                           extension=np.array(ext))
+                if with_model:
+                    out["model"] = model
+                fn = os.path.join(self.outdir, "ensemble.%s" % ext)
+                with open(fn, "wb") as f:
+                    np.savez(f, **out)
+            return
+        for j in range(len(self.model_data)):
+            dd = {"exp": exp}
+            if with_model:
+                dd["model"] = model[j]
+            dd["restraint_index"] = ridx
+            for c, v in cols_tail:
+                dd[c] = v
+            self.biceps_df = pd.DataFrame(dd)
+            if verbose:
+                print(self.biceps_df)
+            if self.outdir:
+                self.write_DataFrame(os.path.join(self.outdir, "%s.%s" % (j, ext)), As=write_as, verbose=verbose)
+
+    def prepare_cs(self, exp_data, model_data, indices, extension, write_as="pickle", verbose=False):
+        """Chemical shifts; extension = nucleus "H" | "Ca" | "N" -> files `<state>.cs_<extension>` (:937-983)."""
+        self._prepare("cs", "cs_%s" % extension, exp_data, model_data, indices, write_as, verbose)
+
+    def prepare_noe(self, exp_data, model_data, indices, extension=None, write_as="pickle", verbose=False):
+        """NOE distances -> `<state>.noe` (:987-1033)."""
+        self._prepare("noe", "noe", exp_data, model_data, indices, write_as, verbose)
+
+    def prepare_J(self, exp_data, model_data, indices, extension=None, write_as="pickle", verbose=False):
+        """Scalar couplings -> `<state>.J` (:1036-1094)."""
+        self._prepare("J", "J", exp_data, model_data, indices, write_as, verbose)
+
+    def prepare_pf(self, exp_data, model_data=None, indices=None, extension=None, write_as="pickle", verbose=False):
+        """HDX protection factors -> `<state>.pf` (:1098-1152).  The reference's own method cannot run
+        (`check_model_data(None)` raises, and with model data its `if model_data:` on an array raises); here
+        model_data=None writes the experimental columns for `nstates` states (what Restraint_pf with
+        precomputed=False reads) and a model array adds the `model` column (precomputed=True)."""
+        if model_data is None:
+            model_data = [None] * int(self.nstates)
+            self._prepare("pf", "pf", exp_data, model_data, indices, write_as, verbose, with_model=False)
+        else:
+            self._prepare("pf", "pf", exp_data, model_data, indices, write_as, verbose)
+
+
 class Ensemble(object):
     """Container of restraint objects for every conformational state (Restraint.py:81-197)."""
 
@@ -416,6 +525,21 @@ Dictionary keys for {R.__name__} are any of: {possible_args}")
                 o._weights, o.Ndof = w, objs_per_k[k][0].Ndof
         self._finalize(device)
         return self
+
+    @classmethod
+    def from_columnar(cls, lam, energies, files, options=None, device=0):
+        """Ensemble from the one-file-per-restraint-type format `Preparation.prepare_*(write_as="columnar")`
+        writes: files in the order of `options`, e.g. ["d/ensemble.J", "d/ensemble.noe"]."""
+        options = options if options is not None else [dict() for _ in files]
+        rs = []
+        for fn, opt in zip(files, options):
+            z = np.load(fn, allow_pickle=False)
+            kind, ext = str(z["kind"]), str(z["extension"])
+            if "model" not in z:
+                raise ValueError("%s holds no model data" % fn)
+            rs.append(dict(cls=kind, extension=ext.split("_")[-1], model=z["model"], exp=z["exp"],
+                           restraint_index=z["restraint_index"].tolist(), options=opt))
+        return cls.from_arrays(lam, energies, rs, device=device)
 
     def _finalize(self, device):
         """Columnar tables + GPU SSE for each restraint type."""

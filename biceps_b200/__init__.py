@@ -2,7 +2,7 @@
 
 `import biceps_b200 as biceps` gives the names the reference exports on this path
 (/root/reference/biceps/__init__.py:8-22): Ensemble, get_restraint_options, PosteriorSampler,
-PosteriorSamplingTrajectory, Analysis, find_all_state_sampled_time, toolbox; the restraint classes
+PosteriorSamplingTrajectory, Analysis, find_all_state_sampled_time, Convergence, Preparation, toolbox; the restraint classes
 live at biceps.Restraint.Restraint_{cs,J,noe,pf} like in the reference.  Every compute step runs in
 the CUDA library (lib/libbiceps_b200.so); there is no CPU fallback.
 """
@@ -11,6 +11,7 @@ name = "biceps_b200"
 
 from . import toolbox                                          # noqa: F401
 from . import Restraint                                        # noqa: F401  (module, as in the reference)
-from .Restraint import Ensemble, get_restraint_options        # noqa: F401
+from .Restraint import Preparation, Ensemble, get_restraint_options        # noqa: F401
 from .PosteriorSampler import PosteriorSampler, PosteriorSamplingTrajectory   # noqa: F401
 from .Analysis import Analysis, find_all_state_sampled_time   # noqa: F401
+from .convergence import Convergence                           # noqa: F401

@@ -19,17 +19,21 @@
 #include "philox.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace bcp {
 
 // ------------------------------------------------------------------------------------------------
 // K8
 constexpr int AC_THREADS = 128;
-constexpr int AC_LPT = 8;                          // lags per thread
-constexpr int AC_LT = AC_THREADS * AC_LPT;         // lags per CTA
 constexpr int AC_TS = 1024;                        // time steps per CTA
-constexpr int AC_BW = AC_TS + AC_LT;               // window of the shifted factor
-__host__ __device__ constexpr int ac_pad(int i) { return i + (i >> 3); }   // one pad word per 8: stride 9
+// LPT lags per thread (8 or 16): a CTA covers AC_THREADS * LPT lags; the shifted factor's window is stored with
+// one pad word per LPT entries, so the threads' stride is LPT + 1 doubles: conflict-free 64-bit loads
+template <int LPT> struct AcCfg {
+    static constexpr int LT = AC_THREADS * LPT;
+    static constexpr int BW = AC_TS + LT;
+    __host__ __device__ static constexpr int pad(int i) { return i + i / LPT; }
+};
 
 // mean (fixed-order block reduction) and centred copy z = f - mean of every series
 __global__ void __launch_bounds__(256)
@@ -49,57 +53,60 @@ center_kernel(const double* __restrict__ f, long long T, double* __restrict__ z)
     for (long long t = threadIdx.x; t < T; t += 256) o[t] = s[t] - mean;
 }
 
-// partial[series][seg][lag] = sum over the segment's t of z[t] * z[t + lag], t + lag <= T - 2
+// partial[series][chunk][lag] = sum over the chunk's time segments of z[t] * z[t + lag], t + lag <= T - 2.
+// A CTA walks seg_per_chunk consecutive segments of AC_TS time steps with its accumulators in registers.
+template <int LPT>
 __global__ void __launch_bounds__(AC_THREADS)
-autocorr_partial_kernel(const double* __restrict__ z, long long T, int n_lags, int n_seg,
+autocorr_partial_kernel(const double* __restrict__ z, long long T, int n_lags, int n_seg, int seg_per_chunk,
                         double* __restrict__ partial) {
-    __shared__ double A[AC_TS];
-    __shared__ double B[ac_pad(AC_BW) + 8];
-    const int tile = blockIdx.x, seg = blockIdx.y, series = blockIdx.z;
+    using Cfg = AcCfg<LPT>;
+    __shared__ __align__(16) double A[AC_TS];
+    __shared__ double B[Cfg::pad(Cfg::BW) + LPT];
+    const int tile = blockIdx.x, chunk = blockIdx.y, series = blockIdx.z;
     const double* s = z + (size_t)series * T;
-    const long long t0 = (long long)seg * AC_TS;
-    const long long tau0 = (long long)tile * AC_LT;
+    const long long tau0 = (long long)tile * Cfg::LT;
     const long long last = T - 1;                   // index of the sample the reference leaves out
-    const int j8 = threadIdx.x * AC_LPT;            // first lag of this thread inside the tile
-    double* out = partial + ((size_t)series * n_seg + seg) * n_lags;
-    if (t0 + tau0 >= last) {                        // empty overlap: nothing to multiply
-        for (int k = 0; k < AC_LPT; ++k)
-            if (tau0 + j8 + k < n_lags) out[tau0 + j8 + k] = 0.0;
-        return;
-    }
-    for (int i = threadIdx.x; i < AC_TS; i += AC_THREADS) {
-        const long long t = t0 + i;
-        A[i] = (t < last) ? s[t] : 0.0;
-    }
-    for (int i = threadIdx.x; i < AC_BW; i += AC_THREADS) {
-        const long long t = t0 + tau0 + i;
-        B[ac_pad(i)] = (t < last) ? s[t] : 0.0;
-    }
-    __syncthreads();
-    double acc[AC_LPT];
-    double w[2 * AC_LPT];
+    const int j0 = threadIdx.x * LPT;               // first lag of this thread inside the tile
+    double acc[LPT];
 #pragma unroll
-    for (int k = 0; k < AC_LPT; ++k) {
-        acc[k] = 0.0;
-        w[k] = B[ac_pad(j8 + k)];
-    }
-    for (int t = 0; t < AC_TS; t += AC_LPT) {
-        // the next 8 window entries: indices j8 + t + 8 .. + 15 share one pad offset
-        const int base = ac_pad(j8 + t + AC_LPT);
-#pragma unroll
-        for (int k = 0; k < AC_LPT; ++k) w[AC_LPT + k] = B[base + k];
-#pragma unroll
-        for (int tt = 0; tt < AC_LPT; ++tt) {
-            const double a = A[t + tt];
-#pragma unroll
-            for (int k = 0; k < AC_LPT; ++k) acc[k] = fma(a, w[tt + k], acc[k]);
+    for (int k = 0; k < LPT; ++k) acc[k] = 0.0;
+    const int seg_end = min((chunk + 1) * seg_per_chunk, n_seg);
+    for (int seg = chunk * seg_per_chunk; seg < seg_end; ++seg) {
+        const long long t0 = (long long)seg * AC_TS;
+        if (t0 + tau0 >= last) break;               // empty overlap from here on
+        __syncthreads();
+        for (int i = threadIdx.x; i < AC_TS; i += AC_THREADS) {
+            const long long t = t0 + i;
+            A[i] = (t < last) ? s[t] : 0.0;
         }
+        for (int i = threadIdx.x; i < Cfg::BW; i += AC_THREADS) {
+            const long long t = t0 + tau0 + i;
+            B[Cfg::pad(i)] = (t < last) ? s[t] : 0.0;
+        }
+        __syncthreads();
+        double w[2 * LPT];
 #pragma unroll
-        for (int k = 0; k < AC_LPT; ++k) w[k] = w[AC_LPT + k];
+        for (int k = 0; k < LPT; ++k) w[k] = B[Cfg::pad(j0 + k)];
+#pragma unroll 2
+        for (int t = 0; t < AC_TS; t += LPT) {
+            // the next LPT window entries: indices j0 + t + LPT .. + 2 LPT - 1 share one pad offset
+            const int base = Cfg::pad(j0 + t + LPT);
+#pragma unroll
+            for (int k = 0; k < LPT; ++k) w[LPT + k] = B[base + k];
+#pragma unroll
+            for (int tt = 0; tt < LPT; ++tt) {
+                const double a = A[t + tt];
+#pragma unroll
+                for (int k = 0; k < LPT; ++k) acc[k] = fma(a, w[tt + k], acc[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < LPT; ++k) w[k] = w[LPT + k];
+        }
     }
+    double* out = partial + ((size_t)series * gridDim.y + chunk) * n_lags;
 #pragma unroll
-    for (int k = 0; k < AC_LPT; ++k) {
-        const long long lag = tau0 + j8 + k;
+    for (int k = 0; k < LPT; ++k) {
+        const long long lag = tau0 + j0 + k;
         if (lag < n_lags) out[lag] = acc[k];
     }
 }
@@ -274,21 +281,36 @@ hist_kernel(const int32_t* __restrict__ idx, const bcp_jsd_task* __restrict__ ta
 static int autocorr_run(const double* d_series, int32_t n_series, int64_t T, int32_t max_tau, int32_t normalize,
                         cudaStream_t st, double* d_curves, double* d_tau) {
     const int n_lags = max_tau + 1;
-    const int n_tiles = (n_lags + AC_LT - 1) / AC_LT;
-    // lags beyond T - 2 have an empty overlap: segments past the series' end are all zero
+    // 16 lags per thread once a CTA's 2048-lag tile is mostly used; BCP_AC_LPT overrides (tuning)
+    int lpt = (n_lags > 1536) ? 16 : 8;
+    if (const char* e = getenv("BCP_AC_LPT")) lpt = (atoi(e) == 16) ? 16 : 8;
+    const int lt = AC_THREADS * lpt;
+    const int n_tiles = (n_lags + lt - 1) / lt;
     const int n_seg = (int)((T + AC_TS - 1) / AC_TS);
+    // time segments are grouped into chunks (one CTA each, accumulators stay in registers) so that the launch
+    // still has a few waves of CTAs but the partial sums stay small: [n_series][n_chunk][n_lags]
+    const long long want_ctas = 148LL * 5 * 6;
+    long long n_chunk = (want_ctas + (long long)n_tiles * n_series - 1) / ((long long)n_tiles * n_series);
+    if (n_chunk > n_seg) n_chunk = n_seg;
+    if (n_chunk < 1) n_chunk = 1;
+    const int seg_per_chunk = (int)((n_seg + n_chunk - 1) / n_chunk);
+    n_chunk = (n_seg + seg_per_chunk - 1) / seg_per_chunk;
     double *z = nullptr, *partial = nullptr;
     BCP_CUDA(cudaMallocAsync((void**)&z, sizeof(double) * (size_t)n_series * T, st));
-    BCP_CUDA(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)n_series * n_seg * n_lags, st));
+    BCP_CUDA(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)n_series * n_chunk * n_lags, st));
     center_kernel<<<n_series, 256, 0, st>>>(d_series, T, z);
     for (int s0 = 0; s0 < n_series; s0 += 65535) {          // gridDim.z limit
         const int ns = (n_series - s0 < 65535) ? n_series - s0 : 65535;
-        dim3 grid(n_tiles, n_seg, ns);
-        autocorr_partial_kernel<<<grid, AC_THREADS, 0, st>>>(z + (size_t)s0 * T, T, n_lags, n_seg,
-                                                             partial + (size_t)s0 * n_seg * n_lags);
+        dim3 grid(n_tiles, (unsigned)n_chunk, ns);
+        if (lpt == 16)
+            autocorr_partial_kernel<16><<<grid, AC_THREADS, 0, st>>>(
+                z + (size_t)s0 * T, T, n_lags, n_seg, seg_per_chunk, partial + (size_t)s0 * n_chunk * n_lags);
+        else
+            autocorr_partial_kernel<8><<<grid, AC_THREADS, 0, st>>>(
+                z + (size_t)s0 * T, T, n_lags, n_seg, seg_per_chunk, partial + (size_t)s0 * n_chunk * n_lags);
         BCP_LAUNCHED(1);
     }
-    autocorr_finish_kernel<<<n_series, 256, 0, st>>>(partial, T, n_lags, n_seg, normalize, d_curves, d_tau);
+    autocorr_finish_kernel<<<n_series, 256, 0, st>>>(partial, T, n_lags, (int)n_chunk, normalize, d_curves, d_tau);
     BCP_LAUNCHED(2);
     BCP_CUDA(cudaGetLastError());
     BCP_CUDA(cudaFreeAsync(z, st));
@@ -304,8 +326,7 @@ extern "C" int bcp_autocorr_dev(const double* d_series, int32_t n_series, int64_
                                 int32_t normalize, int device, void* stream, double* d_curves, double* d_tau) {
     BCP_REQUIRE(d_series && d_curves, "bcp_autocorr_dev: NULL pointer");
     BCP_REQUIRE(n_series > 0 && T >= 2 && max_tau >= 0, "bcp_autocorr_dev: need n_series > 0, T >= 2, max_tau >= 0");
-    BCP_REQUIRE((T + AC_TS - 1) / AC_TS <= 65535, "bcp_autocorr_dev: series longer than %lld samples", 65535LL * AC_TS);
-    DeviceGuard g(device);
+        DeviceGuard g(device);
     return autocorr_run(d_series, n_series, T, max_tau, normalize, (cudaStream_t)stream, d_curves, d_tau);
 }
 
@@ -313,8 +334,7 @@ extern "C" int bcp_autocorr(const double* series, int32_t n_series, int64_t T, i
                             int device, double* curves, double* tau) {
     BCP_REQUIRE(series && curves, "bcp_autocorr: NULL pointer");
     BCP_REQUIRE(n_series > 0 && T >= 2 && max_tau >= 0, "bcp_autocorr: need n_series > 0, T >= 2, max_tau >= 0");
-    BCP_REQUIRE((T + AC_TS - 1) / AC_TS <= 65535, "bcp_autocorr: series longer than %lld samples", 65535LL * AC_TS);
-    DeviceGuard g(device);
+        DeviceGuard g(device);
     cudaStream_t st = 0;
     const size_t n_in = (size_t)n_series * T, n_out = (size_t)n_series * (max_tau + 1);
     double *d_in = nullptr, *d_out = nullptr, *d_tau = nullptr;

@@ -70,6 +70,59 @@ def list_extensions(input_data):
     return [res.split("_")[-1] for res in list_res(input_data)]
 
 
+def check_indices(indices):
+    """toolbox.py:152-159"""
+    if type(indices) == str:
+        indices = np.loadtxt(indices)
+    elif (type(indices) != np.ndarray) and (type(indices) != list):
+        raise TypeError(f"Requires a path to a file (str) OR data as \
+                list/np.ndarray object. You provides {type(indices)}.")
+    return np.array(indices).astype(int)
+
+
+def check_exp_data(exp_data):
+    """toolbox.py:161-167"""
+    if type(exp_data) == str:
+        exp_data = np.loadtxt(exp_data)
+    elif (type(exp_data) != np.ndarray) and (type(exp_data) != list):
+        raise TypeError(f"Requires a path to a file (str) OR data as \
+                list/np.ndarray object. You provides {type(exp_data)}.")
+    return exp_data
+
+
+def check_model_data(model_data):
+    """toolbox.py:169-176"""
+    if type(model_data) == str:
+        model_data = get_files(model_data)
+    elif (type(model_data) != np.ndarray) and (type(model_data) != list):
+        raise TypeError(f"Requires a path to glob files (str) OR data as \
+                list/np.ndarray object. You provides {type(model_data)}.")
+    return model_data
+
+
+def get_state_populations(file):
+    """toolbox.py:268-275"""
+    return np.loadtxt(file)[:][0]
+
+
+def print_scores(file):
+    """BICePs score out of a BS.dat file (toolbox.py:287-294)"""
+    return np.loadtxt(file)[1, 0]
+
+
+def npz_to_DataFrame(file, out_filename="traj_lambda0.00.pkl", verbose=False):
+    """Trajectory npz -> pandas DataFrame pickle (toolbox.py:297-318)."""
+    import pandas as pd
+    npz = np.load(file, allow_pickle=True)["arr_0"].item()
+    if verbose:
+        print(npz.keys())
+    traj = npz["trajectory"]
+    headers = [h.split()[0] for h in npz["trajectory_headers"]]
+    df = pd.DataFrame({h: [fr[k] for fr in traj] for k, h in enumerate(headers)}, columns=headers)
+    df.to_pickle(out_filename)
+    return df
+
+
 def save_object(obj, filename):
     with open(filename, "wb") as output:
         pickle.dump(obj, output, pickle.HIGHEST_PROTOCOL)

@@ -239,3 +239,36 @@ def test_pf_grid_through_the_api(tmp_path):
         e2 = biceps.Ensemble(1.0, g["raw_energies"])
         e2.initialize_restraints(files, [dict(opts, ref="gaussian")])
         biceps.PosteriorSampler(e2)
+
+
+def test_preparation_columnar_route_equals_the_file_route(tmp_path):
+    """Preparation -> per-state files -> initialize_restraints  ==  Preparation(write_as="columnar") ->
+    Ensemble.from_columnar: same tables, same chain."""
+    import biceps_b200 as biceps
+    z, t0, t1 = cineromycin_tables()
+    S = z["obs0_model"].shape[0]
+    J0, J1 = z["obs0_model"].shape[1], z["obs1_model"].shape[1]
+    exp0 = np.column_stack([z["obs0_restraint_index"], z["obs0_exp"]])
+    exp1 = np.column_stack([z["obs1_restraint_index"], z["obs1_exp"]])
+    ind0 = np.arange(4 * J0).reshape(J0, 4)
+    ind1 = np.arange(2 * J1).reshape(J1, 2)
+    samplers = []
+    for mode in ("pickle", "columnar"):
+        d = tmp_path / mode
+        d.mkdir()
+        p = biceps.Preparation(nstates=S, outdir=str(d))
+        p.prepare_J(exp0, list(z["obs0_model"]), ind0, write_as=mode)
+        p.prepare_noe(exp1, list(z["obs1_model"]), ind1, write_as=mode)
+        if mode == "pickle":
+            ens = biceps.Ensemble(1.0, z["raw_energies"])
+            ens.initialize_restraints(p.to_sorted_list(), OPTS)
+        else:
+            ens = biceps.Ensemble.from_columnar(1.0, z["raw_energies"], [str(d / "ensemble.J"), str(d / "ensemble.noe")], OPTS)
+        s = biceps.PosteriorSampler(ens, seed=3)
+        s.sample(3000)
+        samplers.append(s)
+    a, b = samplers
+    for k in range(2):
+        assert np.array_equal(a.tables["restraints"][k]["sse"], b.tables["restraints"][k]["sse"])
+        assert np.max(np.abs(a.tables["restraints"][k]["sse"] - t1["restraints"][k]["sse"]) / t1["restraints"][k]["sse"]) < 1e-11
+    assert a.traj.trajectory == b.traj.trajectory and a.traj.state_trace == b.traj.state_trace

@@ -40,7 +40,9 @@ def test_block_average_matches_reference(conv, gold):
 
 def test_exp_fit_matches_reference(conv, gold):
     conv.get_autocorrelation_curves(method="exp", maxtau=100)
-    assert np.allclose(conv.tau_c, gold["exp_tau"], rtol=1e-6)
+    # scipy's Levenberg-Marquardt stops at a relative step of ~1e-8 in the cost: curves that differ in the
+    # last bits end the iteration a few 1e-5 apart in tau
+    assert np.allclose(conv.tau_c, gold["exp_tau"], rtol=1e-3)
 
 
 def test_jsd_bootstrap_same_mt_stream(conv, gold, tmp_path):
@@ -116,9 +118,9 @@ def test_jsd_modes_edges_and_errors():
     h3 = CO.philox_first_half(333, 166, 4, 18); m3 = np.zeros(333, bool); m3[h3] = True
     want = [CO.jsd(x[:2500], x[2500:], x, 300), CO.jsd(x[m], x[~m], x, 300), CO.jsd(x[m2], x[~m2], x, 300),
             CO.jsd(y[m3], y[~m3], y, 7)]
-    assert np.allclose(got[:4], want, rtol=0, atol=1e-13)
-    # an empty part: the reference divides by N1 = 0 -> nan; here too
-    assert np.isnan(got[4]) and np.isnan(got[5]) and np.isnan(got[6])
+    # an empty part: the reference's 0/0 terms are zeroed by nan_to_num (convergence.py:178), JSD = H - H = 0
+    want += [CO.jsd(y[:0], y, y, 7), CO.jsd(y, y[:0], y, 7), CO.jsd(y[:0], y[:1], y[:1], 7)]
+    assert np.allclose(got, want, rtol=0, atol=1e-13) and not np.isnan(got).any()
     with pytest.raises(RuntimeError):
         BC.jsd_tasks(idx, [(0, 5000, 2500, 0, 0, 100, 0)])          # index >= n_bins
     with pytest.raises(RuntimeError):
@@ -136,7 +138,7 @@ def test_convergence_from_sampler_and_file(tmp_path):
           for r in ens["restraints"]]
     E = biceps.Ensemble.from_arrays(1.0, ens["energies"], rs)
     s = biceps.PosteriorSampler(E, freq_save_traj=10.)
-    s.sample(20000)
+    s.sample(200000)
     fn = str(tmp_path / "traj_lambda1.00.npz")
     s.traj.process_results(fn)
     a = Convergence(filename=fn, outdir=str(tmp_path))
