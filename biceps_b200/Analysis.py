@@ -162,6 +162,32 @@ class Analysis(object):
         self.P_dP[:, K:2 * K] = r["dP"]
         self.save_MBAR()
 
+    @staticmethod
+    def _field(t, key):
+        return t[key] if isinstance(t, dict) else getattr(t, key)
+
+    def get_max_likelihood_parameters(self, model=0, sigma_only=False):
+        """Most-sampled value of every nuisance parameter of trajectory `model` (Analysis.py:119-133)."""
+        import pandas as pd
+        t1 = self.traj[model]
+        out = {}
+        for k, rest in enumerate(self.scheme):
+            if sigma_only and "sigma" not in rest:
+                continue
+            x, y = self._field(t1, 'allowed_parameters')[k], self._field(t1, 'sampled_parameters')[k]
+            out[rest] = [x[np.argmax(y)]]
+        return pd.DataFrame(out)
+
+    def get_traces(self, traj_index=-1):
+        """DataFrame of the parameter traces, columns `<rest_type><occurrence>` (Analysis.py:240-267)."""
+        import pandas as pd
+        t = self.traj[traj_index]
+        seen, columns = {}, []
+        for rest in self._field(t, 'rest_type'):
+            columns.append("%s%d" % (rest, seen.get(rest, 0)))
+            seen[rest] = seen.get(rest, 0) + 1
+        return pd.DataFrame(np.array(self._field(t, 'traces')).transpose(), columns).transpose()
+
     def save_MBAR(self):
         np.savetxt(self.BSdir, self.f_df)
         np.savetxt(self.popdir, self.P_dP)
