@@ -60,6 +60,23 @@ def param_hist(idx, rows, max_bins, device=0):
     return out
 
 
+def chain_autocorrelation_times(sampler, maxtau=1000, device=0):
+    """Autocorrelation curve and time of every nuisance-parameter trace of EVERY chain of a many-chain
+    PosteriorSampler in one launch: -> autocorr[n_chains][P][maxtau+1], tau_c[n_chains][P].  Chain c, parameter
+    p equals Convergence.from_sampler(sampler, chain=c).get_autocorrelation_curves("auto", maxtau=maxtau)."""
+    t = sampler.traj
+    if t.chains is None:
+        raise ValueError("the sampler has not sampled yet")
+    idx = t.chains["indices"]                                   # [T][P][n_chains]
+    T, P, n = idx.shape
+    allowed = [np.asarray(a, dtype=np.float64) for a in t.allowed_parameters]
+    series = np.empty((n, P, T))
+    for p in range(P):
+        series[:, p, :] = allowed[p][idx[:, p, :]].T
+    curves, tau = autocorrelation(series.reshape(n * P, T), maxtau, True, device)
+    return curves.reshape(n, P, int(maxtau) + 1), tau.reshape(n, P)
+
+
 # --------------------------------------------------------------------------------------------------
 # module functions of the reference (same names)
 def single_exp_decay(x, a0, a1, tau1):

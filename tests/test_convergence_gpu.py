@@ -151,3 +151,22 @@ def test_convergence_from_sampler_and_file(tmp_path):
     assert np.array_equal(a.all_JSDs, b.all_JSDs) and np.array_equal(a.all_JSDs, c.all_JSDs)
     want = CO.autocorrelation_curves(a.sampled_parameters, 200, True)
     assert np.allclose(a.autocorr, want, rtol=0, atol=1e-12)
+
+
+def test_all_chains_in_one_launch():
+    import biceps_b200 as biceps
+    from biceps_b200 import synthetic
+    from biceps_b200.convergence import Convergence, chain_autocorrelation_times
+    ens = synthetic.make_ensemble("C1s", seed=2)
+    rs = [dict(cls="J" if r["name"] == "J" else "noe", model=r["model"], exp=r["exp"], weight=r["weight"],
+               options=dict(ref=r["ref"], sigma=r["sigma"], **({"gamma": r["gamma"]} if "gamma" in r else {})))
+          for r in ens["restraints"]]
+    E = biceps.Ensemble.from_arrays(1.0, ens["energies"], rs)
+    s = biceps.PosteriorSampler(E, freq_save_traj=10., nchains=64, seed=4)
+    s.sample(30000)
+    ac, tau = chain_autocorrelation_times(s, maxtau=150)
+    assert ac.shape == (64, 3, 151) and tau.shape == (64, 3)
+    for c in (0, 17, 63):
+        C = Convergence.from_sampler(s, chain=c, outdir=None)
+        C.get_autocorrelation_curves(method="auto", maxtau=150)
+        assert np.array_equal(C.autocorr, ac[c]) and np.array_equal(C.tau_c, tau[c])
