@@ -10,6 +10,9 @@ Differences a user can see, all deliberate:
   * the RNG is counter-based Philox4x32-10 (oracle/philox.py is its specification), not numpy's
     global MT19937; `seed=None` draws the seed from numpy's global stream, so np.random.seed(x)
     before constructing the sampler still makes a run reproducible;
+  * `rng="numpy"` (one chain) instead consumes np.random's global MT19937 stream draw for draw like the
+    reference: after np.random.seed(x) the trajectory, traces and histograms are the reference's own, bit for
+    bit (csrc/sampler_mt.cu; a compatibility path, ~1e6 steps/s);
   * `nchains` (default 1) runs that many independent chains; histograms (state_counts,
     sampled_parameters) are summed over them, the trajectory / traces / state_trace attributes are
     those of chain 0 and `traj.chains` holds every chain's thinned snapshots as arrays.
@@ -58,7 +61,7 @@ def build_tables(ensembles, device=0):
 class PosteriorSampler(object):
 
     def __init__(self, ensemble, freq_write_traj=100., freq_save_traj=100., verbose=False, nchains=1, seed=None,
-                 device=0):
+                 device=0, rng="philox"):
         self.lam = ensemble.lam
         self.ensemble = ensemble.to_list()
         self.nreplicas = 1
@@ -67,7 +70,18 @@ class PosteriorSampler(object):
         self.nstates = len(self.ensemble)
         self.nchains = int(nchains)
         self.device = int(device)
-        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        if rng not in ("philox", "numpy"):
+            raise ValueError("rng must be 'philox' or 'numpy'")
+        if rng == "numpy" and self.nchains != 1:
+            raise ValueError("rng='numpy' replays the reference's single chain on np.random's stream: nchains must be 1")
+        self.rng = rng
+        self._init_state = None
+        if rng == "numpy":
+            # the reference's own draw of the initial state (PosteriorSampler.py:29)
+            self._init_state = np.random.randint(low=0, high=self.nstates, size=self.nreplicas).astype(np.int32)
+            self.seed = 0
+        else:
+            self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
         self.E = 1.0e99
         self.accepted = 0
         self.total = 0
@@ -112,7 +126,9 @@ class PosteriorSampler(object):
             self._device_tables = engine.DeviceTables(self.tables, device=self.device)
         if self._chains is None:
             self._chains = self._device_tables.chains(self.nchains, self.seed, n_groups=1,
-                                                      chain_group=np.zeros(self.nchains, np.int32))
+                                                      chain_group=np.zeros(self.nchains, np.int32),
+                                                      init_state=getattr(self, "_init_state", None),
+                                                      rng_mode=1 if getattr(self, "rng", "philox") == "numpy" else 0)
 
     def __getstate__(self):
         d = dict(self.__dict__)
@@ -165,7 +181,8 @@ class PosteriorSampler(object):
             blk.set_state(indices=np.tile(np.array(start, np.int32), (self.nchains, 1)))
         every = int(self.traj_every)
         # the reference keeps one state trace per sampler: chain 0 stands for it
-        o = blk.sample(int(nsteps), burn=int(burn), traj_every=every, record_state_trace=True, trace_chains=1)
+        run = blk.sample_numpy_stream if getattr(self, "rng", "philox") == "numpy" else blk.sample
+        o = run(int(nsteps), burn=int(burn), traj_every=every, record_state_trace=True, trace_chains=1)
         self._calls += 1
 
         # chain 0 -> the reference's attribute layout

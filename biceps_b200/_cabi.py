@@ -41,7 +41,7 @@ class bcp_tables(C.Structure):
 
 class bcp_chain_cfg(C.Structure):
     _fields_ = [("n_chains", C.c_int64), ("seed", C.c_uint64), ("chain_id0", C.c_uint64),
-                ("n_groups", C.c_int32), ("reserved", C.c_int32),
+                ("n_groups", C.c_int32), ("rng_mode", C.c_int32),
                 ("chain_lambda", c_int32_p), ("chain_group", c_int32_p), ("init_state", c_int32_p)]
 
 
@@ -175,6 +175,8 @@ _SIGS = {
     "bcp_param_layout": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p]),
     "bcp_chains_create": (C.c_int, [C.c_void_p, C.POINTER(bcp_chain_cfg), C.POINTER(C.c_void_p)]),
     "bcp_chains_destroy": (None, [C.c_void_p]),
+    "bcp_chains_set_mt_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.c_int64]),
+    "bcp_chains_mt_consumed": (C.c_int, [C.c_void_p, c_int64_p]),
     "bcp_sample": (C.c_int, [C.c_void_p, C.POINTER(bcp_sample_cfg), C.POINTER(bcp_sample_out)]),
     "bcp_sample_launch": (C.c_int, [C.c_void_p, C.POINTER(bcp_sample_cfg), C.c_void_p]),
     "bcp_chains_sync": (C.c_int, [C.c_void_p]),

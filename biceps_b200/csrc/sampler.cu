@@ -371,6 +371,12 @@ struct bcp_chains {
     long long snaps_piped = 0;
     int last_launches = 0;
     bool sampled = false;
+    // reference-stream mode (bcp_chain_cfg.rng_mode == 1): numpy's MT19937 outputs, one chain
+    int rng_mode = 0;
+    uint32_t* d_mt_raw = nullptr;
+    long long mt_len = 0;
+    long long* d_mt_pos = nullptr;
+    int* d_mt_dry = nullptr;
 };
 
 template <typename T>
@@ -582,8 +588,12 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
             BCP_REQUIRE(cfg->init_state[i] >= 0 && cfg->init_state[i] < T.S,
                         "bcp_chains_create: init_state[%lld]=%d out of range", i, cfg->init_state[i]);
     }
+    BCP_REQUIRE(cfg->rng_mode == 0 || cfg->rng_mode == 1, "bcp_chains_create: rng_mode must be 0 (Philox) or 1 (MT19937 stream)");
+    BCP_REQUIRE(cfg->rng_mode == 0 || (n == 1 && T.pf.q < 0),
+                "bcp_chains_create: the MT19937 stream mode runs one chain and no PF-grid restraint");
     bcp_chains* c = new bcp_chains();
     c->h = h;
+    c->rng_mode = cfg->rng_mode;
     ++h->refs;
     c->n_groups = n_groups;
     c->h_lam = lam;
@@ -635,6 +645,7 @@ extern "C" void bcp_chains_destroy(bcp_chains* c) {
     if (!c) return;
     DeviceGuard guard(c->h->device);
     if (c->sampled) cudaStreamSynchronize(c->last_stream);      // frees are ordered on the default stream only
+    pool_free(c->d_mt_raw); pool_free(c->d_mt_pos); pool_free(c->d_mt_dry);
     pool_free(c->d_lam); pool_free(c->d_group);
     pool_free(c->C.state); pool_free(c->C.isg); pool_free(c->C.igm); pool_free(c->C.ipf); pool_free(c->C.E);
     pool_free(c->C.accepted); pool_free(c->C.sep); pool_free(c->C.state_counts); pool_free(c->C.param_counts);
@@ -733,6 +744,10 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
         fblock = w * 32;
         fgrid = (int)((n + fblock - 1) / fblock);
     }
+    if (c->rng_mode == 1) {
+        if (!c->d_mt_raw) { set_error("bcp_sample: MT19937 stream mode needs bcp_chains_set_mt_stream first"); return BCP_ERR_STATE; }
+        pipe = nullptr;
+    }
     BCP_CUDA(cudaEventRecord(c->ev0, st));
     int launches = 0;
     long long chunk = kMaxStepsPerLaunch;
@@ -769,7 +784,11 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
         }
         const bool fast = which == 1;
         cudaError_t e;
-        if (T.pf.q >= 0) {
+        if (c->rng_mode == 1) {
+            const MtStream M{c->d_mt_raw, c->mt_len, c->d_mt_pos, c->d_mt_dry};
+            e = launch_mcmc_mt(T, c->C, A, M, st);
+        }
+        else if (T.pf.q >= 0) {
             // BCP_PF_KERNEL=generic forces the general warp-per-chain kernel (tests run both)
             const char* pk = getenv("BCP_PF_KERNEL");
             e = (pk && !strcmp(pk, "generic")) ? cudaErrorNotSupported : launch_mcmc_pf2(T, c->C, A, st);
@@ -816,6 +835,38 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     c->last_stream = st;
     c->last_launches = launches;
     c->sampled = true;
+    return BCP_OK;
+}
+
+extern "C" int bcp_chains_set_mt_stream(bcp_chains* c, const uint32_t* raw, int64_t n_raw) {
+    BCP_REQUIRE(c && raw && n_raw > 0, "bcp_chains_set_mt_stream: NULL argument or empty stream");
+    if (c->rng_mode != 1) { set_error("bcp_chains_set_mt_stream: the chain block was not created with rng_mode = 1"); return BCP_ERR_STATE; }
+    DeviceGuard guard(c->h->device);
+    if (c->sampled) BCP_CUDA(cudaStreamSynchronize(c->last_stream));
+    if (n_raw > c->mt_len || !c->d_mt_raw) {
+        pool_free(c->d_mt_raw); c->d_mt_raw = nullptr;
+        BCP_CUDA(pool_alloc(&c->d_mt_raw, (size_t)n_raw));
+    }
+    if (!c->d_mt_pos) BCP_CUDA(pool_alloc(&c->d_mt_pos, 1));
+    if (!c->d_mt_dry) BCP_CUDA(pool_alloc(&c->d_mt_dry, 1));
+    c->mt_len = n_raw;
+    BCP_CUDA(cudaMemcpy(c->d_mt_raw, raw, (size_t)n_raw * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    BCP_CUDA(cudaMemset(c->d_mt_pos, 0, sizeof(long long)));
+    BCP_CUDA(cudaMemset(c->d_mt_dry, 0, sizeof(int)));
+    return BCP_OK;
+}
+
+extern "C" int bcp_chains_mt_consumed(bcp_chains* c, int64_t* n_consumed) {
+    BCP_REQUIRE(c && n_consumed, "bcp_chains_mt_consumed: NULL argument");
+    if (c->rng_mode != 1 || !c->d_mt_pos) { set_error("bcp_chains_mt_consumed: no MT19937 stream set"); return BCP_ERR_STATE; }
+    DeviceGuard guard(c->h->device);
+    if (c->sampled) BCP_CUDA(cudaStreamSynchronize(c->last_stream));
+    long long pos = 0;
+    int dry = 0;
+    BCP_CUDA(cudaMemcpy(&pos, c->d_mt_pos, sizeof(pos), cudaMemcpyDeviceToHost));
+    BCP_CUDA(cudaMemcpy(&dry, c->d_mt_dry, sizeof(dry), cudaMemcpyDeviceToHost));
+    *n_consumed = pos;
+    if (dry) { set_error("the MT19937 stream ran out after %lld outputs: hand over a longer one", pos); return BCP_ERR_STATE; }
     return BCP_OK;
 }
 

@@ -77,6 +77,16 @@ __device__ __forceinline__ void stage_sigma_table(double* s_sig, const double* g
 }
 
 
+// reference-stream mode (sampler_mt.cu): raw MT19937 outputs consumed by the single chain of the block
+struct MtStream {
+    const uint32_t* raw;    // [len] device
+    long long len;
+    long long* pos;         // device: outputs consumed so far (persists over launches)
+    int* dry;               // device: set if the stream ran out
+};
+cudaError_t launch_mcmc_mt(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, const MtStream& M,
+                           cudaStream_t st);
+
 // launches the specialised kernel (sampler_fast.cu); returns cudaErrorNotSupported if the table
 // layout is not the canonical one (at most one gamma restraint, and it is the last)
 cudaError_t launch_mcmc_fast(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, int grid, int block,

@@ -1,0 +1,184 @@
+// K5, reference-stream mode: ONE chain driven by numpy's legacy MT19937 stream, draw for draw like the
+// reference's own sampler, so that np.random.seed(s) gives the reference's trajectory bit for bit on the GPU.
+//
+// The reference consumes a data-dependent number of variates per step from numpy's global generator
+// (/root/reference/biceps/PosteriorSampler.py:298-307, 322-326):
+//     dice = random()                                    move type: nuisance iff dice < 1 - 1/(R+1)
+//     nuisance move: randint(R), then randint(3) - 1 for every parameter of that restraint
+//     state move   : randint(low=0, high=S, size=1)
+//     accept       : E_new < E, else random() < exp(E - E_new)   (the second uniform only then)
+// The host hands over the raw 32-bit outputs of MT19937 (RandomState._bit_generator.random_raw) and this
+// kernel replays numpy's legacy algorithms on them:
+//     random()    = ((a >> 5) * 2^26 + (b >> 6)) / 2^53 from two outputs                 (mt19937_next_double)
+//     randint(n)  = masked rejection: draw & mask until <= n - 1; n == 1 draws nothing  (buffered_bounded_masked_uint32)
+// and reports how many outputs it consumed so that the caller can advance the global generator by the same
+// amount.  Single thread, any restraint layout without a PF grid; this is a compatibility / validation path
+// (tests/test_mt_stream_gpu.py replays the reference's stored trajectories), not a performance path.
+#include "common.cuh"
+#include "sampler_common.cuh"
+
+#include <math.h>
+
+namespace bcp {
+
+struct MtCursor {
+    const uint32_t* raw;
+    long long len, pos;
+    bool dry;
+    __device__ uint32_t next() {
+        if (pos >= len) { dry = true; return 0u; }
+        return raw[pos++];
+    }
+    __device__ double uniform() {
+        const uint32_t a = next() >> 5, b = next() >> 6;
+        return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    }
+    __device__ int randint(int n) {
+        const uint32_t rng = (uint32_t)(n - 1);
+        if (rng == 0u) return 0;
+        uint32_t mask = rng;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        uint32_t v;
+        do { v = next() & mask; } while (v > rng && !dry);
+        return (int)v;
+    }
+};
+
+__device__ __forceinline__ double mt_term(const SamplerTables& T, const double* s_sig, int q, int state, int sg, int gm) {
+    const RestraintDev& rd = T.r[q];
+    const double sse = __ldg(rd.sse + (size_t)state * rd.n_gamma + gm);
+    double t = __dadd_rn(s_sig[rd.sig_off + sg], __ddiv_rn(sse, s_sig[rd.sig_off + rd.n_sigma + sg]));
+    t = __dadd_rn(t, rd.cnorm);
+    if (rd.refsum) t = __dsub_rn(t, __ldg(rd.refsum + state));
+    return t;
+}
+
+__global__ void __launch_bounds__(32)
+mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
+               const __grid_constant__ LaunchArgs A, MtStream M) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_sig = reinterpret_cast<double*>(smem_raw);
+    __shared__ __align__(8) uint64_t mbar;
+    stage_sigma_table(s_sig, T.sig_tab, T.sig_bytes, &mbar);
+    if (threadIdx.x != 0) return;
+
+    const int R = T.R;
+    const long long n = C.n_chains, c = 0;
+    const int lam = C.lam[c];
+    const int grp = C.group[c];
+    const double* energy = T.energy + (size_t)lam * T.S;
+    const double logZ = T.logZ[lam];
+    unsigned long long* g_state_counts = C.state_counts + (size_t)grp * T.S;
+    unsigned long long* g_param_counts = C.param_counts + (size_t)grp * T.HB;
+    MtCursor rng{M.raw, M.len, *M.pos, false};
+    const double p_nuis = 1. - 1. / ((double)R + 1.);            // PosteriorSampler.py:300
+
+    int state = C.state[c];
+    double E = C.E[c];
+    int isg[MAXR], igm[MAXR];
+    double t[MAXR];
+    unsigned int acc_r[MAXR];
+    unsigned int acc_state = 0, acc_total = 0;
+    for (int q = 0; q < R; ++q) {
+        isg[q] = C.isg[(size_t)q * n + c];
+        igm[q] = C.igm[(size_t)q * n + c];
+        t[q] = mt_term(T, s_sig, q, state, isg[q], igm[q]);
+        acc_r[q] = 0;
+    }
+    double Cst = __dadd_rn(__ldg(energy + state), logZ);
+    long long next_snap = -1, snap_idx = 0;
+    if (A.traj_every > 0) {
+        const long long m = A.s_begin <= A.burn ? 0 : (A.s_begin - A.burn + A.traj_every - 1) / A.traj_every;
+        snap_idx = m;
+        next_snap = A.burn + m * A.traj_every;
+    }
+
+    for (long long s = A.s_begin; s < A.s_end; ++s) {
+        const bool nuis = rng.uniform() < p_nuis;
+        int pick = -1, nstate = state, nsg = 0, ngm = 0;
+        double tn[MAXR];
+        for (int q = 0; q < R; ++q) tn[q] = t[q];
+        if (nuis) {
+            pick = rng.randint(R);
+            const RestraintDev& rd = T.r[pick];
+            int v = isg[pick] + rng.randint(3) - 1;
+            nsg = v < 0 ? v + rd.n_sigma : (v >= rd.n_sigma ? v - rd.n_sigma : v);
+            ngm = igm[pick];
+            if (rd.has_gamma) {
+                v = igm[pick] + rng.randint(3) - 1;
+                ngm = v < 0 ? v + rd.n_gamma : (v >= rd.n_gamma ? v - rd.n_gamma : v);
+            }
+            tn[pick] = mt_term(T, s_sig, pick, state, nsg, ngm);
+        } else {
+            nstate = rng.randint(T.S);
+            for (int q = 0; q < R; ++q) tn[q] = mt_term(T, s_sig, q, nstate, isg[q], igm[q]);
+        }
+        const double Cn = nuis ? Cst : __dadd_rn(__ldg(energy + nstate), logZ);
+        double En = Cn;
+        for (int q = 0; q < R; ++q) En = __dadd_rn(En, tn[q]);
+
+        bool acc = En < E;
+        if (!acc) acc = rng.uniform() < exp(__dsub_rn(E, En));   // PosteriorSampler.py:325
+        if (rng.dry) break;
+
+        if (acc) {
+            E = En;
+            if (!nuis) {
+                state = nstate;
+                Cst = Cn;
+                ++acc_state;
+            } else {
+                ++acc_r[pick];
+                isg[pick] = nsg;
+                igm[pick] = ngm;
+            }
+            for (int q = 0; q < R; ++q) t[q] = tn[q];
+            ++acc_total;
+        }
+        if (s >= A.burn) {
+            // one chain: plain per-step counting, no run-length compression needed
+            atomicAdd(g_state_counts + state, 1ull);
+            for (int q = 0; q < R; ++q) {
+                atomicAdd(g_param_counts + T.r[q].hist_sigma + isg[q], 1ull);
+                if (T.r[q].has_gamma) atomicAdd(g_param_counts + T.r[q].hist_gamma + igm[q], 1ull);
+            }
+            if (A.state_trace) A.state_trace[(size_t)(s - A.burn) * A.trace_n + c] = state;
+            if (s == next_snap) {
+                const size_t o = (size_t)snap_idx * n + c;
+                A.traj_E[o] = E;
+                A.traj_state[o] = state;
+                A.traj_accept[o] = acc ? 1 : 0;
+                int p = 0;
+                for (int q = 0; q < R; ++q) {
+                    A.traj_idx[((size_t)snap_idx * T.P + p++) * n + c] = isg[q];
+                    if (T.r[q].has_gamma) A.traj_idx[((size_t)snap_idx * T.P + p++) * n + c] = igm[q];
+                }
+                ++snap_idx;
+                next_snap += A.traj_every;
+            }
+        }
+    }
+    C.state[c] = state;
+    C.E[c] = E;
+    C.accepted[c] += acc_total;
+    C.sep[(size_t)R * n + c] += acc_state;
+    for (int q = 0; q < R; ++q) {
+        C.isg[(size_t)q * n + c] = isg[q];
+        C.igm[(size_t)q * n + c] = igm[q];
+        C.sep[(size_t)q * n + c] += acc_r[q];
+    }
+    *M.pos = rng.pos;
+    if (rng.dry) *M.dry = 1;
+}
+
+cudaError_t launch_mcmc_mt(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, const MtStream& M,
+                           cudaStream_t st) {
+    if (C.n_chains != 1 || T.pf.q >= 0) return cudaErrorNotSupported;
+    const size_t smem = (size_t)T.sig_bytes + 16;
+    cudaError_t e = cudaFuncSetAttribute(mcmc_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mcmc_mt_kernel<<<1, 32, smem, st>>>(T, C, A, M);
+    return cudaGetLastError();
+}
+
+}  // namespace bcp

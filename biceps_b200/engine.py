@@ -37,12 +37,13 @@ def alloc_outputs(n_chains, n_groups, S, P, HB, n_steps, traj_every, record_stat
     return o, s
 
 
-def chain_cfg(n_chains, seed, chain_id0=0, chain_lambda=None, chain_group=None, n_groups=0, init_state=None):
+def chain_cfg(n_chains, seed, chain_id0=0, chain_lambda=None, chain_group=None, n_groups=0, init_state=None,
+              rng_mode=0):
     keep = [None if a is None else A.i32(a) for a in (chain_lambda, chain_group, init_state)]
     for a in keep:
         if a is not None and a.shape != (n_chains,):
             raise ValueError("per-chain arrays must have shape (n_chains,)")
-    cfg = A.bcp_chain_cfg(int(n_chains), int(seed) & (2 ** 64 - 1), int(chain_id0), int(n_groups), 0,
+    cfg = A.bcp_chain_cfg(int(n_chains), int(seed) & (2 ** 64 - 1), int(chain_id0), int(n_groups), int(rng_mode),
                           A.i32ptr(keep[0]), A.i32ptr(keep[1]), A.i32ptr(keep[2]))
     return cfg, keep
 
@@ -94,12 +95,13 @@ class ChainBlock(object):
     """bcp_chains: n independent chains on one DeviceTables."""
 
     def __init__(self, tables, n_chains, seed, chain_id0=0, chain_lambda=None, chain_group=None,
-                 n_groups=0, init_state=None):
+                 n_groups=0, init_state=None, rng_mode=0):
         self._lib = A.lib()
         self.tables = tables
         self.n_chains = int(n_chains)
         self.n_groups = int(n_groups) if n_groups else tables.n_lambda
-        cfg, keep = chain_cfg(n_chains, seed, chain_id0, chain_lambda, chain_group, n_groups, init_state)
+        cfg, keep = chain_cfg(n_chains, seed, chain_id0, chain_lambda, chain_group, n_groups, init_state, rng_mode)
+        self.rng_mode = int(rng_mode)
         c = C.c_void_p()
         A.check(self._lib.bcp_chains_create(tables._h, C.byref(cfg), C.byref(c)), "bcp_chains_create")
         self._c = c
@@ -154,6 +156,34 @@ class ChainBlock(object):
         d = np.diag(theta)
         return dict(f=f, theta=theta, Delta_f=f[None, :] - f[:, None],
                     dDelta_f=np.sqrt(np.abs(d[:, None] + d[None, :] - 2.0 * theta)), P=P, dP=dP, iters=int(it.value), N_k=N_k)
+
+    def set_mt_stream(self, raw):
+        """Reference-stream mode (rng_mode=1): raw 32-bit MT19937 outputs from the generator's current position."""
+        raw = np.ascontiguousarray(raw, dtype=np.uint32)
+        A.check(self._lib.bcp_chains_set_mt_stream(self._c, raw.ctypes.data_as(C.POINTER(C.c_uint32)), raw.shape[0]),
+                "bcp_chains_set_mt_stream")
+
+    def mt_consumed(self):
+        n = C.c_int64(0)
+        A.check(self._lib.bcp_chains_mt_consumed(self._c, C.byref(n)), "bcp_chains_mt_consumed")
+        return int(n.value)
+
+    def sample_numpy_stream(self, n_steps, burn=0, **kw):
+        """sample() driven by np.random's global MT19937 generator exactly like the reference's sampler: the
+        generator's next outputs are handed to the device and the global state is advanced by what the chain
+        consumed, so any later np.random call continues as it would after the reference's sample()."""
+        st0 = np.random.get_state()
+        rs = np.random.RandomState()
+        rs.set_state(st0)
+        raw = rs._bit_generator.random_raw(12 * (int(n_steps) + int(burn)) + 4096).astype(np.uint32)
+        self.set_mt_stream(raw)
+        o = self.sample(n_steps, burn=burn, **kw)
+        used = self.mt_consumed()
+        rs.set_state(st0)
+        if used:
+            rs._bit_generator.random_raw(used)
+        np.random.set_state(rs.get_state())
+        return o
 
     def set_state(self, state=None, indices=None, energy=None):
         """Overwrite chain state / indices [n][P] / energy (None = keep): checkpoint restart."""

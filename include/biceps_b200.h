@@ -116,7 +116,10 @@ typedef struct bcp_chain_cfg {
     uint64_t seed;
     uint64_t chain_id0;
     int32_t n_groups;               /* histogram groups; 0 -> n_lambda */
-    int32_t reserved;
+    int32_t rng_mode;               /* 0: Philox (default); 1: numpy's legacy MT19937 stream, ONE chain, draw for draw
+                                       like the reference (PosteriorSampler.py:298-307, 322-326); see
+                                       bcp_chains_set_mt_stream.  init_state should then be the reference's own
+                                       np.random.randint(nstates) draw (PosteriorSampler.py:29) */
     const int32_t* chain_lambda;    /* host [n_chains] or NULL (all 0) */
     const int32_t* chain_group;     /* host [n_chains] or NULL (= chain_lambda) */
     const int32_t* init_state;      /* host [n_chains] or NULL (Philox draw) */
@@ -124,6 +127,13 @@ typedef struct bcp_chain_cfg {
 
 int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_chains** out);
 void bcp_chains_destroy(bcp_chains* c);
+
+/* Reference-stream mode (rng_mode == 1): the raw 32-bit outputs of numpy's MT19937 from the generator's current
+ * position (RandomState._bit_generator.random_raw), at least ~12 per step.  The chain consumes them exactly as the
+ * reference's calls to np.random.random / randint would; bcp_chains_mt_consumed tells how many were used (so that
+ * the caller can advance the global generator by as many) and fails with BCP_ERR_STATE if the stream ran out.  */
+int bcp_chains_set_mt_stream(bcp_chains* c, const uint32_t* raw, int64_t n_raw);
+int bcp_chains_mt_consumed(bcp_chains* c, int64_t* n_consumed);
 
 /* One PosteriorSampler.sample(nsteps, burn) call (PosteriorSampler.py:251-374) for every
  * chain of the block.  May be called repeatedly: state, E, indices, accepted, total and the
