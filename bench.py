@@ -175,7 +175,7 @@ def run_ours(args, rank, world, local_rank):
     # inputs -> tables through the product's own precompute kernels (K1/K2/K4)
     ens = synthetic.make_ensemble("C3", seed=0, n_lambda=N_LAMBDA)
     tabs = precompute.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], device=dev)
-    packed = _cabi.PackedTables(tabs)
+    packed = _cabi.PackedTables(tabs, pinned=True)      # inputs in page-locked host memory
     T = engine.DeviceTables(packed, device=dev)
     n = CHAINS_PER_GPU
     lam = (np.arange(n) // (n // N_LAMBDA)).astype(np.int32)       # 512 consecutive chains per lambda

@@ -104,8 +104,20 @@ class PackedTables(object):
     """Owns contiguous numpy copies of a `tables` dict (see flatten.py) and exposes the
     bcp_tables struct that points into them.  `tables["energy"]` may be [S] or [K][S]."""
 
-    def __init__(self, tables):
+    def __init__(self, tables, pinned=False):
         self._keep = []
+        self._pool = PinnedPool() if pinned else None
+        host_f64 = globals()["f64"]
+
+        def f64(a):
+            """contiguous fp64 copy; with pinned=True the big tables live in page-locked memory, so that
+            bcp_create uploads them at the full PCIe rate"""
+            a = host_f64(a)
+            if self._pool is None or a.nbytes < 65536:
+                return a
+            b = self._pool.zeros(a.shape, np.float64)
+            b[...] = a
+            return b
         energy = np.atleast_2d(f64(tables["energy"]))
         logZ = np.atleast_1d(f64(tables["logZ"]))
         K, S = energy.shape

@@ -385,7 +385,9 @@ static int upload(bcp_handle* h, const T* host, size_t n, const T** dev) {
     if (n == 0) { *dev = nullptr; return BCP_OK; }
     BCP_CUDA(pool_alloc(&d, n));
     h->allocs.push_back(d);
-    BCP_CUDA(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    // asynchronous on the legacy stream: page-locked caller tables (bcp_host_alloc) stream back to back at the
+    // PCIe rate, pageable ones are staged by the driver before the call returns; bcp_create synchronises once
+    BCP_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, (cudaStream_t)0));
     *dev = d;
     return BCP_OK;
 }
@@ -542,6 +544,10 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
     }
     if ((rc = upload(h, t->energy, (size_t)T.K * T.S, &T.energy)) != BCP_OK) return fail(rc);
     if ((rc = upload(h, t->logZ, (size_t)T.K, &T.logZ)) != BCP_OK) return fail(rc);
+    if (cudaStreamSynchronize((cudaStream_t)0) != cudaSuccess) {       // no caller pointer is kept after the return
+        set_error("bcp_create: table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(BCP_ERR_CUDA);
+    }
     *out = h;
     return BCP_OK;
 }
@@ -752,9 +758,11 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     int launches = 0;
     long long chunk = kMaxStepsPerLaunch;
     if (pipe && n_snap >= 8) {
-        // ~4 launches, cut on snapshot boundaries
+        // ~8 launches (4 for short trajectories), cut on snapshot boundaries: only the last launch's snapshots
+        // are copied with nothing to hide behind
         const long long te = cfg->traj_every;
-        long long per = ((total + 3) / 4 + te - 1) / te * te;
+        const long long cuts = n_snap >= 64 ? 8 : 4;
+        long long per = ((total + cuts - 1) / cuts + te - 1) / te * te;
         if (per < chunk) chunk = per;
         if (!c->copy_stream) BCP_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         if (!c->ev_chunk) BCP_CUDA(cudaEventCreateWithFlags(&c->ev_chunk, cudaEventDisableTiming));

@@ -9,7 +9,7 @@ ens = synthetic.make_ensemble("C3", seed=0, n_lambda=8)
 t0 = time.perf_counter()
 tabs = precompute.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], device=0)
 print("precompute.build_tables %.1f ms" % ((time.perf_counter() - t0) * 1e3))
-packed = _cabi.PackedTables(tabs)
+packed = _cabi.PackedTables(tabs, pinned=True)      # inputs in page-locked host memory
 n = 4096
 lam = (np.arange(n) // (n // 8)).astype(np.int32)
 o = None
