@@ -29,6 +29,35 @@ constexpr int MB_TILE = 256;             // samples per tile == threads per CTA
 constexpr int MB_LD = MB_TILE + 1;       // padded leading dimension (bank-conflict-free pair sums)
 constexpr int MB_MAXK = 96;
 
+// exp(x) for the shifted exponents of a log-sum-exp (x <= 0, -inf allowed): argument reduction x = k ln2 + r,
+// degree-13 Taylor polynomial on |r| <= ln2 / 2 (truncation 4e-18), scaling by 2^k through the exponent field.
+// Branch-free (libdevice's exp carries a slow-path branch per call, which splits the unrolled K exponentials of a
+// sample into K basic blocks and keeps them from overlapping) and 22 instead of ~33 instructions; <= 1 ulp away
+// from libdevice's result.  Arguments below -708 (results below 3e-308, against a sum >= 1) are clamped.
+__device__ __forceinline__ double exp_stream(double x) {
+    x = fmax(x, -708.0);
+    const double t = fma(x, 0x1.71547652b82fep+0, 6755399441055744.0);
+    const double k = t - 6755399441055744.0;
+    double r = fma(k, -0x1.62e42fefa39efp-1, x);
+    r = fma(k, -0x1.abc9e3b39803fp-56, r);
+    double p = 0x1.6124613a86d09p-33;
+    p = fma(p, r, 0x1.1eed8eff8d898p-29);
+    p = fma(p, r, 0x1.ae64567f544e4p-26);
+    p = fma(p, r, 0x1.27e4fb7789f5cp-22);
+    p = fma(p, r, 0x1.71de3a556c734p-19);
+    p = fma(p, r, 0x1.a01a01a01a01ap-16);
+    p = fma(p, r, 0x1.a01a01a01a01ap-13);
+    p = fma(p, r, 0x1.6c16c16c16c17p-10);
+    p = fma(p, r, 0x1.1111111111111p-7);
+    p = fma(p, r, 0x1.5555555555555p-5);
+    p = fma(p, r, 0x1.5555555555555p-3);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int ki = __double2loint(t);                      // low word of k + 1.5 * 2^52 == k (two's complement)
+    return p * __hiloint2double((ki + 1023) << 20, 0);
+}
+
 // a[k] = f_k + ln N_k (or -inf if N_k == 0);  rn[k] = 1/N_k
 __device__ __forceinline__ void sample_weights(const double* __restrict__ u, long long N, long long n, int K,
                                                const double* __restrict__ a, double* __restrict__ Ws, int t) {
@@ -41,7 +70,7 @@ __device__ __forceinline__ void sample_weights(const double* __restrict__ u, lon
     }
     double sum = 0.0;
     for (int k = 0; k < K; ++k) {
-        const double e = exp(Ws[k * MB_LD + t] - mx);
+        const double e = exp_stream(Ws[k * MB_LD + t] - mx);
         Ws[k * MB_LD + t] = e;
         sum += e;
     }
@@ -122,9 +151,10 @@ mbar_pass_kernel(const double* __restrict__ u, long long N, int K, const double*
 // u_kn is read exactly once.  The partials are reduced once at the end: xor butterfly inside the warp,
 // fixed-order sum over the warps.  Same arithmetic per sample as sample_weights().
 constexpr int MB_REGK = 12;
-constexpr int MB_STAGES = 3;
 
-template <int K, bool HESS>
+// MB_STAGES tiles in flight per CTA: 3 for the Hessian pass (255 registers: one CTA per SM), 2 for the plain
+// pass (128 registers, 90 KB at K = 11: two CTAs per SM, twice the warps to overlap the exponentials)
+template <int K, bool HESS, int MB_STAGES>
 __global__ void __launch_bounds__(256)
 mbar_pass_reg_kernel(const double* __restrict__ u, long long N, const double* __restrict__ a_in,
                      const double* __restrict__ rn_in, double* __restrict__ partial) {
@@ -148,7 +178,7 @@ mbar_pass_reg_kernel(const double* __restrict__ u, long long N, const double* __
         double sum = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            w[k] = exp(w[k] - mx);
+            w[k] = exp_stream(w[k] - mx);
             sum += w[k];
         }
         const double inv = 1.0 / sum;
@@ -237,17 +267,20 @@ mbar_pass_reg_kernel(const double* __restrict__ u, long long N, const double* __
     }
 }
 
+// returns the number of CTAs launched (= rows of `partial`)
 template <int K>
-static void launch_pass_reg(bool hess, int grid, cudaStream_t st, const double* u, long long N, const double* a, const double* rn,
-                            double* partial) {
-    const int smem = MB_STAGES * K * 256 * 16;
+static int launch_pass_reg(bool hess, int grid, int grid_plain, cudaStream_t st, const double* u, long long N, const double* a, const double* rn,
+                           double* partial) {
     if (hess) {
-        cudaFuncSetAttribute(mbar_pass_reg_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        mbar_pass_reg_kernel<K, true><<<grid, 256, smem, st>>>(u, N, a, rn, partial);
-    } else {
-        cudaFuncSetAttribute(mbar_pass_reg_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        mbar_pass_reg_kernel<K, false><<<grid, 256, smem, st>>>(u, N, a, rn, partial);
+        const int smem = 3 * K * 256 * 16;
+        cudaFuncSetAttribute(mbar_pass_reg_kernel<K, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        mbar_pass_reg_kernel<K, true, 3><<<grid, 256, smem, st>>>(u, N, a, rn, partial);
+        return grid;
     }
+    const int smem = 2 * K * 256 * 16;
+    cudaFuncSetAttribute(mbar_pass_reg_kernel<K, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    mbar_pass_reg_kernel<K, false, 2><<<grid_plain, 256, smem, st>>>(u, N, a, rn, partial);
+    return grid_plain;
 }
 
 // fixed-order reduction of the per-CTA partials: one warp per accumulator (lane-strided partial sums, then
@@ -338,7 +371,7 @@ mbar_pop_reg_kernel(const double* __restrict__ u, long long N, const double* __r
         double sum = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            w[k] = exp(w[k] - mx);
+            w[k] = exp_stream(w[k] - mx);
             sum += w[k];
         }
         const double inv = 1.0 / sum;
@@ -409,7 +442,7 @@ static size_t pass_smem(int K, int n_acc) { return ((size_t)K * MB_LD + 2 * K) *
 struct MbarWork {
     int device = 0, K = 0, sms = 148;
     long long N = 0;
-    int n_acc_h = 0, grid = 0;
+    int n_acc_h = 0, grid = 0, grid_plain = 0;
     double *d_a = nullptr, *d_rn = nullptr, *d_partial = nullptr, *d_out = nullptr;
     std::vector<double> lnN, rn;
     cudaStream_t st = nullptr;      // workspace is stream-ordered (cudaMallocAsync pool)
@@ -422,18 +455,22 @@ static int mbar_work_init(MbarWork& w, int device, int K, long long N, const int
     const long long tiles = (N + MB_TILE - 1) / MB_TILE;
     w.grid = (int)std::min<long long>(tiles, (long long)w.sms * 4);
     if (K <= MB_REGK) {      // persistent CTAs of the staged small-K kernel: as many per SM as their shared memory allows
-        const int smem = MB_STAGES * K * 256 * 16;
+        const int smem = 3 * K * 256 * 16;                  // Hessian pass: 3 stages
         const int per_sm = std::max(1, std::min(4, 220 * 1024 / smem));
         w.grid = (int)std::min<long long>((N + 511) / 512, (long long)w.sms * per_sm);
+        const int smem2 = 2 * K * 256 * 16;                 // plain pass: 2 stages, 128 registers -> 2 CTAs per SM
+        const int per_sm2 = std::max(1, std::min(2, 220 * 1024 / smem2));
+        w.grid_plain = (int)std::min<long long>((N + 511) / 512, (long long)w.sms * per_sm2);
     }
     if (w.grid < 1) w.grid = 1;
+    if (w.grid_plain < 1) w.grid_plain = w.grid;
     w.lnN.resize(K); w.rn.resize(K);
     for (int k = 0; k < K; ++k) {
         w.lnN[k] = N_k[k] > 0 ? log((double)N_k[k]) : -INFINITY;
         w.rn[k] = N_k[k] > 0 ? 1.0 / (double)N_k[k] : 0.0;
     }
     BCP_CUDA(cudaMallocAsync((void**)&w.d_a, K * 8, st)); BCP_CUDA(cudaMallocAsync((void**)&w.d_rn, K * 8, st));
-    BCP_CUDA(cudaMallocAsync((void**)&w.d_partial, (size_t)w.grid * w.n_acc_h * 8, st));
+    BCP_CUDA(cudaMallocAsync((void**)&w.d_partial, std::max((size_t)w.grid * w.n_acc_h, (size_t)w.grid_plain * K) * 8, st));
     BCP_CUDA(cudaMallocAsync((void**)&w.d_out, (size_t)w.n_acc_h * 8, st));
     BCP_CUDA(cudaMemcpyAsync(w.d_rn, w.rn.data(), K * 8, cudaMemcpyHostToDevice, st));
     const size_t sm = pass_smem(K, w.n_acc_h);
@@ -451,9 +488,10 @@ static int mbar_pass(MbarWork& w, const double* d_u, const double* f, bool hess,
     BCP_CUDA(cudaMemcpyAsync(w.d_a, a.data(), K * 8, cudaMemcpyHostToDevice, st));
     const int n_acc = hess ? w.n_acc_h : K;
     const size_t sm = pass_smem(K, n_acc);
+    int n_blocks = w.grid;
     if (K <= MB_REGK) {
         switch (K) {
-#define BCP_PASS(k) case k: launch_pass_reg<k>(hess, w.grid, st, d_u, w.N, w.d_a, w.d_rn, w.d_partial); break;
+#define BCP_PASS(k) case k: n_blocks = launch_pass_reg<k>(hess, w.grid, w.grid_plain, st, d_u, w.N, w.d_a, w.d_rn, w.d_partial); break;
             BCP_PASS(1) BCP_PASS(2) BCP_PASS(3) BCP_PASS(4) BCP_PASS(5) BCP_PASS(6)
             BCP_PASS(7) BCP_PASS(8) BCP_PASS(9) BCP_PASS(10) BCP_PASS(11) BCP_PASS(12)
 #undef BCP_PASS
@@ -461,7 +499,7 @@ static int mbar_pass(MbarWork& w, const double* d_u, const double* f, bool hess,
     }
     else if (hess) mbar_pass_kernel<true><<<w.grid, MB_TILE, sm, st>>>(d_u, w.N, K, w.d_a, w.d_rn, w.d_partial, n_acc);
     else mbar_pass_kernel<false><<<w.grid, MB_TILE, sm, st>>>(d_u, w.N, K, w.d_a, w.d_rn, w.d_partial, n_acc);
-    mbar_finish_kernel<<<(n_acc * 32 + 127) / 128, 128, 0, st>>>(w.d_partial, w.grid, n_acc, w.d_out);
+    mbar_finish_kernel<<<(n_acc * 32 + 127) / 128, 128, 0, st>>>(w.d_partial, n_blocks, n_acc, w.d_out);
     BCP_LAUNCHED(2);
     BCP_CUDA(cudaGetLastError());
     std::vector<double> out(n_acc);
