@@ -53,6 +53,16 @@ namespace bcp {
 #ifndef SPEC_MINBLOCKS
 #define SPEC_MINBLOCKS 1           // __launch_bounds__ second argument (register cap)
 #endif
+#ifndef SPEC_DEPTH
+#define SPEC_DEPTH 2               // batches between the generation (+ prefetch) of a step and its batch; with 3 the
+                                   // cp.async wait moves from the last step of a batch to the batch boundary
+#endif
+#ifndef SPEC_FINISH_BRANCHFREE
+#define SPEC_FINISH_BRANCHFREE 0   // 1: philox_finish without the branch ptxas makes of `nuis ? ... : ...`
+#endif
+#ifndef SPEC_STEP_FENCE
+#define SPEC_STEP_FENCE 0          // 1: compiler-level memory fence between the steps of a batch
+#endif
 #ifndef SPEC_LDS_VOLATILE
 #define SPEC_LDS_VOLATILE 1        // shared-memory loads as volatile asm (pins their order in the PTX)
 #endif
@@ -129,8 +139,8 @@ template <int L>
 struct SpecCfg {
     static constexpr int BL = SPEC_BL(L);        // steps per batch (one basic block, one rollback unit)
     static constexpr int NB = BL / L;            // Philox blocks a lane generates per batch
-    static constexpr int D = 2;                  // batches between the generation of a step and its batch
-    static constexpr int NBATCH = 3;             // batches whose proposal slots are alive (this, next, generated)
+    static constexpr int D = SPEC_DEPTH;         // batches between the generation of a step and its batch
+    static constexpr int NBATCH = D + 1;         // batches whose proposal slots are alive (this ... the generated one)
     static constexpr int NSLOT = NBATCH * BL;    // proposal slots per chain
 };
 
@@ -273,8 +283,14 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         const uint32_t a = (uint32_t)(z1 >> 32);
         const uint32_t b = (HG && hi == (uint32_t)(R - 1)) ? (uint32_t)(z2 >> 32) : 1u;
         SpecGen g;
+#if SPEC_FINISH_BRANCHFREE
+        uint32_t dwn = (0x80000000u | SPEC_DW_IDLE | (0x00100000u << hi)) ^ ((a ^ 1u) << (2 * hi)) ^ ((b ^ 1u) << 16);
+        asm volatile("" : "+r"(dwn));
+        g.dw = nuis ? dwn : SPEC_DW_IDLE;
+#else
         g.dw = nuis ? ((0x80000000u | SPEC_DW_IDLE | (0x00100000u << hi)) ^ ((a ^ 1u) << (2 * hi)) ^ ((b ^ 1u) << 16))
                     : SPEC_DW_IDLE;
+#endif
         g.istate = hi;
         g.u = spec_u2(pc2, pc3);
         // steps past the end of the launch are executed as padding of the last batch: never accepted
@@ -435,7 +451,11 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
 
     for (int s0 = 0; s0 < s_end; s0 += BL) {
         const int sb1 = sb0 + 1 == SpecCfg<L>::NBATCH ? 0 : sb0 + 1;         // slot batch of the next batch
-        const int sb2 = sb1 + 1 == SpecCfg<L>::NBATCH ? 0 : sb1 + 1;         // ... of the batch generated now
+        const int sb2 = sb0 + D >= SpecCfg<L>::NBATCH ? sb0 + D - SpecCfg<L>::NBATCH : sb0 + D;   // ... of the batch generated now
+        if (D >= 3) {            // the next batch's proposals (requested two batches ago) are read by this batch's last step
+            cp_async_wait<1>();
+            __syncwarp();
+        }
         uint32_t ev_bin[BL], ev_cnt[BL];
 #pragma unroll
         for (int j = 0; j < BL; ++j) { ev_bin[j] = 0; ev_cnt[j] = 0; }
@@ -462,7 +482,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                     if (r * L / 10 == j % L) philox_round(r);
                 if (j % L == L - 1) gnew[j / L] = philox_finish(s0 + D * BL + (j / L) * L + q);
                 // the proposals of the next batch (requested one batch ago) are first read by the last step
-                if (j == BL - 1) {
+                if (D < 3 && j == BL - 1) {
                     cp_async_wait<0>();
                     __syncwarp();
                 }
@@ -490,6 +510,9 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 commit(acc, s, En, ev_bin[j], ev_cnt[j]);
                 x_prop = acc ? k.xB : k.xA;
                 dw_s = dw_n; lu_s = lu_n; d0 = k.d1; g0 = k.g1; own_s = k.own;
+#if SPEC_STEP_FENCE
+                asm volatile("" ::: "memory");
+#endif
             }
             if (__any_sync(SPEC_FULL, rare)) {               // roll the batch back
                 E = sv_E; x_prop = sv_x; sg = sv_sg; gm = sv_gm; pg = sv_pg; since_sg = sv_ssg; since_gm = sv_sgm;
@@ -512,7 +535,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
 #pragma unroll 1
             for (int j = 0; j < BL; ++j) {
                 const int s = s0 + j;
-                if (j == BL - 1) {
+                if (D < 3 && j == BL - 1) {
                     cp_async_wait<0>();
                     __syncwarp();
                 }
