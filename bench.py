@@ -346,6 +346,31 @@ def run_ours(args, rank, world, local_rank):
                                       "r01_mcmc_pf2_32k.summary.txt, same launch): 14.5 GB of DRAM reads = 883 B per "
                                       "chain-step, L2 serves the rest (a nuisance move re-reads rows of the chain's state)"}}
 
+    # ---- convergence diagnostics of the sampled traces: K8 autocorrelation against the fp64 pipe ----
+    conv = None
+    if rank == 0:
+        import ctypes as C
+        nser, Tser, mtau = 64, 100000, 10000
+        xs = torch.randn((nser, Tser), dtype=torch.float64, device="cuda").cumsum_(1).mul_(1e-2)
+        cur = torch.empty((nser, mtau + 1), dtype=torch.float64, device="cuda")
+        tau = torch.empty(nser, dtype=torch.float64, device="cuda")
+        ms8 = []
+        for _ in range(4):
+            a8, b8 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a8.record()
+            _cabi.check(lib.bcp_autocorr_dev(C.c_void_p(xs.data_ptr()), nser, Tser, mtau, 1, dev, C.c_void_p(stream),
+                                             C.c_void_p(cur.data_ptr()), C.c_void_p(tau.data_ptr())), "bcp_autocorr_dev")
+            b8.record(); b8.synchronize()
+            ms8.append(a8.elapsed_time(b8))
+        fma = float(nser) * sum(Tser - 1 - t for t in range(mtau + 1))
+        peak_fma = torch.cuda.get_device_properties(dev).multi_processor_count * 64 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6
+        conv = {"workload": "K8 autocorrelation: 64 traces x 1e5 snapshots x 1e4 lags (device-resident)",
+                "ms": min(ms8[1:]), "fp64_fma_per_s": fma / (min(ms8[1:]) * 1e-3),
+                "roofline": {"bound": "fp64 pipe", "achieved": fma / (min(ms8[1:]) * 1e-3) / 1e12, "peak": peak_fma / 1e12,
+                             "unit": "TFMA/s", "frac": fma / (min(ms8[1:]) * 1e-3) / peak_fma,
+                             "note": "peak = SMs x 64 fp64 FMA/clk x max SM clock; ncu: profiles/r01_autocorr.summary.txt"}}
+        del xs, cur, tau
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----
@@ -398,7 +423,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "mcmc_steps_per_chain": N_MCMC_E2E, "traj_every": 100},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "saturated": saturated,
-            "score_pipeline": score, "c2": c2, "pf_c4": pf_c4}
+            "score_pipeline": score, "c2": c2, "pf_c4": pf_c4, "convergence": conv}
     emit(line)
 
 
