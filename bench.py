@@ -55,9 +55,11 @@ def bytes_per_chain_step(tables):
 
 
 def start_clock_sampler(gpu_index):
+    """nvidia-smi sampling every 50 ms with timestamps; started BEFORE the warm-up steps (its start-up takes longer
+    than a short timed region on an 8-GPU box), the samples are later cut to the timed window."""
     f = tempfile.NamedTemporaryFile(prefix="bcp_clocks_", suffix=".csv", delete=False)
     f.close()
-    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
     try:
@@ -68,33 +70,45 @@ def start_clock_sampler(gpu_index):
     return p, f.name
 
 
-def stop_clock_sampler(p, path):
+def stop_clock_sampler(p, path, window=None):
+    """window = (datetime start, datetime end) of the timed region: samples inside it are used; if the region was
+    too short to catch one, the samples of the whole sampled span (warm-up + timed, the same load) are used and
+    the result says so."""
+    import datetime
     if p is not None:
         p.terminate()
         try:
             p.wait(timeout=5)
         except Exception:
             p.kill()
-    sm, mx, reasons = [], [], set()
+    rows = []
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     try:
         for line in open(path):
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 8:
+            if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[0])); mx.append(float(c[1]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(c[1]), float(c[2]), [nm for nm, v in zip(names, c[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, c[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(path)
     except OSError:
         pass
-    if not sm:
+    span = "timed region"
+    use = rows
+    if window is not None:
+        inside = [r for r in rows if window[0] <= r[0] <= window[1]]
+        if inside:
+            use = inside
+        else:
+            span = "same load around the timed region (warm-up / untimed continuation: the timed region was shorter than the sampler's period)"
+    if not use:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+    reasons = sorted({nm for r in use for nm in r[3]})
+    return {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": float(max(r[2] for r in use)),
+            "reasons": reasons, "samples": len(use), "window": span}
 
 
 def measured_peak_hbm():
@@ -196,12 +210,14 @@ def run_ours(args, rank, world, local_rank):
                 dst.copy_(src)
                 dist.all_reduce(dst, op=dist.ReduceOp.SUM)
 
+    import datetime
+    clk_p, clk_f = start_clock_sampler(local_rank)
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clk_p, clk_f = start_clock_sampler(local_rank)
+    t_win0 = datetime.datetime.now()
     launches0 = lib.bcp_kernel_launches()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ms = []
@@ -217,7 +233,19 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     launches = int(lib.bcp_kernel_launches() - launches0)
-    clocks = stop_clock_sampler(clk_p, clk_f)
+    t_win1 = datetime.datetime.now()
+    # nvidia-smi can take longer to start than a short run lasts (8-GPU boxes): keep the same load running, untimed,
+    # until it has delivered samples, so that the clocks are always those of the GPU under this load
+    t_wait = time.perf_counter()
+    while clk_p is not None and time.perf_counter() - t_wait < 5.0:
+        try:
+            if sum(1 for _ in open(clk_f)) >= 2:
+                break
+        except OSError:
+            break
+        one_step()
+        torch.cuda.synchronize()
+    clocks = stop_clock_sampler(clk_p, clk_f, (t_win0, t_win1))
     ms_total = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
