@@ -119,3 +119,27 @@ def test_c5_mbar_properties_at_full_size():
     fk = np.array([-(np.logaddexp.reduce(-u[k] - den)) for k in range(K)])
     assert np.max(np.abs((fk - fk[0]) - r["f"])) < 1e-9
     assert sub.shape[0] == K
+
+
+def test_c4_pf_grid_properties_at_scale():
+    """C4 shape (default 6-D grid 20 x 26 x 50 x 7 x 8 x 1, 107 residues) on 20 000 states (260 MB of counts, far beyond
+    what the dense reference tables could hold: 232 GB): conservation, rescoring idempotence, block-split invariance
+    and an oracle subset."""
+    from biceps_b200 import engine, synthetic
+    from oracle import cbind
+    tabs = synthetic.make_pf_tables(n_states=20000, n_obs=107, seed=1)
+    T = engine.DeviceTables(tabs, device=0)
+    n, steps = 2048, 400
+    o = T.chains(n, 3).sample(steps, burn=50, traj_every=100)
+    assert int(o["state_counts"].sum()) == n * steps
+    off = T.hist_offsets
+    for p in range(T.n_params):
+        assert int(o["param_counts"][0, off[p]:off[p] + T.grid_len[p]].sum()) == n * steps
+    assert np.array_equal(T.neglogp(o["state"], o["indices"]), o["energy"])
+    lo = T.chains(n // 2, 3).sample(steps, burn=50, traj_every=100)
+    hi = T.chains(n // 2, 3, chain_id0=n // 2).sample(steps, burn=50, traj_every=100)
+    assert np.array_equal(np.concatenate([lo["energy"], hi["energy"]]), o["energy"])
+    assert np.array_equal(lo["state_counts"] + hi["state_counts"], o["state_counts"])
+    w = cbind.sample(tabs, 16, 3, steps, burn=50, traj_every=100, n_threads=8)
+    for k in ("state", "indices", "energy", "accepted"):
+        assert np.array_equal(o[k][:16], w[k]), k
