@@ -87,6 +87,7 @@ class PosteriorSampler(object):
         self.total = 0
         self.verbose = verbose
 
+        self._columns = ensemble.columns
         self.tables = build_tables([ensemble], device=self.device)
         self.logZ = float(self.tables["logZ"][0])
         # reference-potential parameters back onto the restraint objects (PosteriorSampler.py:102-104, 147-150)
@@ -120,6 +121,48 @@ class PosteriorSampler(object):
                 self.traj.ref[i].append(rt["ref_sigma"])
         self._calls = 0
 
+    # -- reference potentials of one restraint type, recomputed on the GPU (PosteriorSampler.py:74-150) --------
+    def _build_ref(self, rest_index, ref, use_global_ref_sigma=True):
+        col = None
+        k = 0
+        if getattr(self, "_columns", None) is None:
+            raise RuntimeError("build_*_ref needs the raw observables: not available on an unpickled sampler")
+        for c in self._columns:
+            if k == rest_index:
+                col = c
+            k += 1
+        if col is None or col["kind"] == "pfgrid":
+            raise ValueError("restraint %r has no tabulated reference potential" % (rest_index,))
+        out = precompute.restraint_tables(col["kind"], col["model"], col["exp"], col["weight"], ref=ref,
+                                          gamma=col["gamma"], log_normal=col["log_normal"],
+                                          use_global_ref_sigma=use_global_ref_sigma, device=self.device)
+        rt = self.tables["restraints"][rest_index]
+        rt["ref"], rt["refsum"] = ref, out["refsum"]
+        for key in ("betas", "ref_mean", "ref_sigma"):
+            if key in out:
+                rt[key] = out[key]
+        for i, s_ in enumerate(self.ensemble):
+            R = s_[rest_index]
+            R.ref = ref
+            if ref == "exponential":
+                R.betas, R.sum_neglog_exp_ref = out["betas"], out["refsum"][i]
+            else:
+                R.ref_mean, R.ref_sigma, R.sum_neglog_gaussian_ref = out["ref_mean"], out["ref_sigma"], out["refsum"][i]
+        # the device copy of the tables is stale now
+        if self._chains is not None:
+            self._chains.close()
+        if self._device_tables is not None:
+            self._device_tables.close()
+        self._chains = self._device_tables = None
+
+    def build_exp_ref(self, rest_index, verbose=False):
+        """beta_j = sum_i r_j(X_i) / (S + 1) and the per-state sums of -ln P_ref (PosteriorSampler.py:74-104)."""
+        self._build_ref(rest_index, "exponential")
+
+    def build_gaussian_ref(self, rest_index, use_global_ref_sigma=True, verbose=False):
+        """mean / sigma per observable and the per-state sums of -ln P_ref (PosteriorSampler.py:107-150)."""
+        self._build_ref(rest_index, "gaussian", use_global_ref_sigma)
+
     # -- device objects are rebuilt on demand (a pickled sampler carries only host tables) -----
     def _ensure_chains(self):
         if self._device_tables is None:
@@ -134,6 +177,7 @@ class PosteriorSampler(object):
         d = dict(self.__dict__)
         d["_device_tables"] = None
         d["_chains"] = None
+        d["_columns"] = None          # raw observables stay out of the pickle (build_*_ref needs a live sampler)
         return d
 
     def compute_logZ(self):

@@ -143,6 +143,20 @@ class Restraint(object):
                                           log_normal=getattr(self, "log_normal", False))
         return out["sse"][0]
 
+    def compute_neglogP(self, parameters, parameter_indices, sse):
+        """-ln P of this restraint for one state given its sum of squared errors (Restraint.py:356-383, 457-477,
+        881): the reference's scalar expression (`Ndof`, not `Ndof + 1`, :376).  sse and the reference-potential
+        sums come from the precompute kernels; the sampler evaluates the same expression on the device."""
+        result = 0
+        result += (self.Ndof) * np.log(parameters[0])
+        result += sse / (2.0 * float(parameters[0]) ** 2.0)
+        result += (self.Ndof) / 2.0 * np.log(2.0 * np.pi)
+        if self.ref == "exponential":
+            result -= self.sum_neglog_exp_ref
+        if self.ref == "gaussian":
+            result -= self.sum_neglog_gaussian_ref
+        return result
+
     # label used in rest_type, reproducing the reference's parsing of str(R.__repr__)
     # (PosteriorSampler.py:280, 414): 'sigma_J', 'sigma_noe', 'gamma_noe', and for cs 'sigma_H>>'
     def _label(self):
@@ -218,6 +232,10 @@ class Restraint_noe(_Grouped):
         self.gamma = self.allowed_gamma[self.gamma_index]
         self.log_normal = log_normal
         self._ingest(data, energy, extension, weight, file_fmt)
+
+    def compute_neglogP(self, parameters, parameter_indices, sse):
+        """NOE: sse is the row over the gamma grid, indexed by the gamma index (Restraint.py:572-592)."""
+        return Restraint.compute_neglogP(self, parameters, parameter_indices, sse[int(parameter_indices[1])])
 
     def _param_names(self):
         return ["sigma", "gamma"]

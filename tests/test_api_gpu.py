@@ -272,3 +272,32 @@ def test_preparation_columnar_route_equals_the_file_route(tmp_path):
         assert np.array_equal(a.tables["restraints"][k]["sse"], b.tables["restraints"][k]["sse"])
         assert np.max(np.abs(a.tables["restraints"][k]["sse"] - t1["restraints"][k]["sse"]) / t1["restraints"][k]["sse"]) < 1e-11
     assert a.traj.trajectory == b.traj.trajectory and a.traj.state_trace == b.traj.state_trace
+
+
+def test_restraint_compute_neglogp_and_rebuilt_reference_potentials(dataset):
+    """R.compute_neglogP (Restraint.py:356-383, 572-592) on the kernels' tables adds up to sampler.neglogP, and
+    PosteriorSampler.build_exp_ref / build_gaussian_ref (PosteriorSampler.py:74-150) recompute a reference potential."""
+    import biceps_b200 as biceps
+    from oracle import precompute_oracle as PO
+    d, z, t0, t1 = dataset
+    ens = biceps.Ensemble(1.0, z["raw_energies"])
+    ens.initialize_restraints(biceps.toolbox.sort_data(d), OPTS)
+    s = biceps.PosteriorSampler(ens, seed=1)
+    lst = ens.to_list()
+    i, idx = 17, [[150], [120, 80]]
+    vals = [[lst[i][0].allowed_sigma[150]], [lst[i][1].allowed_sigma[120], lst[i][1].allowed_gamma[80]]]
+    total = lst[i][0].energy + s.logZ
+    for k in range(2):
+        total += lst[i][k].compute_neglogP(vals[k], idx[k], lst[i][k].sse)
+    assert abs(total - s.neglogP([i], vals, idx)) < 1e-9 * abs(total)
+    # switch the J restraint to a gaussian reference potential and the NOE one to exponential again
+    s.build_gaussian_ref(0, use_global_ref_sigma=True)
+    s.build_exp_ref(1)
+    m, e, w = z["obs0_model"], z["obs0_exp"], z["obs0_weight"]
+    mean, sig, ref = PO.gaussian_ref(m, w, use_global_ref_sigma=True)
+    assert lst[3][0].ref == "gaussian" and lst[3][0].ref_sigma is not None and np.isfinite(lst[3][0].sum_neglog_gaussian_ref)
+    assert np.max(np.abs(s.tables["restraints"][1]["refsum"] - t1["restraints"][1]["refsum"])) < 1e-10
+    e_new = s.neglogP([i], vals, idx)
+    assert abs((e_new - total) + lst[i][0].sum_neglog_gaussian_ref) < 1e-9 * abs(total)
+    assert np.allclose(s.tables["restraints"][0]["refsum"], ref, rtol=1e-11)
+    assert np.allclose(lst[0][0].ref_mean, mean, rtol=1e-12) and np.allclose(lst[0][0].ref_sigma, sig, rtol=1e-12)
