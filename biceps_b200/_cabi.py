@@ -213,6 +213,7 @@ _SIGS = {
     "bcp_autocorr": (C.c_int, [c_double_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int, c_double_p, c_double_p]),
     "bcp_autocorr_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    "bcp_chains_autocorr": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_int32, c_double_p, c_double_p]),
     "bcp_jsd": (C.c_int, [c_int32_p, C.c_int64, c_int32_p, C.c_int64, C.POINTER(bcp_jsd_task), C.c_int64, C.c_uint64,
                           C.c_int, c_double_p]),
     "bcp_param_hist": (C.c_int, [c_int32_p, C.c_int64, C.POINTER(bcp_jsd_task), C.c_int64, C.c_int32, C.c_int,

@@ -67,6 +67,8 @@ def chain_autocorrelation_times(sampler, maxtau=1000, device=0):
     t = sampler.traj
     if t.chains is None:
         raise ValueError("the sampler has not sampled yet")
+    if getattr(sampler, "_chains", None) is not None:           # snapshots still resident in HBM: no host round trip
+        return sampler._chains.autocorrelation(t.allowed_parameters, maxtau, True)
     idx = t.chains["indices"]                                   # [T][P][n_chains]
     T, P, n = idx.shape
     allowed = [np.asarray(a, dtype=np.float64) for a in t.allowed_parameters]

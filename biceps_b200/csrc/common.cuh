@@ -76,6 +76,10 @@ static inline void pool_free(void* p) {
 // gives every block back to the driver at each sync, which makes cudaMallocAsync as slow as cudaMalloc)
 void keep_pool_memory(int device);
 
+// K8 on device-resident series (convergence.cu): curves[n_series][max_tau+1], tau[n_series]
+int autocorr_run(const double* d_series, int32_t n_series, int64_t T, int32_t max_tau, int32_t normalize,
+                 cudaStream_t st, double* d_curves, double* d_tau);
+
 static inline int num_sms(int device) {
     int n = 148;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);

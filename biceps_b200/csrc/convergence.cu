@@ -278,7 +278,7 @@ hist_kernel(const int32_t* __restrict__ idx, const bcp_jsd_task* __restrict__ ta
         out[(size_t)blockIdx.x * max_bins + b] = (b < tk.n_bins) ? h[b] : 0;
 }
 
-static int autocorr_run(const double* d_series, int32_t n_series, int64_t T, int32_t max_tau, int32_t normalize,
+int autocorr_run(const double* d_series, int32_t n_series, int64_t T, int32_t max_tau, int32_t normalize,
                         cudaStream_t st, double* d_curves, double* d_tau) {
     const int n_lags = max_tau + 1;
     // 16 lags per thread once a CTA's 2048-lag tile is mostly used; BCP_AC_LPT overrides (tuning)

@@ -1012,6 +1012,61 @@ extern "C" int bcp_sample(bcp_chains* c, const bcp_sample_cfg* cfg, bcp_sample_o
     return bcp_chains_fetch(c, out);
 }
 
+// series[(chain * P + p)][t] = grid value of parameter p at snapshot t of the chain (traj_idx is [n_snap][P][n])
+__global__ void __launch_bounds__(256)
+gather_traces_kernel(const int* __restrict__ traj_idx, const double* __restrict__ grid, const int* __restrict__ off,
+                     long long n, int P, long long n_snap, double* __restrict__ series) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over [n_snap][P][n], chain fastest
+    if (i >= n_snap * P * n) return;
+    const long long chain = i % n;
+    const int p = (int)((i / n) % P);
+    const long long t = i / (n * P);
+    series[((size_t)chain * P + p) * n_snap + t] = grid[off[p] + traj_idx[i]];
+}
+
+extern "C" int bcp_chains_autocorr(bcp_chains* c, const double* grid_values, int32_t max_tau, int32_t normalize,
+                                   double* curves, double* tau) {
+    BCP_REQUIRE(c && grid_values && curves, "bcp_chains_autocorr: NULL argument");
+    BCP_REQUIRE(c->sampled && c->n_snap >= 2, "bcp_chains_autocorr: needs the snapshots of a sample() call (traj_every > 0)");
+    BCP_REQUIRE(max_tau >= 0, "bcp_chains_autocorr: max_tau must be >= 0");
+    bcp_handle* h = c->h;
+    DeviceGuard guard(h->device);
+    const SamplerTables& T = h->T;
+    const long long n = c->C.n_chains, ns = c->n_snap;
+    const int P = T.P;
+    cudaStream_t st = c->last_stream;
+    std::vector<int> off(P);
+    int acc = 0;
+    for (int p = 0; p < P; ++p) { off[p] = acc; acc += h->grid_len[p]; }
+    double *d_grid = nullptr, *d_series = nullptr, *d_curves = nullptr, *d_tau = nullptr;
+    int* d_off = nullptr;
+    const size_t n_series = (size_t)n * P, n_out = n_series * ((size_t)max_tau + 1);
+    int rc = BCP_OK;
+    do {
+#define STEP(x) if ((x) != cudaSuccess) { set_error("bcp_chains_autocorr: %s: %s", #x, cudaGetErrorString(cudaGetLastError())); rc = BCP_ERR_CUDA; break; }
+        STEP(cudaMallocAsync((void**)&d_grid, sizeof(double) * (size_t)T.HB, st));
+        STEP(cudaMallocAsync((void**)&d_off, sizeof(int) * (size_t)P, st));
+        STEP(cudaMallocAsync((void**)&d_series, sizeof(double) * n_series * (size_t)ns, st));
+        STEP(cudaMallocAsync((void**)&d_curves, sizeof(double) * n_out, st));
+        STEP(cudaMallocAsync((void**)&d_tau, sizeof(double) * n_series, st));
+        STEP(cudaMemcpyAsync(d_grid, grid_values, sizeof(double) * (size_t)T.HB, cudaMemcpyHostToDevice, st));
+        STEP(cudaMemcpyAsync(d_off, off.data(), sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, st));
+        const long long work = ns * P * n;
+        gather_traces_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(c->d_traj_idx, d_grid, d_off, n, P, ns, d_series);
+        BCP_LAUNCHED(1);
+        STEP(cudaGetLastError());
+        rc = autocorr_run(d_series, (int32_t)n_series, ns, max_tau, normalize, st, d_curves, d_tau);
+        if (rc != BCP_OK) break;
+        STEP(cudaMemcpyAsync(curves, d_curves, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+        if (tau) STEP(cudaMemcpyAsync(tau, d_tau, sizeof(double) * n_series, cudaMemcpyDeviceToHost, st));
+        STEP(cudaStreamSynchronize(st));
+#undef STEP
+    } while (0);
+    cudaFreeAsync(d_grid, st); cudaFreeAsync(d_off, st); cudaFreeAsync(d_series, st); cudaFreeAsync(d_curves, st);
+    cudaFreeAsync(d_tau, st);
+    return rc;
+}
+
 extern "C" int bcp_chains_score(bcp_chains* c, int32_t want_pops, double tol, int32_t max_iter, int64_t* N_k_out,
                                 double* f_k, double* theta, double* pops, double* dpops, int32_t* iters) {
     BCP_REQUIRE(c && f_k && theta, "bcp_chains_score: NULL argument");

@@ -157,6 +157,19 @@ class ChainBlock(object):
         return dict(f=f, theta=theta, Delta_f=f[None, :] - f[:, None],
                     dDelta_f=np.sqrt(np.abs(d[:, None] + d[None, :] - 2.0 * theta)), P=P, dP=dP, iters=int(it.value), N_k=N_k)
 
+    def autocorrelation(self, grids, max_tau, normalize=True):
+        """Autocorrelation curves / times of every parameter trace of every chain from the device-resident snapshots
+        of the last sample() call (bcp_chains_autocorr): -> curves[n][P][max_tau+1], tau[n][P]."""
+        T = self.tables
+        g = A.f64(np.concatenate([np.asarray(x, dtype=np.float64) for x in grids]))
+        if g.shape[0] != T.param_bins:
+            raise ValueError("grids must be the %d parameter grids of the ensemble" % T.n_params)
+        curves = np.zeros((self.n_chains, T.n_params, int(max_tau) + 1))
+        tau = np.zeros((self.n_chains, T.n_params))
+        A.check(self._lib.bcp_chains_autocorr(self._c, A.dptr(g), int(max_tau), int(bool(normalize)), A.dptr(curves),
+                                              A.dptr(tau)), "bcp_chains_autocorr")
+        return curves, tau
+
     def set_mt_stream(self, raw):
         """Reference-stream mode (rng_mode=1): raw 32-bit MT19937 outputs from the generator's current position."""
         raw = np.ascontiguousarray(raw, dtype=np.uint32)

@@ -270,6 +270,13 @@ int bcp_autocorr(const double* series, int32_t n_series, int64_t T, int32_t max_
 int bcp_autocorr_dev(const double* d_series, int32_t n_series, int64_t T, int32_t max_tau, int32_t normalize,
                      int device, void* stream, double* d_curves, double* d_tau);
 
+/* The same for every nuisance-parameter trace of every chain of the block, straight from the device-resident
+ * snapshots of the last sample() call (no host round trip): series (chain, p) = grid_values[offset_p + index], with
+ * grid_values the concatenated parameter grids (bcp_param_bins doubles, bcp_param_layout order).
+ * curves [n_chains][P][max_tau+1], tau [n_chains][P] (may be NULL); host pointers.                                 */
+int bcp_chains_autocorr(bcp_chains* c, const double* grid_values, int32_t max_tau, int32_t normalize,
+                        double* curves, double* tau);
+
 /* One Jensen-Shannon divergence (compute_JSD, convergence.py:145-186) of a parameter-index series
  * idx[offset .. offset + n_total) split into a first part of n_first samples and the rest:
  *   mode 0  first part = the first n_first samples            (Convergence.process :503-507)

@@ -164,8 +164,12 @@ def test_all_chains_in_one_launch():
     E = biceps.Ensemble.from_arrays(1.0, ens["energies"], rs)
     s = biceps.PosteriorSampler(E, freq_save_traj=10., nchains=64, seed=4)
     s.sample(30000)
-    ac, tau = chain_autocorrelation_times(s, maxtau=150)
+    ac, tau = chain_autocorrelation_times(s, maxtau=150)          # device-resident snapshots (bcp_chains_autocorr)
     assert ac.shape == (64, 3, 151) and tau.shape == (64, 3)
+    blk, s._chains = s._chains, None                               # host route: the fetched snapshot arrays
+    ac_h, tau_h = chain_autocorrelation_times(s, maxtau=150)
+    s._chains = blk
+    assert np.array_equal(ac_h, ac) and np.array_equal(tau_h, tau)
     for c in (0, 17, 63):
         C = Convergence.from_sampler(s, chain=c, outdir=None)
         C.get_autocorrelation_curves(method="auto", maxtau=150)
