@@ -123,6 +123,21 @@ def npz_to_DataFrame(file, out_filename="traj_lambda0.00.pkl", verbose=False):
     return df
 
 
+def convert_pop_to_energy(pop_filename, out_filename=None):
+    """Populations -> reduced energies U = -ln(P / sum P), NaN populations count as 0.001 (toolbox.py:322-348)."""
+    if pop_filename.endswith('txt') or pop_filename.endswith('dat'):
+        pop = np.loadtxt(pop_filename)
+    elif pop_filename.endswith('npy'):
+        pop = np.load(pop_filename)
+    else:
+        raise ValueError('Incompatible file extention. Use:{.txt,.dat,.npy}')
+    pop[np.isnan(pop)] = 0.001
+    total = float(sum(pop))
+    energy = [-np.log((i / total)) for i in pop]
+    np.savetxt('energy.txt' if out_filename is None else out_filename, energy)
+    return energy
+
+
 def save_object(obj, filename):
     with open(filename, "wb") as output:
         pickle.dump(obj, output, pickle.HIGHEST_PROTOCOL)
