@@ -108,3 +108,51 @@ def _single(tabs):
     t["logZ"] = float(np.asarray(tabs["logZ"])[0])
     t["n_states"] = t["energy"].shape[0]
     return t
+
+
+def test_random_ensembles_on_the_mt_stream():
+    """Randomised: 1-6 restraints, with / without a gamma restraint (also non-canonical positions), tiny grids and
+    single-state ensembles (randint(1) draws nothing), flat tables (frequent second uniforms); the CUDA chain on
+    numpy's stream against the Python oracle that calls np.random itself."""
+    from biceps_b200 import engine
+    from oracle import philox as PX, sampler_oracle as O
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        R = int(rng.integers(1, 7))
+        S = int(rng.choice([1, 2, 5, 40]))
+        flat = bool(rng.integers(0, 2))
+        scale = 1e-3 if flat else 1.0
+        rest = []
+        for q in range(R):
+            nsig = int(rng.choice([1, 2, 3, 9, 40]))
+            sig = np.linspace(0.5, 1.5, nsig) if nsig > 1 else np.array([0.9])
+            ndof = float(rng.uniform(1, 6))
+            d = dict(kind="scalar", name="r%d" % q, ref="uniform", ndof=ndof, sigma=sig, nlsig=ndof * np.log(sig),
+                     two_sig2=2.0 * sig ** 2, cnorm=float(rng.uniform(0, 3)), grids=[], refsum=None)
+            if rng.integers(0, 3) == 0:
+                G = int(rng.choice([1, 2, 3, 17]))
+                d.update(kind="gamma", grids=[np.linspace(0.8, 1.2, G)], sse=2.0 + scale * rng.uniform(0, 3, (S, G)))
+            else:
+                d["sse"] = 2.0 + scale * rng.uniform(0, 3, S)
+            if rng.integers(0, 2):
+                d["refsum"] = scale * rng.uniform(0, 1, S)
+                d["ref"] = "exponential"
+            rest.append(d)
+        tabs = dict(n_states=S, energy=scale * rng.uniform(0, 2, S), logZ=float(rng.uniform(0, 1)), restraints=rest)
+        steps, burn, te = int(rng.choice([1, 7, 300])), int(rng.choice([0, 3])), int(rng.choice([1, 4, 50]))
+        seed = 100 + case
+        T = engine.DeviceTables(tabs, device=0)
+        np.random.seed(seed)
+        init = np.random.randint(low=0, high=S, size=1).astype(np.int32)
+        blk = T.chains(1, 0, init_state=init, rng_mode=1)
+        o = blk.sample_numpy_stream(steps, burn=burn, traj_every=te, record_state_trace=True)
+        after = np.random.random()
+        r = O.run_chain(tabs, PX.MTGlobalRNG(seed), steps, burn=burn, traj_every=te, accept_fn=O.accept_np_exp)
+        tag = "case %d R=%d S=%d" % (case, R, S)
+        assert np.array_equal(o["traj_energy"][:, 0], np.array(r.traj_E)), tag
+        assert np.array_equal(o["traj_indices"][:, :, 0], np.array(r.traj_indices).reshape(-1, T.n_params)), tag
+        assert np.array_equal(o["state_trace"][:, 0], np.array(r.state_trace)), tag
+        assert np.array_equal(o["state_counts"][0] + 1, r.state_counts), tag
+        assert np.array_equal(o["param_counts"][0], np.concatenate(r.sampled_parameters)), tag
+        assert int(o["accepted"][0]) == r.accepted and after == np.random.random(), tag
+        blk.close(); T.close()
