@@ -595,8 +595,7 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
                         "bcp_chains_create: init_state[%lld]=%d out of range", i, cfg->init_state[i]);
     }
     BCP_REQUIRE(cfg->rng_mode == 0 || cfg->rng_mode == 1, "bcp_chains_create: rng_mode must be 0 (Philox) or 1 (MT19937 stream)");
-    BCP_REQUIRE(cfg->rng_mode == 0 || (n == 1 && T.pf.q < 0),
-                "bcp_chains_create: the MT19937 stream mode runs one chain and no PF-grid restraint");
+    BCP_REQUIRE(cfg->rng_mode == 0 || n == 1, "bcp_chains_create: the MT19937 stream mode runs one chain");
     bcp_chains* c = new bcp_chains();
     c->h = h;
     c->rng_mode = cfg->rng_mode;

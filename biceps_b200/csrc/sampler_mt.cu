@@ -12,7 +12,8 @@
 //     random()    = ((a >> 5) * 2^26 + (b >> 6)) / 2^53 from two outputs                 (mt19937_next_double)
 //     randint(n)  = masked rejection: draw & mask until <= n - 1; n == 1 draws nothing  (buffered_bounded_masked_uint32)
 // and reports how many outputs it consumed so that the caller can advance the global generator by the same
-// amount.  Single thread, any restraint layout without a PF grid; this is a compatibility / validation path
+// amount.  Single thread, any restraint layout (PF-grid restraints included: their term is summed over the residues in
+// the reference's own order here); this is a compatibility / validation path
 // (tests/test_mt_stream_gpu.py replays the reference's stored trajectories), not a performance path.
 #include "common.cuh"
 #include "sampler_common.cuh"
@@ -44,10 +45,39 @@ struct MtCursor {
     }
 };
 
-__device__ __forceinline__ double mt_term(const SamplerTables& T, const double* s_sig, int q, int state, int sg, int gm) {
+// restraint term in the reference's order: ((nlsig + sse / two_sig2) [+ prior]) + cnorm [- ref].  The PF-grid term is
+// summed over the residues left to right, which is the order in which the reference accumulates its dense 6-D
+// tables (`sse += weight * err**2.0` per residue, Restraint.py:742-749; `sum += weight * max(-model, 0)`, :843-849;
+// model = beta_c * Nc + beta_h * Nh + beta_0 elementwise, :765-801) -- so energies equal the reference's bit for bit.
+__device__ double mt_term(const SamplerTables& T, const double* s_sig, int q, int state, int sg, int gm, const int* ci) {
     const RestraintDev& rd = T.r[q];
+    const double a = s_sig[rd.sig_off + sg], d = s_sig[rd.sig_off + rd.n_sigma + sg];
+    if (q == T.pf.q) {
+        const PfDev& pf = T.pf;
+        const int J = pf.J;
+        const double bc = pf.grid[ci[0]], bh = pf.grid[pf.n[0] + ci[1]], b0 = pf.grid[pf.n[0] + pf.n[1] + ci[2]];
+        const double* Nc = pf.Nc + (((size_t)state * pf.n[3] + ci[3]) * pf.n[5] + ci[5]) * J;
+        const double* Nh = pf.Nh + (((size_t)state * pf.n[4] + ci[4]) * pf.n[5] + ci[5]) * J;
+        double sse = 0.0, ref = 0.0;
+        for (int j = 0; j < J; ++j) {
+            const double model = __dadd_rn(__dadd_rn(__dmul_rn(bc, Nc[j]), __dmul_rn(bh, Nh[j])), b0);
+            const double err = __dsub_rn(model, pf.exp[j]);
+            sse = __dadd_rn(sse, __dmul_rn(pf.weight[j], __dmul_rn(err, err)));
+            const double neg = __dmul_rn(-1.0, model);
+            ref = __dadd_rn(ref, __dmul_rn(pf.weight[j], neg > 0.0 ? neg : 0.0));
+        }
+        double t = __dadd_rn(a, __ddiv_rn(sse, d));
+        if (pf.prior) {
+            size_t cell = 0;
+            for (int k = 0; k < BCP_PF_NGRID; ++k) cell = cell * (size_t)pf.n[k] + (size_t)ci[k];
+            t = __dadd_rn(t, pf.prior[cell]);
+        }
+        t = __dadd_rn(t, rd.cnorm);
+        if (pf.ref_kind == 1) t = __dsub_rn(t, ref);
+        return t;
+    }
     const double sse = __ldg(rd.sse + (size_t)state * rd.n_gamma + gm);
-    double t = __dadd_rn(s_sig[rd.sig_off + sg], __ddiv_rn(sse, s_sig[rd.sig_off + rd.n_sigma + sg]));
+    double t = __dadd_rn(a, __ddiv_rn(sse, d));
     t = __dadd_rn(t, rd.cnorm);
     if (rd.refsum) t = __dsub_rn(t, __ldg(rd.refsum + state));
     return t;
@@ -75,14 +105,16 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
 
     int state = C.state[c];
     double E = C.E[c];
-    int isg[MAXR], igm[MAXR];
+    int isg[MAXR], igm[MAXR], ipf[BCP_PF_NGRID];
     double t[MAXR];
     unsigned int acc_r[MAXR];
     unsigned int acc_state = 0, acc_total = 0;
+    const int QP = T.pf.q;
+    for (int k = 0; k < BCP_PF_NGRID; ++k) ipf[k] = QP >= 0 ? C.ipf[(size_t)k * n + c] : 0;
     for (int q = 0; q < R; ++q) {
         isg[q] = C.isg[(size_t)q * n + c];
         igm[q] = C.igm[(size_t)q * n + c];
-        t[q] = mt_term(T, s_sig, q, state, isg[q], igm[q]);
+        t[q] = mt_term(T, s_sig, q, state, isg[q], igm[q], ipf);
         acc_r[q] = 0;
     }
     double Cst = __dadd_rn(__ldg(energy + state), logZ);
@@ -95,9 +127,10 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
 
     for (long long s = A.s_begin; s < A.s_end; ++s) {
         const bool nuis = rng.uniform() < p_nuis;
-        int pick = -1, nstate = state, nsg = 0, ngm = 0;
+        int pick = -1, nstate = state, nsg = 0, ngm = 0, npf[BCP_PF_NGRID];
         double tn[MAXR];
         for (int q = 0; q < R; ++q) tn[q] = t[q];
+        for (int k = 0; k < BCP_PF_NGRID; ++k) npf[k] = ipf[k];
         if (nuis) {
             pick = rng.randint(R);
             const RestraintDev& rd = T.r[pick];
@@ -108,10 +141,16 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
                 v = igm[pick] + rng.randint(3) - 1;
                 ngm = v < 0 ? v + rd.n_gamma : (v >= rd.n_gamma ? v - rd.n_gamma : v);
             }
-            tn[pick] = mt_term(T, s_sig, pick, state, nsg, ngm);
+            if (pick == QP) {              // the six grid parameters follow sigma, in the reference's parameter order
+                for (int k = 0; k < BCP_PF_NGRID; ++k) {
+                    v = ipf[k] + rng.randint(3) - 1;
+                    npf[k] = v < 0 ? v + T.pf.n[k] : (v >= T.pf.n[k] ? v - T.pf.n[k] : v);
+                }
+            }
+            tn[pick] = mt_term(T, s_sig, pick, state, nsg, ngm, npf);
         } else {
             nstate = rng.randint(T.S);
-            for (int q = 0; q < R; ++q) tn[q] = mt_term(T, s_sig, q, nstate, isg[q], igm[q]);
+            for (int q = 0; q < R; ++q) tn[q] = mt_term(T, s_sig, q, nstate, isg[q], igm[q], ipf);
         }
         const double Cn = nuis ? Cst : __dadd_rn(__ldg(energy + nstate), logZ);
         double En = Cn;
@@ -131,6 +170,7 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
                 ++acc_r[pick];
                 isg[pick] = nsg;
                 igm[pick] = ngm;
+                for (int k = 0; k < BCP_PF_NGRID; ++k) ipf[k] = npf[k];
             }
             for (int q = 0; q < R; ++q) t[q] = tn[q];
             ++acc_total;
@@ -142,6 +182,8 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
                 atomicAdd(g_param_counts + T.r[q].hist_sigma + isg[q], 1ull);
                 if (T.r[q].has_gamma) atomicAdd(g_param_counts + T.r[q].hist_gamma + igm[q], 1ull);
             }
+            if (QP >= 0)
+                for (int k = 0; k < BCP_PF_NGRID; ++k) atomicAdd(g_param_counts + T.pf.hist[k] + ipf[k], 1ull);
             if (A.state_trace) A.state_trace[(size_t)(s - A.burn) * A.trace_n + c] = state;
             if (s == next_snap) {
                 const size_t o = (size_t)snap_idx * n + c;
@@ -152,6 +194,8 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
                 for (int q = 0; q < R; ++q) {
                     A.traj_idx[((size_t)snap_idx * T.P + p++) * n + c] = isg[q];
                     if (T.r[q].has_gamma) A.traj_idx[((size_t)snap_idx * T.P + p++) * n + c] = igm[q];
+                    if (q == QP)
+                        for (int k = 0; k < BCP_PF_NGRID; ++k) A.traj_idx[((size_t)snap_idx * T.P + p++) * n + c] = ipf[k];
                 }
                 ++snap_idx;
                 next_snap += A.traj_every;
@@ -167,13 +211,15 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
         C.igm[(size_t)q * n + c] = igm[q];
         C.sep[(size_t)q * n + c] += acc_r[q];
     }
+    if (QP >= 0)
+        for (int k = 0; k < BCP_PF_NGRID; ++k) C.ipf[(size_t)k * n + c] = ipf[k];
     *M.pos = rng.pos;
     if (rng.dry) *M.dry = 1;
 }
 
 cudaError_t launch_mcmc_mt(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, const MtStream& M,
                            cudaStream_t st) {
-    if (C.n_chains != 1 || T.pf.q >= 0) return cudaErrorNotSupported;
+    if (C.n_chains != 1) return cudaErrorNotSupported;
     const size_t smem = (size_t)T.sig_bytes + 16;
     cudaError_t e = cudaFuncSetAttribute(mcmc_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

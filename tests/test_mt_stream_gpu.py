@@ -156,3 +156,21 @@ def test_random_ensembles_on_the_mt_stream():
         assert np.array_equal(o["param_counts"][0], np.concatenate(r.sampled_parameters)), tag
         assert int(o["accepted"][0]) == r.accepted and after == np.random.random(), tag
         blk.close(); T.close()
+
+
+def test_pf_grid_reference_trajectory_bit_for_bit():
+    """HDX protection factors on the 6-D nuisance grid: in this mode the PF term is summed over the residues in the
+    reference's own order, so even the energies of the reference's MT-seeded run (dense 6-D tables,
+    tests/golden/pf_grid.npz) are reproduced bit for bit from the raw <N_c>/<N_h> counts."""
+    from helpers import pf_raw_tables
+    g = load_npz("pf_grid.npz")
+    raw = pf_raw_tables(g, tables_from_npz(g, "t_"))
+    T, blk, o, _ = _run(raw, int(g["t_seed"]), int(g["t_nsteps"]), 0)
+    assert T.n_params == 7
+    assert np.array_equal(o["traj_energy"][:, 0].view(np.int64), g["t_E"].view(np.int64))
+    assert np.array_equal(o["traj_indices"][:, :, 0], g["t_indices"])
+    assert np.array_equal(o["traj_state"][:, 0], g["t_state"].reshape(-1))
+    assert np.array_equal(o["state_trace"][:, 0], g["t_state_trace"].reshape(-1))
+    assert np.array_equal(o["state_counts"][0] + 1, g["t_state_counts"])
+    assert np.array_equal(o["param_counts"][0], g["t_sampled_parameters"])
+    assert int(o["accepted"][0]) == int(g["t_accepted"]) and o["energy"][0] == g["t_final_E"]
