@@ -12,7 +12,7 @@ Differences a user can see, all deliberate:
     before constructing the sampler still makes a run reproducible;
   * `rng="numpy"` (one chain) instead consumes np.random's global MT19937 stream draw for draw like the
     reference: after np.random.seed(x) the trajectory, traces and histograms are the reference's own, bit for
-    bit (csrc/sampler_mt.cu; a compatibility path, ~1e6 steps/s);
+    bit (csrc/sampler_mt.cu; a compatibility path: 6e5 steps/s, 12x the reference itself);
   * `nchains` (default 1) runs that many independent chains; histograms (state_counts,
     sampled_parameters) are summed over them, the trajectory / traces / state_trace attributes are
     those of chain 0 and `traj.chains` holds every chain's thinned snapshots as arrays.
