@@ -107,19 +107,18 @@ class PackedTables(object):
     def __init__(self, tables, pinned=False):
         self._keep = []
         self._pool = PinnedPool() if pinned else None
-        host_f64 = globals()["f64"]
 
-        def f64(a):
+        def conv(a):
             """contiguous fp64 copy; with pinned=True the big tables live in page-locked memory, so that
             bcp_create uploads them at the full PCIe rate"""
-            a = host_f64(a)
+            a = f64(a)
             if self._pool is None or a.nbytes < 65536:
                 return a
             b = self._pool.zeros(a.shape, np.float64)
             b[...] = a
             return b
-        energy = np.atleast_2d(f64(tables["energy"]))
-        logZ = np.atleast_1d(f64(tables["logZ"]))
+        energy = np.atleast_2d(conv(tables["energy"]))
+        logZ = np.atleast_1d(conv(tables["logZ"]))
         K, S = energy.shape
         if logZ.shape[0] != K:
             raise ValueError("logZ must have one entry per lambda (got %d for %d)" % (logZ.shape[0], K))
@@ -131,14 +130,14 @@ class PackedTables(object):
             r = arr[q]
             kind = {"scalar": BCP_KIND_SCALAR, "gamma": BCP_KIND_GAMMA, "pfgrid": BCP_KIND_PFGRID}[rt["kind"]]
             r.kind = kind
-            nlsig, two = f64(rt["nlsig"]), f64(rt["two_sig2"])
+            nlsig, two = conv(rt["nlsig"]), conv(rt["two_sig2"])
             r.n_sigma = nlsig.shape[0]
             r.cnorm = float(rt["cnorm"])
             r.nlsig, r.two_sig2 = dptr(nlsig), dptr(two)
             self._keep += [nlsig, two]
             r.n_gamma = 1
             if kind != BCP_KIND_PFGRID:
-                sse = f64(rt["sse"])
+                sse = conv(rt["sse"])
                 if kind == BCP_KIND_GAMMA:
                     if sse.ndim != 2 or sse.shape[0] != S:
                         raise ValueError("restraint %d: sse must be [S][G]" % q)
@@ -148,25 +147,25 @@ class PackedTables(object):
                 r.sse = dptr(sse)
                 self._keep.append(sse)
                 if rt.get("refsum") is not None:
-                    ref = f64(rt["refsum"])
+                    ref = conv(rt["refsum"])
                     if ref.shape != (S,):
                         raise ValueError("restraint %d: refsum must be [S]" % q)
                     r.has_ref, r.refsum = 1, dptr(ref)
                     self._keep.append(ref)
             else:
                 pf = rt["pf"]
-                grids = [f64(g) for g in rt["grids"]]
+                grids = [conv(g) for g in rt["grids"]]
                 for k in range(BCP_PF_NGRID):
                     r.pf_n[k] = grids[k].shape[0]
-                gcat = f64(np.concatenate(grids))
-                Nc, Nh = f64(pf["Nc"]), f64(pf["Nh"])
-                ex, w = f64(pf["exp"]), f64(pf["weight"])
+                gcat = conv(np.concatenate(grids))
+                Nc, Nh = conv(pf["Nc"]), conv(pf["Nh"])
+                ex, w = conv(pf["exp"]), conv(pf["weight"])
                 r.pf_n_obs = ex.shape[0]
                 r.pf_ref_kind = 1 if rt.get("ref") == "exponential" else 0
                 r.pf_grid, r.pf_Nc, r.pf_Nh, r.pf_exp, r.pf_weight = dptr(gcat), dptr(Nc), dptr(Nh), dptr(ex), dptr(w)
                 self._keep += [gcat, Nc, Nh, ex, w]
                 if rt.get("prior") is not None:
-                    pr = f64(rt["prior"])
+                    pr = conv(rt["prior"])
                     r.pf_prior = dptr(pr)
                     self._keep.append(pr)
         self._keep += [energy, logZ, arr]
