@@ -71,8 +71,10 @@ def mbar_solve(pass_fn, N_k, tol=1e-12, max_iter=10000, group=None, reduce=True)
             import torch
             import torch.distributed as dist
             t = torch.from_numpy(buf)
+            if dist.get_backend(group) == "nccl":          # NCCL reduces device tensors (K + K^2 doubles over NVLink)
+                t = t.cuda()
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-            buf = t.numpy()
+            buf = t.cpu().numpy()
         return buf[:K].copy(), buf[K:].reshape(K, K).copy()
 
     def gnorm(s):
