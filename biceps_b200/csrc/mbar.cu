@@ -407,8 +407,8 @@ mbar_pop_reg_kernel(const double* __restrict__ u, long long N, const double* __r
 // K6: u[l][n] = ((energy[l][state_n] + logZ[l]) + t_0) + t_1 + ...  (PosteriorSampler.neglogP order);
 // the restraint terms do not depend on lambda and are evaluated once per snapshot.
 __global__ void __launch_bounds__(256)
-ukn_kernel(const SamplerTables T, long long N, const int* __restrict__ state, const int* __restrict__ indices,
-           double* __restrict__ u) {
+ukn_kernel(const SamplerTables T, const double* __restrict__ energy_t, long long N, const int* __restrict__ state,
+           const int* __restrict__ indices, double* __restrict__ u) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const int st = state[n];
@@ -427,8 +427,9 @@ ukn_kernel(const SamplerTables T, long long N, const int* __restrict__ state, co
             t[q] = v;
         }
     }
+    const double* __restrict__ erow = energy_t + (size_t)st * T.K;         // the K energies of the state, contiguous
     for (int l = 0; l < T.K; ++l) {
-        double E = __dadd_rn(T.energy[(size_t)l * T.S + st], T.logZ[l]);
+        double E = __dadd_rn(erow[l], T.logZ[l]);
 #pragma unroll
         for (int q = 0; q < BCP_MAX_RESTRAINTS; ++q)
             if (q < T.R) E = __dadd_rn(E, t[q]);
@@ -643,7 +644,7 @@ extern "C" int bcp_ukn(bcp_handle* h, int64_t n, const int32_t* state, const int
         STEP(dev_alloc(&d_idx, (size_t)n * T.P)); STEP(cudaMemcpy(d_idx, indices, (size_t)n * T.P * 4, cudaMemcpyHostToDevice));
         STEP(dev_alloc(&d_u, (size_t)n * T.K));
         if (T.pf.q >= 0) { STEP(launch_energy_pf(T, n, nullptr, d_state, d_idx, d_u, 1, nullptr)); }
-        else ukn_kernel<<<(unsigned)((n + 255) / 256), 256>>>(T, n, d_state, d_idx, d_u);
+        else ukn_kernel<<<(unsigned)((n + 255) / 256), 256>>>(T, handle_energy_t(h), n, d_state, d_idx, d_u);
         BCP_LAUNCHED(1);
         STEP(cudaGetLastError());
         STEP(cudaMemcpy(u_kn, d_u, (size_t)n * T.K * 8, cudaMemcpyDeviceToHost));
@@ -660,7 +661,7 @@ extern "C" int bcp_ukn_dev(bcp_handle* h, int64_t n, const int32_t* d_state, con
     const SamplerTables& T = handle_tables(h);
     DeviceGuard guard(handle_device(h));
     if (T.pf.q >= 0) BCP_CUDA(launch_energy_pf(T, n, nullptr, d_state, d_indices, d_u_kn, 1, (cudaStream_t)stream));
-    else ukn_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, n, d_state, d_indices, d_u_kn);
+    else ukn_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, handle_energy_t(h), n, d_state, d_indices, d_u_kn);
     BCP_LAUNCHED(1);
     BCP_CUDA(cudaGetLastError());
     return BCP_OK;

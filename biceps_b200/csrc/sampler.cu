@@ -215,6 +215,14 @@ mcmc_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ Cha
     }
 }
 
+// energy[K][S] -> energy_t[S][K]
+__global__ void transpose_energy_kernel(const double* __restrict__ e, int K, int S, double* __restrict__ et) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [S][K]
+    if (i >= (long long)K * S) return;
+    const int st = (int)(i / K), l = (int)(i - (long long)st * K);
+    et[i] = e[(size_t)l * S + st];
+}
+
 // initial state of every chain from the Philox block at step 2^64-1 (oracle/philox.py)
 __global__ void init_chains_kernel(long long n, unsigned long long seed, unsigned long long chain_id0,
                                    int S, int R, const int* init_state, int* state, double* E,
@@ -298,9 +306,9 @@ __global__ void build_layouts_kernel(const SamplerTables T, double* rec, double*
 // restraint terms do not depend on lambda: evaluated once, K energies written in
 // PosteriorSampler.neglogP order.  m is the fastest thread index, so the K * 8-byte writes coalesce.
 __global__ void __launch_bounds__(256)
-ukn_traj_kernel(const SamplerTables T, long long n_chains, long long n_snap, long long N, const long long* __restrict__ pos0,
-                const int* __restrict__ traj_state, const int* __restrict__ traj_idx, double* __restrict__ u,
-                int* __restrict__ state_n) {
+ukn_traj_kernel(const SamplerTables T, const double* __restrict__ energy_t, long long n_chains, long long n_snap, long long N,
+                const long long* __restrict__ pos0, const int* __restrict__ traj_state, const int* __restrict__ traj_idx,
+                double* __restrict__ u, int* __restrict__ state_n) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_chains * n_snap) return;
     const long long c = idx / n_snap, m = idx - c * n_snap;
@@ -321,8 +329,9 @@ ukn_traj_kernel(const SamplerTables T, long long n_chains, long long n_snap, lon
             t[q] = v;
         }
     }
+    const double* __restrict__ erow = energy_t + (size_t)st * T.K;         // the K energies of the state, contiguous
     for (int l = 0; l < T.K; ++l) {
-        double E = __dadd_rn(T.energy[(size_t)l * T.S + st], T.logZ[l]);
+        double E = __dadd_rn(erow[l], T.logZ[l]);
 #pragma unroll
         for (int q = 0; q < BCP_MAX_RESTRAINTS; ++q)
             if (q < T.R) E = __dadd_rn(E, t[q]);
@@ -346,6 +355,7 @@ struct bcp_handle {
     int32_t rest_index[BCP_MAX_PARAMS];
     int32_t grid_len[BCP_MAX_PARAMS];
     int32_t p_slot[BCP_MAX_PARAMS];   // where parameter p lives: 0 sigma, 1 gamma, 2 + k PF grid k
+    double* d_energy_t = nullptr;     // energy[K][S] transposed to [S][K] for the rescoring kernels (K6)
 };
 
 struct bcp_chains {
@@ -544,6 +554,10 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
     }
     if ((rc = upload(h, t->energy, (size_t)T.K * T.S, &T.energy)) != BCP_OK) return fail(rc);
     if ((rc = upload(h, t->logZ, (size_t)T.K, &T.logZ)) != BCP_OK) return fail(rc);
+    if (pool_alloc(&h->d_energy_t, (size_t)T.K * T.S) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
+    h->allocs.push_back(h->d_energy_t);
+    transpose_energy_kernel<<<(unsigned)(((long long)T.K * T.S + 255) / 256), 256>>>(T.energy, T.K, T.S, h->d_energy_t);
+    BCP_LAUNCHED(1);
     if (cudaStreamSynchronize((cudaStream_t)0) != cudaSuccess) {       // no caller pointer is kept after the return
         set_error("bcp_create: table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(BCP_ERR_CUDA);
@@ -562,6 +576,7 @@ extern "C" void bcp_destroy(bcp_handle* h) {
 
 namespace bcp {
 const SamplerTables& handle_tables(const bcp_handle* h) { return h->T; }
+const double* handle_energy_t(const bcp_handle* h) { return h->d_energy_t; }
 int handle_device(const bcp_handle* h) { return h->device; }
 }  // namespace bcp
 
@@ -1093,7 +1108,7 @@ extern "C" int bcp_chains_score(bcp_chains* c, int32_t want_pops, double tol, in
         STEP(pool_alloc(&d_u, (size_t)K * N));
         STEP(pool_alloc(&d_sn, (size_t)N));
         STEP(cudaMemcpyAsync(d_pos, pos0.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        ukn_traj_kernel<<<(unsigned)((n * ns + 255) / 256), 256, 0, st>>>(T, n, ns, N, d_pos, c->d_traj_state, c->d_traj_idx, d_u, d_sn);
+        ukn_traj_kernel<<<(unsigned)((n * ns + 255) / 256), 256, 0, st>>>(T, h->d_energy_t, n, ns, N, d_pos, c->d_traj_state, c->d_traj_idx, d_u, d_sn);
         BCP_LAUNCHED(1);
         STEP(cudaGetLastError());
 #undef STEP

@@ -78,5 +78,7 @@ struct SamplerTables {
 
 const SamplerTables& handle_tables(const bcp_handle* h);
 int handle_device(const bcp_handle* h);
+// energy transposed to [S][K] (built by bcp_create): the K energies of a state are contiguous for the rescoring kernels
+const double* handle_energy_t(const bcp_handle* h);
 
 }  // namespace bcp
