@@ -753,7 +753,10 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     // (scripts/probe_sampler.py, probe_c2.py): C3 (L = 4) 1.5e10 steps/s at 4096 chains, 1.7e10 at 32768 vs
     // fast 4.2e9 / 2.9e10; C2 (L = 8) spec 3.7e9 / 7.3e9 at 1024 / 8192 chains vs fast 1.1e9 / 8.5e9.
     const int lanes = T.R <= 2 ? 2 : (T.R <= 4 ? 4 : 8);
-    int which = !T.canonical ? 0 : (n * lanes <= 2ll * sms * 128 ? 3 : 1);      // 0 generic, 1 fast, 2 coop, 3 spec
+    // 8-lane chains (R >= 5): two waves of 8-warp CTAs still beat the thread-per-chain kernel (C2, 8192 chains:
+    // 1.18e10 against 1.10e10 chain-steps/s)
+    const long long spec_threads = lanes == 8 ? 2ll * sms * 256 : 2ll * sms * 128;
+    int which = !T.canonical ? 0 : (n * lanes <= spec_threads ? 3 : 1);      // 0 generic, 1 fast, 2 coop, 3 spec
     if (kern && T.canonical)
         which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : 2));
     if (force && force[0] == '1') which = 0;

@@ -160,7 +160,7 @@ __host__ __device__ inline SpecLayout spec_layout(int nslot, int R, bool hg, int
 }
 
 template <int L, int R, bool HG, bool TRACE>
-__global__ void __launch_bounds__(128, SPEC_MINBLOCKS)
+__global__ void __launch_bounds__(256, SPEC_MINBLOCKS)
 mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                  const __grid_constant__ LaunchArgs A) {
     constexpr int D = SpecCfg<L>::D;
@@ -690,7 +690,7 @@ static cudaError_t launch_spec_one(const SamplerTables& T, const ChainBuffers& C
     const long long threads = C.n_chains * L;
     const long long n_warps = (threads + 31) / 32;
     int wpb = (int)((n_warps + sms - 1) / sms);
-    wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
+    wpb = wpb < 1 ? 1 : (wpb > 8 ? 8 : wpb);      // up to 8 warps per CTA: two waves of 8-lane chains (C2) stay resident per SM
     int dev = 0, max_optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
