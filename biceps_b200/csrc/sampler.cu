@@ -755,6 +755,8 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     const int lanes = T.R <= 2 ? 2 : (T.R <= 4 ? 4 : 8);
     // 8-lane chains (R >= 5): two waves of 8-warp CTAs still beat the thread-per-chain kernel (C2, 8192 chains:
     // 1.18e10 against 1.10e10 chain-steps/s)
+    // (4-lane chains: a second wave, 9472 .. 16 384 chains, is only 3 % ahead of the thread-per-chain kernel and a
+    // third one far behind -- measured on C3 with scripts/probe_spec_n.py -- so the one-wave threshold stays)
     const long long spec_threads = lanes == 8 ? 2ll * sms * 256 : 2ll * sms * 128;
     int which = !T.canonical ? 0 : (n * lanes <= spec_threads ? 3 : 1);      // 0 generic, 1 fast, 2 coop, 3 spec
     if (kern && T.canonical)
