@@ -174,3 +174,24 @@ def test_all_chains_in_one_launch():
         C = Convergence.from_sampler(s, chain=c, outdir=None)
         C.get_autocorrelation_curves(method="auto", maxtau=150)
         assert np.array_equal(C.autocorr, ac[c]) and np.array_equal(C.tau_c, tau[c])
+
+
+def test_bad_arguments_are_reported():
+    import ctypes as C
+    from biceps_b200 import _cabi as A, convergence as BC
+    lib = A.lib()
+    x = np.zeros((2, 10))
+    out = np.zeros((2, 4))
+    assert lib.bcp_autocorr(None, 2, 10, 3, 1, 0, A.dptr(out), None) == -1            # NULL series
+    assert lib.bcp_autocorr(A.dptr(x), 2, 1, 3, 1, 0, A.dptr(out), None) == -1         # T < 2
+    assert lib.bcp_autocorr(A.dptr(x), 2, 10, -1, 1, 0, A.dptr(out), None) == -1       # negative max_tau
+    assert b"bcp_autocorr" in lib.bcp_last_error()
+    with pytest.raises(RuntimeError):
+        BC.jsd_tasks(np.zeros(10, np.int32), [(0, 10, 5, 0, 0, 5000, 0)])              # more bins than the kernel holds
+    with pytest.raises(RuntimeError):
+        BC.jsd_tasks(np.zeros(10, np.int32), [(0, 10, 11, 0, 0, 4, 0)])                # n_first > n_total
+    with pytest.raises(RuntimeError):
+        BC.jsd_tasks(np.zeros(10, np.int32), [(0, 10, 5, 0, 0, 4, 1)], sel=np.arange(3, dtype=np.int32))   # sel too short
+    # a constant series has zero variance: g(0) = 0 and the normalised curve is 0/0 = nan, like the reference
+    c, t = BC.autocorrelation(np.full((1, 50), 2.5), 5, True)
+    assert np.isnan(c).all()
