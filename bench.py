@@ -345,7 +345,7 @@ def run_ours(args, rank, world, local_rank):
         b2c.close(); T2c.close()
         c2 = {"workload": "C2: 1000 states, R=5 (cs_H, cs_Ca, cs_N, J, NOE), 8 lambdas x 1024 chains, 20000 steps",
               "value": n2 * steps2 / (min(ms2) * 1e-3), "unit": "chain-steps/s",
-              "kernel": "auto-selected (thread-per-chain kernel above one wave of the speculative kernel)"}
+              "kernel": "auto-selected (speculative 8-lane kernel, two waves of 8-warp CTAs)"}
 
     # ---- C4 (BASELINE configs[3]): HDX protection factors on the 6-D grid, 1e5 states (1.3 GB of <N_c>/<N_h>
     #      counts in HBM), warp-per-chain kernel evaluating the term on the fly: the one HBM-bound sampler ----
