@@ -301,3 +301,18 @@ def test_restraint_compute_neglogp_and_rebuilt_reference_potentials(dataset):
     assert abs((e_new - total) + lst[i][0].sum_neglog_gaussian_ref) < 1e-9 * abs(total)
     assert np.allclose(s.tables["restraints"][0]["refsum"], ref, rtol=1e-11)
     assert np.allclose(lst[0][0].ref_mean, mean, rtol=1e-12) and np.allclose(lst[0][0].ref_sigma, sig, rtol=1e-12)
+
+
+def test_quickstart_example_runs(tmp_path):
+    """examples/quickstart.py: Preparation -> Ensemble -> PosteriorSampler -> Analysis -> Convergence, the reference's
+    workflow with only the import line changed; the synthetic experiment must point back at the state it came from."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "quickstart.py"), str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "BICePs score" in r.stdout and "experiment generated from state 78" in r.stdout
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("most populated states")][0]
+    assert line.split("[")[1].split()[0].strip("],") == "78"
+    assert sorted(os.listdir(tmp_path / "results"))[:2] == ["BS.dat", "all_JSD.npy"]
