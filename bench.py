@@ -399,6 +399,34 @@ def run_ours(args, rank, world, local_rank):
                              "note": "peak = SMs x 64 fp64 FMA/clk x max SM clock; ncu: profiles/r01_autocorr.summary.txt"}}
         del xs, cur, tau
 
+    # ---- reference-stream mode: one chain on numpy's MT19937 stream, checked against the reference's own stored
+    #      trajectory (tests/golden/cineromycin_mt_traj.npz, generated from the live reference) ----
+    ref_stream = None
+    if rank == 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from helpers import cineromycin_tables, load_npz
+            z, t0_, t1_ = cineromycin_tables()
+            g = load_npz("cineromycin_mt_traj.npz")
+            Tm = engine.DeviceTables(t1_, device=dev)
+            np.random.seed(int(g["lam1_seed"]))
+            init = np.random.randint(low=0, high=Tm.n_states, size=1).astype(np.int32)
+            bm = Tm.chains(1, 0, init_state=init, rng_mode=1)
+            om = bm.sample_numpy_stream(int(g["lam1_nsteps"]), burn=int(g["lam1_burn"]), traj_every=100)
+            same = bool(np.array_equal(om["traj_energy"][:, 0].view(np.int64), g["lam1_E"].view(np.int64))
+                        and np.array_equal(om["traj_indices"][:, :, 0], g["lam1_indices"])
+                        and np.array_equal(om["traj_state"][:, 0], g["lam1_state"].reshape(-1)))
+            t_ms = time.perf_counter()
+            bm.sample_numpy_stream(200000, traj_every=100)
+            dt_ms = time.perf_counter() - t_ms
+            ref_stream = {"workload": "cineromycin B (100 states, J + NOE), one chain, np.random.seed(%d)" % int(g["lam1_seed"]),
+                          "bit_exact_vs_reference_trajectory": same, "steps_per_s": 200000 / dt_ms,
+                          "note": "csrc/sampler_mt.cu: numpy's MT19937 outputs consumed draw for draw like the reference; "
+                                  "energies, states and sigma/gamma indices of the reference's stored run compared bitwise"}
+            bm.close(); Tm.close()
+        except Exception as e:                       # a side entry must never take the headline down
+            ref_stream = {"error": repr(e)}
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----
@@ -451,7 +479,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "mcmc_steps_per_chain": N_MCMC_E2E, "traj_every": 100},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "saturated": saturated,
-            "score_pipeline": score, "c2": c2, "pf_c4": pf_c4, "convergence": conv}
+            "score_pipeline": score, "c2": c2, "pf_c4": pf_c4, "convergence": conv, "reference_stream": ref_stream}
     emit(line)
 
 
