@@ -10,7 +10,8 @@ Differences a user can see, all deliberate:
   * the RNG is counter-based Philox4x32-10 (oracle/philox.py is its specification), not numpy's
     global MT19937; `seed=None` draws the seed from numpy's global stream, so np.random.seed(x)
     before constructing the sampler still makes a run reproducible;
-  * `rng="numpy"` (one chain) instead consumes np.random's global MT19937 stream draw for draw like the
+  * `rng="numpy"` (one chain; the default when neither `nchains` nor `seed` is given, i.e. for an unchanged
+    reference script) instead consumes np.random's global MT19937 stream draw for draw like the
     reference: after np.random.seed(x) the trajectory, traces and histograms are the reference's own, bit for
     bit (csrc/sampler_mt.cu; a compatibility path: 6e5 steps/s, 12x the reference itself);
   * `nchains` (default 1) runs that many independent chains; histograms (state_counts,
@@ -61,7 +62,7 @@ def build_tables(ensembles, device=0):
 class PosteriorSampler(object):
 
     def __init__(self, ensemble, freq_write_traj=100., freq_save_traj=100., verbose=False, nchains=1, seed=None,
-                 device=0, rng="philox"):
+                 device=0, rng=None):
         self.lam = ensemble.lam
         self.ensemble = ensemble.to_list()
         self.nreplicas = 1
@@ -70,6 +71,10 @@ class PosteriorSampler(object):
         self.nstates = len(self.ensemble)
         self.nchains = int(nchains)
         self.device = int(device)
+        if rng is None:
+            # drop-in default: ONE chain and no explicit seed -> numpy's global MT19937 stream, draw for draw like the
+            # reference (np.random.seed(s) then gives the reference's own trajectory); otherwise Philox
+            rng = "numpy" if (self.nchains == 1 and seed is None) else "philox"
         if rng not in ("philox", "numpy"):
             raise ValueError("rng must be 'philox' or 'numpy'")
         if rng == "numpy" and self.nchains != 1:

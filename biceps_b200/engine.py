@@ -185,6 +185,9 @@ class ChainBlock(object):
         """sample() driven by np.random's global MT19937 generator exactly like the reference's sampler: the
         generator's next outputs are handed to the device and the global state is advanced by what the chain
         consumed, so any later np.random call continues as it would after the reference's sample()."""
+        if int(n_steps) + int(burn) > 50000000:
+            raise ValueError("the numpy-stream mode hands the generator's outputs over in one piece (12 per step): "
+                             "split runs longer than 5e7 steps into several sample() calls or use the Philox mode")
         st0 = np.random.get_state()
         rs = np.random.RandomState()
         rs.set_state(st0)

@@ -90,8 +90,11 @@ def test_posterior_sampler_rng_numpy_equals_oracle_under_the_same_seed(tmp_path)
     ens = biceps.Ensemble.from_arrays(1.0, z["raw_energies"], [
         dict(cls="J", model=z["obs0_model"], exp=z["obs0_exp"], restraint_index=list(z["obs0_restraint_index"]), options=OPTS[0]),
         dict(cls="noe", model=z["obs1_model"], exp=z["obs1_exp"], restraint_index=list(z["obs1_restraint_index"]), options=OPTS[1])])
+    # the drop-in default (one chain, no seed argument) is the reference's stream; a seed or several chains mean Philox
+    assert biceps.PosteriorSampler(ens, seed=1).rng == "philox" and biceps.PosteriorSampler(ens, nchains=4).rng == "philox"
     np.random.seed(3)
-    s = biceps.PosteriorSampler(ens, rng="numpy")
+    s = biceps.PosteriorSampler(ens)
+    assert s.rng == "numpy"
     s.sample(5000, burn=100)
     r = O.run_chain(s.tables_single() if hasattr(s, "tables_single") else _single(s.tables), PX.MTGlobalRNG(3), 5000,
                     burn=100, traj_every=100, accept_fn=O.accept_np_exp)
