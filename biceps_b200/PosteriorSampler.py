@@ -13,7 +13,7 @@ Differences a user can see, all deliberate:
   * `rng="numpy"` (one chain; the default when neither `nchains` nor `seed` is given, i.e. for an unchanged
     reference script) instead consumes np.random's global MT19937 stream draw for draw like the
     reference: after np.random.seed(x) the trajectory, traces and histograms are the reference's own, bit for
-    bit (csrc/sampler_mt.cu; a compatibility path: 6e5 steps/s, 12x the reference itself);
+    bit (csrc/sampler_mt.cu; a compatibility path: 8.5e5 steps/s, 17x the reference itself);
   * `nchains` (default 1) runs that many independent chains; histograms (state_counts,
     sampled_parameters) are summed over them, the trajectory / traces / state_trace attributes are
     those of chain 0 and `traj.chains` holds every chain's thinned snapshots as arrays.

@@ -83,6 +83,9 @@ __device__ double mt_term(const SamplerTables& T, const double* s_sig, int q, in
     return t;
 }
 
+// R is a template parameter so that the per-restraint state (indices, terms, counters) lives in registers: every
+// access below uses a compile-time index (`q == pick` selects instead of `isg[pick]`)
+template <int R>
 __global__ void __launch_bounds__(32)
 mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                const __grid_constant__ LaunchArgs A, MtStream M) {
@@ -92,7 +95,6 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
     stage_sigma_table(s_sig, T.sig_tab, T.sig_bytes, &mbar);
     if (threadIdx.x != 0) return;
 
-    const int R = T.R;
     const long long n = C.n_chains, c = 0;
     const int lam = C.lam[c];
     const int grp = C.group[c];
@@ -105,12 +107,14 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
 
     int state = C.state[c];
     double E = C.E[c];
-    int isg[MAXR], igm[MAXR], ipf[BCP_PF_NGRID];
-    double t[MAXR];
-    unsigned int acc_r[MAXR];
+    int isg[R], igm[R], ipf[BCP_PF_NGRID];
+    double t[R];
+    unsigned int acc_r[R];
     unsigned int acc_state = 0, acc_total = 0;
     const int QP = T.pf.q;
+#pragma unroll
     for (int k = 0; k < BCP_PF_NGRID; ++k) ipf[k] = QP >= 0 ? C.ipf[(size_t)k * n + c] : 0;
+#pragma unroll
     for (int q = 0; q < R; ++q) {
         isg[q] = C.isg[(size_t)q * n + c];
         igm[q] = C.igm[(size_t)q * n + c];
@@ -128,32 +132,44 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
     for (long long s = A.s_begin; s < A.s_end; ++s) {
         const bool nuis = rng.uniform() < p_nuis;
         int pick = -1, nstate = state, nsg = 0, ngm = 0, npf[BCP_PF_NGRID];
-        double tn[MAXR];
+        double tn[R];
+#pragma unroll
         for (int q = 0; q < R; ++q) tn[q] = t[q];
+#pragma unroll
         for (int k = 0; k < BCP_PF_NGRID; ++k) npf[k] = ipf[k];
         if (nuis) {
             pick = rng.randint(R);
+            int cur_sg = 0, cur_gm = 0;
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                if (q == pick) { cur_sg = isg[q]; cur_gm = igm[q]; }
             const RestraintDev& rd = T.r[pick];
-            int v = isg[pick] + rng.randint(3) - 1;
+            int v = cur_sg + rng.randint(3) - 1;
             nsg = v < 0 ? v + rd.n_sigma : (v >= rd.n_sigma ? v - rd.n_sigma : v);
-            ngm = igm[pick];
+            ngm = cur_gm;
             if (rd.has_gamma) {
-                v = igm[pick] + rng.randint(3) - 1;
+                v = cur_gm + rng.randint(3) - 1;
                 ngm = v < 0 ? v + rd.n_gamma : (v >= rd.n_gamma ? v - rd.n_gamma : v);
             }
             if (pick == QP) {              // the six grid parameters follow sigma, in the reference's parameter order
+#pragma unroll
                 for (int k = 0; k < BCP_PF_NGRID; ++k) {
                     v = ipf[k] + rng.randint(3) - 1;
                     npf[k] = v < 0 ? v + T.pf.n[k] : (v >= T.pf.n[k] ? v - T.pf.n[k] : v);
                 }
             }
-            tn[pick] = mt_term(T, s_sig, pick, state, nsg, ngm, npf);
+            const double tp = mt_term(T, s_sig, pick, state, nsg, ngm, npf);
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                if (q == pick) tn[q] = tp;
         } else {
             nstate = rng.randint(T.S);
+#pragma unroll
             for (int q = 0; q < R; ++q) tn[q] = mt_term(T, s_sig, q, nstate, isg[q], igm[q], ipf);
         }
         const double Cn = nuis ? Cst : __dadd_rn(__ldg(energy + nstate), logZ);
         double En = Cn;
+#pragma unroll
         for (int q = 0; q < R; ++q) En = __dadd_rn(En, tn[q]);
 
         bool acc = En < E;
@@ -167,17 +183,20 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
                 Cst = Cn;
                 ++acc_state;
             } else {
-                ++acc_r[pick];
-                isg[pick] = nsg;
-                igm[pick] = ngm;
+#pragma unroll
+                for (int q = 0; q < R; ++q)
+                    if (q == pick) { ++acc_r[q]; isg[q] = nsg; igm[q] = ngm; }
+#pragma unroll
                 for (int k = 0; k < BCP_PF_NGRID; ++k) ipf[k] = npf[k];
             }
+#pragma unroll
             for (int q = 0; q < R; ++q) t[q] = tn[q];
             ++acc_total;
         }
         if (s >= A.burn) {
             // one chain: plain per-step counting, no run-length compression needed
             atomicAdd(g_state_counts + state, 1ull);
+#pragma unroll
             for (int q = 0; q < R; ++q) {
                 atomicAdd(g_param_counts + T.r[q].hist_sigma + isg[q], 1ull);
                 if (T.r[q].has_gamma) atomicAdd(g_param_counts + T.r[q].hist_gamma + igm[q], 1ull);
@@ -191,6 +210,7 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
                 A.traj_state[o] = state;
                 A.traj_accept[o] = acc ? 1 : 0;
                 int p = 0;
+#pragma unroll
                 for (int q = 0; q < R; ++q) {
                     A.traj_idx[((size_t)snap_idx * T.P + p++) * n + c] = isg[q];
                     if (T.r[q].has_gamma) A.traj_idx[((size_t)snap_idx * T.P + p++) * n + c] = igm[q];
@@ -206,6 +226,7 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
     C.E[c] = E;
     C.accepted[c] += acc_total;
     C.sep[(size_t)R * n + c] += acc_state;
+#pragma unroll
     for (int q = 0; q < R; ++q) {
         C.isg[(size_t)q * n + c] = isg[q];
         C.igm[(size_t)q * n + c] = igm[q];
@@ -217,14 +238,30 @@ mcmc_mt_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
     if (rng.dry) *M.dry = 1;
 }
 
+template <int R>
+static cudaError_t launch_mt_one(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, const MtStream& M,
+                                 cudaStream_t st) {
+    const size_t smem = (size_t)T.sig_bytes + 16;
+    cudaError_t e = cudaFuncSetAttribute(mcmc_mt_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mcmc_mt_kernel<R><<<1, 32, smem, st>>>(T, C, A, M);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mcmc_mt(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, const MtStream& M,
                            cudaStream_t st) {
     if (C.n_chains != 1) return cudaErrorNotSupported;
-    const size_t smem = (size_t)T.sig_bytes + 16;
-    cudaError_t e = cudaFuncSetAttribute(mcmc_mt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    mcmc_mt_kernel<<<1, 32, smem, st>>>(T, C, A, M);
-    return cudaGetLastError();
+    switch (T.R) {
+        case 1: return launch_mt_one<1>(T, C, A, M, st);
+        case 2: return launch_mt_one<2>(T, C, A, M, st);
+        case 3: return launch_mt_one<3>(T, C, A, M, st);
+        case 4: return launch_mt_one<4>(T, C, A, M, st);
+        case 5: return launch_mt_one<5>(T, C, A, M, st);
+        case 6: return launch_mt_one<6>(T, C, A, M, st);
+        case 7: return launch_mt_one<7>(T, C, A, M, st);
+        case 8: return launch_mt_one<8>(T, C, A, M, st);
+        default: return cudaErrorNotSupported;
+    }
 }
 
 }  // namespace bcp
