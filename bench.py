@@ -36,13 +36,11 @@ N_MCMC_E2E = 100000
 SEED = 20251019
 
 
-def workload_dict(n_gpus, n_mcmc):
+def workload_dict(n_gpus):
     return {"workload": "C3 synthetic: 10000 states x 1000 observables (cs_H 200, cs_Ca 100, J 300, NOE 400), "
                         "R=4 restraints, P=5 nuisance parameters, 8 lambdas",
             "n_states": 10000, "n_observables": 1000, "n_lambda": N_LAMBDA,
             "chains_per_gpu": CHAINS_PER_GPU, "chains_total": CHAINS_PER_GPU * n_gpus,
-            "mcmc_steps_per_chain_per_bench_step": n_mcmc,
-            "chain_steps_per_bench_step": CHAINS_PER_GPU * n_gpus * n_mcmc,
             "parallelism": "chains sharded over %d GPU(s), tables replicated" % n_gpus,
             "l2": "tables (14 MB) are L2-resident by construction; a 256 MiB memset flushes L2 between timed steps"}
 
@@ -129,46 +127,76 @@ def table_bytes(tables):
 
 
 # ---------------------------------------------------------------------------------------------
-def run_reference(args, rank, world):
-    """The reference's CPU algorithm for the path, timed on the host cores.  The reference is pure
-    Python (no compiled sources to build into oracle/_ref), so this arm runs the plain-C oracle port
-    (oracle/biceps_oracle.c) on all host threads; tables come from the numpy oracle -- none of the
-    product's kernels are on this path."""
-    if rank != 0:
-        return
-    from biceps_b200 import synthetic
-    from oracle import cbind, precompute_oracle as PO, sampler_oracle as O, philox as PX
+def time_c_port(tabs, n_chains, lam, seconds):
+    """The plain-C restatement (oracle/biceps_oracle.c, pthreads) on all host threads, ~`seconds` of work."""
+    from oracle import cbind
     cbind.build()
-    ens = synthetic.make_ensemble("C3", seed=0, n_lambda=N_LAMBDA)
-    tabs = PO.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], exact_pow=False)
     cores = os.cpu_count() or 1
-    n_chains = CHAINS_PER_GPU * args.gpus
-    lam = (np.arange(n_chains) // (CHAINS_PER_GPU // N_LAMBDA) % N_LAMBDA).astype(np.int32)
-    # size a step to ~3 s of CPU work from a short calibration
     t0 = time.perf_counter()
     cbind.sample(tabs, n_chains, SEED, 50, chain_lambda=lam, n_threads=cores)
     rate = n_chains * 50 / (time.perf_counter() - t0)
-    n_mcmc = max(50, int(3.0 * rate / n_chains))
-    for _ in range(args.warmup):
-        cbind.sample(tabs, n_chains, SEED, max(10, n_mcmc // 10), chain_lambda=lam, n_threads=cores)
+    n_mcmc = max(50, int(seconds * rate / n_chains))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cbind.sample(tabs, n_chains, SEED, n_mcmc, chain_lambda=lam, n_threads=cores)
-    dt = time.perf_counter() - t0
-    value = n_chains * n_mcmc * args.steps / dt
-    # the Python restatement (interpreter-bound like the reference itself), one chain, for orientation
-    one = dict(tabs); one["energy"] = tabs["energy"][-1]; one["logZ"] = float(tabs["logZ"][-1])
-    t1 = time.perf_counter()
-    O.run_chain(one, PX.PhiloxStepRNG(SEED, 0), 5000, accept_fn=O.accept_bcp, record_state_trace=False)
-    py_rate = 5000 / (time.perf_counter() - t1)
-    sample = ("C oracle port of PosteriorSampler.sample, %d chains x %d steps per bench step, %d pthreads; "
-              "python restatement (reference-like interpreter loop) %.3g steps/s on 1 core" % (n_chains, n_mcmc, cores, py_rate))
-    cfg = workload_dict(args.gpus, n_mcmc)
+    cbind.sample(tabs, n_chains, SEED, n_mcmc, chain_lambda=lam, n_threads=cores)
+    return n_chains * n_mcmc / (time.perf_counter() - t0), n_mcmc, cores
+
+
+REF_STATES = int(os.environ.get("BCP_REF_STATES", "1000"))
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path, timed on the host cores: the UNMODIFIED reference package
+    (baseline/_ref, installed from /root/reference by baseline/install_ref.sh) through its public API --
+    biceps.Ensemble.initialize_restraints + biceps.PosteriorSampler(ensemble).sample(nsteps), PosteriorSampler.py:251-374
+    -- one process per host core like biceps.multiprocess (decorators.py:27-37).  The ensemble has the C3 layout
+    (cs_H 200 + cs_Ca 100 + J 300 + NOE 400 observables per state) with REF_STATES states: the reference builds its
+    tables with Python loops over states x observables x gamma (48 ms per state here -> 8 minutes at 10 000 states),
+    and the cost of one sample() step does not depend on the number of states (one table lookup per restraint).
+    None of this repository's kernels or engine is on this path.  The C port (oracle/biceps_oracle.c) is timed next
+    to it as a second, stated number.  Without baseline/_ref the port alone is reported (kind "port")."""
+    if rank != 0:
+        return
+    from baseline import ref_arm
+    from biceps_b200 import synthetic
+    from oracle import precompute_oracle as PO
+    cores = os.cpu_count() or 1
+    n_chains = CHAINS_PER_GPU * args.gpus
+    lam = (np.arange(n_chains) // (CHAINS_PER_GPU // N_LAMBDA) % N_LAMBDA).astype(np.int32)
+    ens = synthetic.make_ensemble("C3", seed=0, n_lambda=N_LAMBDA)
+    tabs = PO.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], exact_pow=False)
+    port_value, port_mcmc, _ = time_c_port(tabs, n_chains, lam, 3.0)
+    port_note = ("C port oracle/biceps_oracle.c on the same 10000-state tables: %.4g chain-steps/s (%d chains x %d steps, "
+                 "%d pthreads)" % (port_value, n_chains, port_mcmc, cores))
+    if ref_arm.available():
+        ens_ref = synthetic.make_ensemble("C3", seed=0, n_states=REF_STATES)
+        # a bench step = every process runs sample(n_mcmc), n_mcmc sized to ~3 s from a short calibration
+        sampler, t_build = ref_arm.build(ens_ref, 1.0)
+        per = ref_arm.time_sample(sampler, cores, 2000, 1, 1)
+        n_mcmc = max(1000, int(3.0 * 2000 / per[0]))
+        per = ref_arm.time_sample(sampler, cores, n_mcmc, args.steps, max(args.warmup, 1))
+        dt = float(sum(per))
+        value = cores * n_mcmc * args.steps / dt
+        kind = "reference"
+        sample = ("unmodified reference biceps.PosteriorSampler.sample (baseline/_ref), C3 layout with %d states "
+                  "(construction through biceps.Ensemble.initialize_restraints: %.1f s; the per-step cost of sample() "
+                  "does not depend on the number of states), one process per core: %d processes x %d steps per bench "
+                  "step.  %s" % (REF_STATES, t_build, cores, n_mcmc, port_note))
+        extra = {"port_value": port_value, "reference_states": REF_STATES, "reference_construction_s": t_build}
+    else:
+        n_mcmc = port_mcmc
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            v, _, _ = time_c_port(tabs, n_chains, lam, 3.0)
+        dt = time.perf_counter() - t0
+        value = v
+        kind = "port"
+        sample = "baseline/_ref is missing (run baseline/install_ref.sh where /root/reference exists).  " + port_note
+        extra = {"port_value": port_value}
     line = {"impl": "reference", "metric": "MCMC chain-steps/sec", "value": value, "unit": "chain-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": cfg,
-            "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_dict(args.gpus), "mcmc_steps_per_chain_per_bench_step": n_mcmc,
+            "cpu_baseline": dict({"value": value, "unit": "chain-steps/s", "cores": cores, "kind": kind, "sample": sample}, **extra),
             "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -475,7 +503,7 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": "MCMC chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_dict(world, N_MCMC), "clocks": clocks,
+            "config": workload_dict(world), "mcmc_steps_per_chain_per_bench_step": N_MCMC, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "chain-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "mcmc_steps_per_chain": N_MCMC_E2E, "traj_every": 100},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "saturated": saturated,
