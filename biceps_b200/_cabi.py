@@ -219,6 +219,10 @@ _SIGS = {
                                  c_int64_p]),
     "bcp_mbar_pass_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, c_int64_p, c_double_p, C.c_int32, C.c_int,
                                     C.c_void_p, c_double_p, c_double_p]),
+    "bcp_chains_n_samples": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p]),
+    "bcp_chains_ukn_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bcp_mbar_pops_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, c_int64_p, c_double_p, C.c_void_p, C.c_int32,
+                                    C.c_int, C.c_void_p, c_double_p, c_double_p]),
 }
 
 _lib = None

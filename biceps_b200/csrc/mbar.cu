@@ -767,3 +767,31 @@ extern "C" int bcp_mbar_pass_dev(const double* d_u_kn, int64_t n_local, int32_t 
     if (rc != BCP_OK) return rc;
     return mbar_pass(w, d_u_kn, f_k, want_hess != 0, s_out, M_out, (cudaStream_t)stream);
 }
+
+// the weighted state histograms of a LOCAL shard at free energies f: P[K][S] = sum_n W_nl [s_n = i] and
+// Q[K][S] = sum_n W_nl^2 [s_n = i] (host outputs; a multi-GPU caller all-reduces both and finishes with
+// P_i(l) = P, dP_i(l) = |P| sqrt(Q/P^2 + theta_ll - 2 Q/P))
+extern "C" int bcp_mbar_pops_dev(const double* d_u_kn, int64_t n_local, int32_t K, const int64_t* N_k_global,
+                                 const double* f_k, const int32_t* d_state_n, int32_t S, int device, void* stream,
+                                 double* P_out, double* Q_out) {
+    BCP_REQUIRE(d_u_kn && N_k_global && f_k && d_state_n && P_out && Q_out, "bcp_mbar_pops_dev: NULL argument");
+    BCP_REQUIRE(K >= 1 && K <= MB_MAXK && n_local > 0 && S > 0, "bcp_mbar_pops_dev: bad K, n_local or S");
+    DeviceGuard guard(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    MbarWork w;
+    int rc = mbar_work_init(w, device, K, n_local, N_k_global, st);
+    if (rc != BCP_OK) return rc;
+    double *d_P = nullptr, *d_Q = nullptr;
+    BCP_CUDA(cudaMallocAsync((void**)&d_P, (size_t)K * S * 8, st));
+    cudaError_t e = cudaMallocAsync((void**)&d_Q, (size_t)K * S * 8, st);
+    if (e != cudaSuccess) { cudaFreeAsync(d_P, st); set_error("bcp_mbar_pops_dev: cudaMallocAsync: %s", cudaGetErrorString(e)); return BCP_ERR_CUDA; }
+    rc = mbar_populations(w, d_u_kn, f_k, d_state_n, S, d_P, d_Q, st);
+    if (rc == BCP_OK) {
+        e = cudaMemcpyAsync(P_out, d_P, (size_t)K * S * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(Q_out, d_Q, (size_t)K * S * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("bcp_mbar_pops_dev: copy back: %s", cudaGetErrorString(e)); rc = BCP_ERR_CUDA; }
+    }
+    cudaFreeAsync(d_P, st); cudaFreeAsync(d_Q, st);
+    return rc;
+}

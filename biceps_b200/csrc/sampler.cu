@@ -758,9 +758,12 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     // (4-lane chains: a second wave, 9472 .. 16 384 chains, is only 3 % ahead of the thread-per-chain kernel and a
     // third one far behind -- measured on C3 with scripts/probe_spec_n.py -- so the one-wave threshold stays)
     const long long spec_threads = lanes == 8 ? 2ll * sms * 256 : 2ll * sms * 128;
-    int which = !T.canonical ? 0 : (n * lanes <= spec_threads ? 3 : 1);      // 0 generic, 1 fast, 2 coop, 3 spec
+    // 0 generic, 1 fast, 2 coop, 3 spec, 4 ws (the spec kernel's critical path in consumer warps, Philox / prefetch /
+    // bookkeeping in producer warps: sampler_ws.cu; bit-identical, selectable with BCP_KERNEL=ws -- measured on C3 / 4096
+    // chains: 6.9 ms per 20 000 steps against 4.6 ms for spec, DESIGN.md section 4, so spec stays the automatic choice)
+    int which = !T.canonical ? 0 : (n * lanes <= spec_threads ? 3 : 1);
     if (kern && T.canonical)
-        which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : 2));
+        which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : (!strcmp(kern, "ws") ? 4 : 2)));
     if (force && force[0] == '1') which = 0;
     int fgrid = grid, fblock = block;
     {                                                        // launch shape of the thread-per-chain kernel
@@ -820,6 +823,11 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
             const char* pk = getenv("BCP_PF_KERNEL");
             e = (pk && !strcmp(pk, "generic")) ? cudaErrorNotSupported : launch_mcmc_pf2(T, c->C, A, st);
             if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_pf(T, c->C, A, st); }
+        }
+        else if (which == 4) {
+            e = launch_mcmc_ws(T, c->C, A, st, sms);
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_spec(T, c->C, A, st, sms); }
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); }
         }
         else if (which == 3) {
             e = launch_mcmc_spec(T, c->C, A, st, sms);
@@ -1086,6 +1094,67 @@ extern "C" int bcp_chains_autocorr(bcp_chains* c, const double* grid_values, int
     return rc;
 }
 
+// sample order of a chain block's snapshots: runs (lambda) in order, the chains of a run in chain order, a chain's
+// snapshots in time order (== Analysis.py:214 kln_to_kn order); pos0[i] = first column of chain i
+static long long snapshot_layout(const bcp_chains* c, std::vector<long long>& pos0, std::vector<int64_t>& N_k) {
+    const long long n = c->C.n_chains, ns = c->n_snap;
+    const int K = c->h->T.K;
+    std::vector<long long> cnt(K, 0), off(K + 1, 0), seen(K, 0);
+    pos0.assign(n, 0);
+    for (long long i = 0; i < n; ++i) ++cnt[c->h_lam[i]];
+    for (int k = 0; k < K; ++k) off[k + 1] = off[k] + cnt[k] * ns;
+    for (long long i = 0; i < n; ++i) { const int k = c->h_lam[i]; pos0[i] = off[k] + seen[k] * ns; ++seen[k]; }
+    N_k.assign(K, 0);
+    for (int k = 0; k < K; ++k) N_k[k] = cnt[k] * ns;
+    return off[K];
+}
+
+static int chains_ukn_launch(bcp_chains* c, const std::vector<long long>& pos0, long long N, double* d_u, int* d_sn,
+                             cudaStream_t st) {
+    bcp_handle* h = c->h;
+    const long long n = c->C.n_chains, ns = c->n_snap;
+    long long* d_pos = nullptr;
+    BCP_CUDA(pool_alloc(&d_pos, (size_t)n));
+    cudaError_t e = cudaMemcpyAsync(d_pos, pos0.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        ukn_traj_kernel<<<(unsigned)((n * ns + 255) / 256), 256, 0, st>>>(h->T, h->d_energy_t, n, ns, N, d_pos, c->d_traj_state,
+                                                                        c->d_traj_idx, d_u, d_sn);
+        BCP_LAUNCHED(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // pos0 is the caller's; d_pos is freed on the default stream
+    pool_free(d_pos);
+    if (e != cudaSuccess) { set_error("bcp_chains_ukn: %s", cudaGetErrorString(e)); return BCP_ERR_CUDA; }
+    return BCP_OK;
+}
+
+extern "C" int bcp_chains_n_samples(bcp_chains* c, int64_t* n_samples, int64_t* N_k_out) {
+    BCP_REQUIRE(c && n_samples, "bcp_chains_n_samples: NULL argument");
+    BCP_REQUIRE(c->sampled && c->n_snap > 0, "bcp_chains_n_samples: no snapshots (sample with traj_every > 0 first)");
+    std::vector<long long> pos0;
+    std::vector<int64_t> N_k;
+    *n_samples = snapshot_layout(c, pos0, N_k);
+    if (N_k_out) for (int k = 0; k < c->h->T.K; ++k) N_k_out[k] = N_k[k];
+    return BCP_OK;
+}
+
+extern "C" int bcp_chains_ukn_dev(bcp_chains* c, double* d_u_kn, int32_t* d_state_n, void* stream) {
+    BCP_REQUIRE(c && d_u_kn, "bcp_chains_ukn_dev: NULL argument");
+    BCP_REQUIRE(c->sampled && c->n_snap > 0, "bcp_chains_ukn_dev: no snapshots (sample with traj_every > 0 first)");
+    BCP_REQUIRE(c->h->T.pf.q < 0, "bcp_chains_ukn_dev: ensembles with a PFGRID restraint go through bcp_ukn");
+    DeviceGuard guard(c->h->device);
+    std::vector<long long> pos0;
+    std::vector<int64_t> N_k;
+    const long long N = snapshot_layout(c, pos0, N_k);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (st != c->last_stream) BCP_CUDA(cudaStreamSynchronize(c->last_stream));     // the snapshots must be complete
+    int* d_sn = d_state_n;
+    if (!d_sn) BCP_CUDA(pool_alloc(&d_sn, (size_t)N));
+    const int rc = chains_ukn_launch(c, pos0, N, d_u_kn, d_sn, st);
+    if (!d_state_n) pool_free(d_sn);
+    return rc;
+}
+
 extern "C" int bcp_chains_score(bcp_chains* c, int32_t want_pops, double tol, int32_t max_iter, int64_t* N_k_out,
                                 double* f_k, double* theta, double* pops, double* dpops, int32_t* iters) {
     BCP_REQUIRE(c && f_k && theta, "bcp_chains_score: NULL argument");
@@ -1094,34 +1163,26 @@ extern "C" int bcp_chains_score(bcp_chains* c, int32_t want_pops, double tol, in
     const SamplerTables& T = h->T;
     BCP_REQUIRE(T.pf.q < 0, "bcp_chains_score: ensembles with a PFGRID restraint go through bcp_ukn + bcp_mbar");
     DeviceGuard guard(h->device);
-    const long long n = c->C.n_chains, ns = c->n_snap;
     const int K = T.K;
-    std::vector<long long> cnt(K, 0), off(K + 1, 0), pos0(n);
-    for (long long i = 0; i < n; ++i) ++cnt[c->h_lam[i]];
-    for (int k = 0; k < K; ++k) off[k + 1] = off[k] + cnt[k] * ns;
-    std::vector<long long> seen(K, 0);
-    for (long long i = 0; i < n; ++i) { const int k = c->h_lam[i]; pos0[i] = off[k] + seen[k] * ns; ++seen[k]; }
-    std::vector<int64_t> N_k(K);
-    for (int k = 0; k < K; ++k) { N_k[k] = cnt[k] * ns; if (N_k_out) N_k_out[k] = N_k[k]; }
-    const long long N = off[K];
+    std::vector<long long> pos0;
+    std::vector<int64_t> N_k;
+    const long long N = snapshot_layout(c, pos0, N_k);
+    if (N_k_out) for (int k = 0; k < K; ++k) N_k_out[k] = N_k[k];
     cudaStream_t st = c->last_stream;
-    long long* d_pos = nullptr; double* d_u = nullptr; int* d_sn = nullptr;
+    double* d_u = nullptr; int* d_sn = nullptr;
     int rc = BCP_OK;
     do {
 #define STEP(x) if ((x) != cudaSuccess) { set_error("bcp_chains_score: %s: %s", #x, cudaGetErrorString(cudaGetLastError())); rc = BCP_ERR_CUDA; break; }
-        STEP(pool_alloc(&d_pos, (size_t)n));
         STEP(pool_alloc(&d_u, (size_t)K * N));
         STEP(pool_alloc(&d_sn, (size_t)N));
-        STEP(cudaMemcpyAsync(d_pos, pos0.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        ukn_traj_kernel<<<(unsigned)((n * ns + 255) / 256), 256, 0, st>>>(T, h->d_energy_t, n, ns, N, d_pos, c->d_traj_state, c->d_traj_idx, d_u, d_sn);
-        BCP_LAUNCHED(1);
-        STEP(cudaGetLastError());
 #undef STEP
+        rc = chains_ukn_launch(c, pos0, N, d_u, d_sn, st);
+        if (rc != BCP_OK) break;
         rc = bcp_mbar_dev(d_u, N_k.data(), K, N, want_pops ? d_sn : nullptr, want_pops ? T.S : 0, h->device, st, tol, max_iter,
                           f_k, theta, pops, dpops, iters);
     } while (0);
     cudaStreamSynchronize(st);
-    pool_free(d_pos); pool_free(d_u); pool_free(d_sn);
+    pool_free(d_u); pool_free(d_sn);
     return rc;
 }
 

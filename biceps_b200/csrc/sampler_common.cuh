@@ -98,6 +98,9 @@ cudaError_t launch_mcmc_coop(const SamplerTables& T, const ChainBuffers& C, cons
 // speculative cooperative kernel (sampler_spec.cu): canonical layout, chain blocks in shared memory;
 // cudaErrorNotSupported if the tables do not qualify (layout, shared-memory budget, division range)
 cudaError_t launch_mcmc_spec(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms);
+// warp-specialised speculative kernel (sampler_ws.cu): the spec kernel's critical path in a consumer warp, Philox /
+// prefetch / histogram bookkeeping in a producer warp; same qualification rules as launch_mcmc_spec
+cudaError_t launch_mcmc_ws(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms);
 // warp-per-chain kernel for ensembles with a PFGRID restraint (sampler_pf.cu); any layout
 cudaError_t launch_mcmc_pf(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st);
 // tuned variant for scalar restraints + one PFGRID restraint (sampler_pf2.cu); cudaErrorNotSupported otherwise

@@ -123,3 +123,62 @@ def gpu_pass_fn(d_u_kn_ptr, n_local, K, N_k_global, device=0, stream=None):
                 "bcp_mbar_pass_dev")
         return s, M
     return fn
+
+
+def finish_populations(P, Q, theta):
+    """P_i(l) and its 'approximate' uncertainty from the (all-reduced) weighted histograms P[K][S], Q[K][S]:
+    dP = |P| sqrt(Q / P^2 + theta_ll - 2 Q / P), nan where a state was never sampled (the same
+    arithmetic as csrc/mbar.cu:mbar_finish_outputs).  Returns pops[S][K], dpops[S][K]."""
+    P = np.asarray(P, np.float64); Q = np.asarray(Q, np.float64)
+    th = np.diag(np.asarray(theta, np.float64))[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.abs(P) * np.sqrt(np.abs(Q / (P * P) + th - 2.0 * Q / P))
+    d[P == 0.0] = np.nan
+    return P.T.copy(), d.T.copy()
+
+
+def score_chains(block, populations=True, tol=1e-12, group=None, reduce=True):
+    """BICePs scores from the snapshots of a chain block that holds a SHARD of the chains (every rank calls this
+    with its own block after sampling; reduce=False: one block holds everything).  The local snapshots are rescored
+    under every lambda into a device-resident u_kn shard (bcp_chains_ukn_dev), MBAR runs over the shards with one
+    all-reduce of K + K^2 doubles per pass (mbar_solve + bcp_mbar_pass_dev), the weighted state histograms are
+    all-reduced once (bcp_mbar_pops_dev).  Same dict as ChainBlock.score (f, theta, Delta_f, dDelta_f, P, dP, iters,
+    N_k), identical on every rank."""
+    import torch
+    lib = A.lib()
+    T = block.tables
+    K, S, dev = T.n_lambda, T.n_states, T.device
+    n_loc = C.c_int64(0)
+    N_k = np.zeros(K, np.int64)
+    A.check(lib.bcp_chains_n_samples(block._c, C.byref(n_loc), A.i64ptr(N_k)), "bcp_chains_n_samples")
+    n_loc = int(n_loc.value)
+    d_u = torch.empty((K, n_loc), dtype=torch.float64, device="cuda:%d" % dev)
+    d_s = torch.empty(n_loc, dtype=torch.int32, device="cuda:%d" % dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    A.check(lib.bcp_chains_ukn_dev(block._c, C.c_void_p(d_u.data_ptr()), C.c_void_p(d_s.data_ptr()), C.c_void_p(st)),
+            "bcp_chains_ukn_dev")
+
+    def allred(a):
+        if not reduce:
+            return a
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+
+    N_k_glob = allred(N_k)
+    f, theta, it = mbar_solve(gpu_pass_fn(d_u.data_ptr(), n_loc, K, N_k_glob, device=dev, stream=st), N_k_glob, tol=tol,
+                              group=group, reduce=reduce)
+    P = dP = None
+    if populations:
+        Pl = np.zeros((K, S)); Ql = np.zeros((K, S))
+        A.check(lib.bcp_mbar_pops_dev(C.c_void_p(d_u.data_ptr()), n_loc, K, A.i64ptr(np.ascontiguousarray(N_k_glob, np.int64)),
+                                      A.dptr(A.f64(f)), C.c_void_p(d_s.data_ptr()), S, dev, C.c_void_p(st), A.dptr(Pl),
+                                      A.dptr(Ql)), "bcp_mbar_pops_dev")
+        PQ = allred(np.concatenate([Pl.ravel(), Ql.ravel()]))
+        P, dP = finish_populations(PQ[:K * S].reshape(K, S), PQ[K * S:].reshape(K, S), theta)
+    d = np.diag(theta)
+    return dict(f=f, theta=theta, Delta_f=f[None, :] - f[:, None],
+                dDelta_f=np.sqrt(np.abs(d[:, None] + d[None, :] - 2.0 * theta)), P=P, dP=dP, iters=it, N_k=N_k_glob)

@@ -252,10 +252,22 @@ int bcp_mbar_dev(const double* d_u_kn, const int64_t* N_k, int32_t K, int64_t N,
  * N_k_out [K] (may be NULL) receives the samples per run; pops / dpops [S][K] only if want_pops.  */
 int bcp_chains_score(bcp_chains* c, int32_t want_pops, double tol, int32_t max_iter, int64_t* N_k_out,
                      double* f_k, double* theta, double* pops, double* dpops, int32_t* iters);
+/* Building blocks of the same step for a block that holds a SHARD of the chains (multi-GPU score pipeline,
+ * biceps_b200/distributed.py:score_chains): the number of local samples and the local samples per run, and the
+ * local u_kn [K][n_samples] / state_n [n_samples] (may be NULL) written to caller-owned device buffers in the
+ * sample order described above.  Replaces the u_kln loop of Analysis.py:145-185 for the local trajectories. */
+int bcp_chains_n_samples(bcp_chains* c, int64_t* n_samples, int64_t* N_k_local);
+int bcp_chains_ukn_dev(bcp_chains* c, double* d_u_kn, int32_t* d_state_n, void* stream);
 /* One streaming reduction over a local shard of samples (multi-GPU MBAR: the caller all-reduces
  * s and M across ranks between passes): s[K] = sum_n W_nk, M[K][K] = sum_n W_nk W_nl.        */
 int bcp_mbar_pass_dev(const double* d_u_kn, int64_t n_local, int32_t K, const int64_t* N_k_global,
                       const double* f_k, int32_t want_hess, int device, void* stream, double* s_out, double* M_out);
+
+/* Weighted state histograms of a local shard at free energies f_k (compute_expectations of the state indicators,
+ * Analysis.py:217-223, before the sum over shards): P[K][S] = sum_n W_nl [s_n = i], Q[K][S] = sum_n W_nl^2 [s_n = i];
+ * host outputs.  After an all-reduce of both: P_i(l) = P, dP_i(l) = |P| sqrt(Q / P^2 + theta_ll - 2 Q / P).          */
+int bcp_mbar_pops_dev(const double* d_u_kn, int64_t n_local, int32_t K, const int64_t* N_k_global, const double* f_k,
+                      const int32_t* d_state_n, int32_t S, int device, void* stream, double* P_out, double* Q_out);
 
 /* ---------------------------------------------------------------------------------------
  * Convergence diagnostics of the sampled traces.

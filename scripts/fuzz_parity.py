@@ -45,7 +45,7 @@ for case in range(n_cases):
     want = cbind.sample(tabs, n, 7 + case, steps, chain_lambda=lam, n_threads=4, **kw)
     want2 = cbind.sample(tabs, n, 7 + case, 50, chain_lambda=lam, n_threads=4, step0=steps + burn, resume=want, traj_every=3)
     T = engine.DeviceTables(tabs)
-    for kern in ("spec", "fast", "coop", "generic", "auto"):
+    for kern in ("ws", "spec", "fast", "coop", "generic", "auto"):
         if kern == "auto":
             os.environ.pop("BCP_KERNEL", None)
         else:
@@ -62,5 +62,5 @@ for case in range(n_cases):
             print("MISMATCH case %d kernel %s R=%d S=%d K=%d hg=%d flat=%d n=%d steps=%d burn=%d te=%d trace=%d: %s" % (
                 case, kern, R, S, K, hg, flat, n, steps, burn, te, trace, str(e)[:80]), flush=True)
     T.close()
-print("fuzz: %d cases x 5 kernel choices, %d mismatches" % (n_cases, bad))
+print("fuzz: %d cases x 6 kernel choices, %d mismatches" % (n_cases, bad))
 sys.exit(1 if bad else 0)
