@@ -117,6 +117,15 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profile_json(name):
+    """Numbers taken from an ncu capture of this round, kept under profiles/ with the capture they come from."""
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def table_bytes(tables):
     n = tables["energy"].nbytes + np.asarray(tables["logZ"]).nbytes
     for rt in tables["restraints"]:
@@ -225,18 +234,16 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
-    hist_views = None
+    hist_flat = None
     if world > 1:
-        hist_views = distributed.device_histograms(blk)
-        sc, pc = hist_views
-        red = (torch.empty_like(sc), torch.empty_like(pc))
+        _sc, _pc, hist_flat = distributed.device_histograms(blk, fused=True)
+        red = torch.empty_like(hist_flat)
 
     def one_step():
         blk.launch(N_MCMC, stream=stream)
-        if hist_views is not None:             # per-lambda histograms summed over all GPUs' chains
-            for src, dst in zip(hist_views, red):
-                dst.copy_(src)
-                dist.all_reduce(dst, op=dist.ReduceOp.SUM)
+        if hist_flat is not None:              # per-lambda state + parameter histograms summed over all GPUs' chains:
+            red.copy_(hist_flat)               # one copy, ONE all-reduce (the two histograms are one block in HBM)
+            dist.all_reduce(red, op=dist.ReduceOp.SUM)
 
     import datetime
     clk_p, clk_f = start_clock_sampler(local_rank)
@@ -327,38 +334,48 @@ def run_ours(args, rank, world, local_rank):
                  "note": "same C3 tables, 303104 chains per GPU (thread-per-chain kernel); best of 3 launches"}
 
     # ---- BICePs-score time-to-solution (BASELINE configs[4], "C5"): 11 lambdas x 64 seeds sampled, snapshots
-    #      kept in HBM, rescored under every lambda and reweighted by MBAR (bcp_chains_score).  One GPU only. ----
-    score = None
-    if world == 1:
-        ens5 = synthetic.make_ensemble("C3", seed=0, n_lambda=11)
-        tabs5 = precompute.build_tables(ens5["energies"], ens5["lambdas"], ens5["restraints"], device=dev)
-        T5 = engine.DeviceTables(tabs5, device=dev)
-        n5, steps5 = 11 * 64, 1000000
-        lam5 = (np.arange(n5) % 11).astype(np.int32)
-        best = None
-        for rep in range(2):
-            b5 = T5.chains(n5, SEED + 10 + rep, chain_lambda=lam5)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            b5.launch(steps5, burn=0, traj_every=100, stream=stream)
-            b5.sync()
-            t1 = time.perf_counter()
-            r5 = b5.score(populations=True)
-            t2 = time.perf_counter()
-            b5.close()
-            if best is None or t2 - t0 < best[0]:
-                best = (t2 - t0, t1 - t0, t2 - t1, r5)
-        T5.close()
-        r5 = best[3]
-        score = {"workload": "C5: C3 tables, 11 lambdas x 64 seeds = 704 chains x 1e6 steps, traj_every 100 -> "
-                             "N = 7.04e6 snapshots, rescoring + MBAR (K = 11) + populations of 10000 states on the device",
-                 "seconds": best[0], "sampling_s": best[1], "rescoring_mbar_s": best[2], "mbar_iterations": r5["iters"],
-                 "biceps_score_lambda1": float(r5["f"][-1] - r5["f"][0]), "d_score": float(r5["dDelta_f"][0, -1]),
-                 "chain_steps_per_s": n5 * steps5 / best[1], "note": "best of 2; tables resident, results on the host"}
+    #      kept in HBM, rescored under every lambda and reweighted by MBAR.  One GPU: bcp_chains_score.  N GPUs: the
+    #      704 chains are sharded over the ranks, every rank rescores its own snapshots (bcp_chains_ukn_dev) and MBAR
+    #      runs over the sample shards with one NCCL all-reduce of K + K^2 doubles per pass and one of the weighted
+    #      state histograms (distributed.score_chains).  Time = max over ranks, tables resident, results on the host. ----
+    ens5 = synthetic.make_ensemble("C3", seed=0, n_lambda=11)
+    tabs5 = precompute.build_tables(ens5["energies"], ens5["lambdas"], ens5["restraints"], device=dev)
+    T5 = engine.DeviceTables(tabs5, device=dev)
+    n5_total, steps5 = 11 * 64, 1000000
+    first5, n5 = distributed.shard(n5_total, rank, world)
+    lam5 = ((first5 + np.arange(n5)) % 11).astype(np.int32)
+    best = None
+    for rep in range(2):
+        b5 = T5.chains(n5, SEED + 10 + rep, chain_id0=first5, chain_lambda=lam5)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        b5.launch(steps5, burn=0, traj_every=100, stream=stream)
+        b5.sync()
+        t1 = time.perf_counter()
+        r5 = b5.score(populations=True) if world == 1 else distributed.score_chains(b5, populations=True)
+        t2 = time.perf_counter()
+        b5.close()
+        tt = torch.tensor([t2 - t0, t1 - t0, t2 - t1], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tt = [float(x) for x in tt.tolist()]
+        if best is None or tt[0] < best[0]:
+            best = (tt[0], tt[1], tt[2], r5)
+    T5.close()
+    r5 = best[3]
+    score = {"workload": "C5: C3 tables, 11 lambdas x 64 seeds = 704 chains x 1e6 steps (sharded over %d GPU(s)), traj_every 100 -> "
+                         "N = 7.04e6 snapshots, rescoring + MBAR (K = 11) + populations of 10000 states on the device" % world,
+             "seconds": best[0], "sampling_s": best[1], "rescoring_mbar_s": best[2], "mbar_iterations": r5["iters"],
+             "biceps_score_lambda1": float(r5["f"][-1] - r5["f"][0]), "d_score": float(r5["dDelta_f"][0, -1]),
+             "chain_steps_per_s": n5_total * steps5 / best[1], "n_gpus": world,
+             "collectives": "none" if world == 1 else "NCCL all-reduce of N_k, of s[K] + M[K][K] per MBAR pass, of P/Q[K][S]",
+             "note": "best of 2; max over ranks; tables resident, results on the host"}
 
     # ---- C2 (BASELINE configs[1]): chignolin-scale, 1000 states, cs_H/cs_Ca/cs_N/J/NOE, 8 lambdas x 1024 chains ----
     c2 = None
-    if world == 1:
+    if rank == 0:
         ens2 = synthetic.make_ensemble("C2", seed=0, n_lambda=N_LAMBDA)
         tabs2 = precompute.build_tables(ens2["energies"], ens2["lambdas"], ens2["restraints"], device=dev)
         T2c = engine.DeviceTables(tabs2, device=dev)
@@ -378,11 +395,11 @@ def run_ours(args, rank, world, local_rank):
     # ---- C4 (BASELINE configs[3]): HDX protection factors on the 6-D grid, 1e5 states (1.3 GB of <N_c>/<N_h>
     #      counts in HBM), warp-per-chain kernel evaluating the term on the fly: the one HBM-bound sampler ----
     pf_c4 = None
-    if world == 1:
+    if True:
         tabs4 = synthetic.make_pf_tables(n_states=100000)
         T4 = engine.DeviceTables(tabs4, device=dev)
         n4, steps4 = 32768, 500
-        b4 = T4.chains(n4, SEED + 20)
+        b4 = T4.chains(n4, SEED + 20, chain_id0=rank * n4)
         b4.launch(100, stream=stream)
         ms4 = []
         for _ in range(3):
@@ -390,17 +407,25 @@ def run_ours(args, rank, world, local_rank):
             b4.sync()
             ms4.append(b4.last_kernel_ms()[0])
         b4.close(); T4.close()
-        rate4 = n4 * steps4 / (min(ms4) * 1e-3)
+        t = torch.tensor([min(ms4)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rate4 = world * n4 * steps4 / (float(t.item()) * 1e-3)
         row_bytes = 16.0 * 107                      # two 8 J-byte rows per evaluated proposal
         peak4, _src = measured_peak_hbm()
-        pf_c4 = {"workload": "C4: 100000 states x 107 residues, default 6-D grid (20x26x50x7x8x1), 32768 chains x 500 steps",
-                 "value": rate4, "unit": "chain-steps/s", "kernel": "bcp::mcmc_pf2_kernel<1,4>",
-                 "roofline": {"bound": "hbm", "achieved": rate4 * row_bytes / 1e9, "peak": peak4, "unit": "GB/s",
-                              "frac": rate4 * row_bytes / 1e9 / peak4, "algorithmic_bytes_per_chain_step": row_bytes,
-                              "traffic": 14.467e9 + 8.3e6,
-                              "note": "algorithmic = the two rows of counts every proposal reads; ncu (profiles/"
-                                      "r01_mcmc_pf2_32k.summary.txt, same launch): 14.5 GB of DRAM reads = 883 B per "
-                                      "chain-step, L2 serves the rest (a nuisance move re-reads rows of the chain's state)"}}
+        prof4 = profile_json("r02_mcmc_pf2_traffic.json") or profile_json("r01_mcmc_pf2_traffic.json") or {}
+        dram_per_step = prof4.get("dram_bytes_per_chain_step")
+        pf_c4 = {"workload": "C4: 100000 states x 107 residues, default 6-D grid (20x26x50x7x8x1), 32768 chains x 500 steps "
+                             "per GPU, chains sharded over %d GPU(s), counts replicated" % world,
+                 "value": rate4, "unit": "chain-steps/s", "n_gpus": world, "kernel": "bcp::mcmc_pf2_kernel<1,4>",
+                 "roofline": {"bound": "hbm", "achieved": rate4 / world * row_bytes / 1e9, "peak": peak4, "unit": "GB/s",
+                              "frac": rate4 / world * row_bytes / 1e9 / peak4, "algorithmic_bytes_per_chain_step": row_bytes,
+                              "traffic": None if dram_per_step is None else dram_per_step * n4 * steps4,
+                              "dram_frac": None if dram_per_step is None else rate4 / world * dram_per_step / 1e9 / peak4,
+                              "traffic_source": prof4.get("source"),
+                              "note": "per GPU; algorithmic = the two rows of counts every proposal reads (L2 serves the "
+                                      "re-reads of a chain's own state); traffic / dram_frac = DRAM bytes of the ncu capture "
+                                      "named in traffic_source scaled to this launch"}}
 
     # ---- convergence diagnostics of the sampled traces: K8 autocorrelation against the fp64 pipe ----
     conv = None

@@ -19,7 +19,6 @@ def find_all_state_sampled_time(trace, nstates, verbose=True):
     """First step at which every state has been visited (Analysis.py:16-35), vectorised."""
     trace = np.asarray(trace, dtype=np.int64)
     first = np.full(nstates, -1, dtype=np.int64)
-    seen_at = {}
     uniq, idx = np.unique(trace, return_index=True)
     first[uniq] = idx
     order = np.sort(idx)
@@ -33,7 +32,6 @@ def find_all_state_sampled_time(trace, nstates, verbose=True):
             print('not all state sampled, these states', np.where(first < 0)[0], 'are not sampled')
         return 'null', list(frac_steps)
     init = int(first.max()) + 1
-    del seen_at
     return init, list(frac_steps[:init])
 
 

@@ -15,4 +15,3 @@ from .Restraint import Preparation, Ensemble, get_restraint_options        # noq
 from .PosteriorSampler import PosteriorSampler, PosteriorSamplingTrajectory   # noqa: F401
 from .Analysis import Analysis, find_all_state_sampled_time   # noqa: F401
 from .convergence import Convergence                           # noqa: F401
-from .decorators import multiprocess                           # noqa: F401

@@ -142,16 +142,6 @@ def compute_JSD(T1, T2, T_total, ind, allowed_parameters):
     return jsd_tasks(idx, [(0, idx.shape[0], a.shape[0], 0, 0, len(allowed_parameters), 0)])[0]
 
 
-def _pyplot():
-    try:
-        import matplotlib
-        matplotlib.use('Agg')
-        from matplotlib import pyplot as plt
-        return plt
-    except Exception:
-        return None
-
-
 class Convergence(object):
 
     def __init__(self, traj=None, filename=None, outdir="./", verbose=False, device=0):
@@ -224,109 +214,6 @@ class Convergence(object):
                 labels.append("$\\%s_{{%s}_{%s}}$" % tuple(r.split('_')[:3]))
         return labels
 
-    # ---- figures (optional) ----------------------------------------------------------------------
-    def plot_traces(self, figname="traj_traces.png", xlim=None):
-        plt = _pyplot()
-        if plt is None:
-            return
-        total_steps = len(self.sampled_parameters[0])
-        x = np.arange(1, total_steps + 0.1, 1) * self.freq_save_traj
-        n = len(self.rest_type)
-        plt.figure(figsize=(3 * n, 15))
-        for i in range(n):
-            plt.subplot(n, 1, i + 1)
-            plt.plot(x, self.sampled_parameters[i], label=self.labels[i])
-            plt.xlabel('steps')
-            if xlim:
-                plt.xlim(left=xlim[0], right=xlim[1])
-            plt.legend(loc='best')
-        plt.tight_layout()
-        plt.savefig(os.path.join(self.outdir, figname))
-        plt.close()
-
-    def plot_auto_curve(self, xlim=None, figname="autocorrelation_curve.png", std_x=None, std_y=None):
-        plt = _pyplot()
-        if plt is None:
-            return
-        n = len(self.autocorr)
-        plt.figure(figsize=(10, 5 * n))
-        for i in range(n):
-            ax = plt.subplot(n, 1, i + 1)
-            ax.plot(np.arange(self.autocorr[i].shape[0]), self.autocorr[i], label=self.labels[i])
-            if isinstance(std_y, np.ndarray):
-                ax.fill_between(np.arange(self.autocorr[i].shape[0]), self.autocorr[i] - std_y[i],
-                                self.autocorr[i] + std_y[i], color='r', alpha=0.4)
-            ax.set_xlabel(r'$\tau$')
-            ax.set_ylabel(r'$g(\tau)$')
-            if xlim:
-                ax.set_xlim(left=xlim[0], right=xlim[1])
-            ax.legend(loc='best')
-        plt.tight_layout()
-        plt.savefig(os.path.join(self.outdir, figname))
-        plt.close()
-
-    def plot_auto_curve_with_exp_fitting(self, figname="autocorrelation_curve_with_exp_fitting.png"):
-        plt = _pyplot()
-        if plt is None:
-            return
-        n = len(self.autocorr)
-        plt.figure(figsize=(10, 5 * n))
-        for i in range(n):
-            ax = plt.subplot(n, 1, i + 1)
-            ax.plot(np.arange(self.autocorr[i].shape[0]), self.autocorr[i], label=self.labels[i])
-            ax.plot(np.arange(self.yFits[i].shape[0]), self.yFits[i], 'r--', label='fit')
-            ax.legend(loc='best')
-        plt.tight_layout()
-        plt.savefig(os.path.join(self.outdir, figname))
-        plt.close()
-
-    def plot_block_avg(self, nblock, r_max, figname="block_avg.png"):
-        plt = _pyplot()
-        if plt is None:
-            return
-        x = np.arange(1., nblock + 1., 1.)
-        n = len(self.rest_type)
-        plt.figure(figsize=(10, 5 * n))
-        for i in range(n):
-            plt.subplot(n, 1, i + 1)
-            plt.plot(x, r_max[i], 'o-', label=self.labels[i])
-            plt.xlabel('block')
-            plt.legend(loc='best')
-        plt.tight_layout()
-        plt.savefig(os.path.join(self.outdir, figname))
-        plt.close()
-
-    def plot_JSD_conv(self, JSD, JSDs, p_limit=0.99):
-        plt = _pyplot()
-        if plt is None:
-            return
-        for k in range(len(JSD)):
-            plt.figure(figsize=(10, 5))
-            for j in range(len(JSD[0])):
-                both = np.append(JSDs[k][j], JSD[k][j])
-                srt = np.sort(both)
-                ind = np.where(srt == JSD[k][j])[0][0]
-                plt.plot(j + 1, ind / (len(both) - 1.), 'o', ms=5, color='red')
-            plt.axhline(p_limit, color='r', ls='--')
-            plt.savefig(os.path.join(self.outdir, "JSD_conv_%s.pdf" % self.rest_type[k]))
-            plt.close()
-
-    def plot_JSD_distribution(self, all_JSD, all_JSDs, nround, nfold, figname="JSD_distribution.png"):
-        plt = _pyplot()
-        if plt is None:
-            return
-        n = len(self.rest_type)
-        x = np.arange(int(100 / nfold), 101., int(100 / nfold))
-        plt.figure(figsize=(10, 5 * n))
-        for i in range(n):
-            plt.subplot(n, 1, i + 1)
-            plt.plot(x, all_JSD[i], 'o-', label=self.labels[i])
-            b = np.sort(all_JSDs[i])
-            plt.fill_between(x, b[:, int(nround * 0.05)], b[:, int(nround * 0.95)], alpha=0.4)
-            plt.legend(loc='best')
-        plt.savefig(os.path.join(self.outdir, figname))
-        plt.close()
-
     # ---- numbers -----------------------------------------------------------------------------------
     def get_autocorrelation_curves(self, method="auto", nblocks=5, maxtau=10000, plot_traces=False):
         """convergence.py:380-440.  method: "auto" | "block-avg-auto" | "exp"."""
@@ -353,7 +240,6 @@ class Convergence(object):
             else:
                 std_y, std_x = np.std(y, axis=1), np.std(x, axis=1)
             self.std_y, self.std_x = std_y, std_x
-            self.plot_auto_curve(std_x=std_x, std_y=std_y)
         elif method == "exp":
             self.yFits, self.popts = [], []
             for i in range(len(self.autocorr)):
@@ -361,11 +247,8 @@ class Convergence(object):
                 self.popts.append(popt)
                 self.yFits.append(yFit)
             self.tau_c = np.array(self.popts)
-            self.plot_auto_curve_with_exp_fitting()
         else:
             raise KeyError(f"Method must be 'block-avg-auto' or 'exp' or 'auto'. You provided: {method}")
-        if plot_traces:
-            self.plot_traces()
 
     def process(self, nblock=5, nfold=10, nround=100, savefile=True, block_avg=False, normalize=True,
                 rng="numpy", seed=0):
@@ -394,7 +277,6 @@ class Convergence(object):
             h = param_hist(idx, rows, max(nb), self.device).reshape(P, nblock, max(nb))
             self.r_total = [[h[i, b, :nb[i]].astype(np.float64) for b in range(nblock)] for i in range(P)]
             self.r_max = [[self.allowed_parameters[i][int(np.argmax(r))] for r in self.r_total[i]] for i in range(P)]
-            self.plot_block_avg(nblock, self.r_max)
 
         rows, sel, sel_off = [], [], 0
         for i in range(P):
@@ -422,5 +304,3 @@ class Convergence(object):
         if savefile:
             np.save(os.path.join(self.outdir, "all_JSD.npy"), self.all_JSD)
             np.save(os.path.join(self.outdir, "all_JSDs.npy"), self.all_JSDs)
-        self.plot_JSD_distribution(self.all_JSD, self.all_JSDs, nround, nfold)
-        self.plot_JSD_conv(self.all_JSD, self.all_JSDs)

@@ -13,18 +13,34 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-void keep_pool_memory(int device) {
-    static std::atomic<uint64_t> done{0};
-    if (device < 0 || device >= 64) return;
-    const uint64_t bit = 1ull << device;
-    if (done.load(std::memory_order_relaxed) & bit) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+cudaMemPool_t library_pool(int device) {
+    static std::atomic<cudaMemPool_t> pools[64];
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return nullptr;
+    if (device < 0 || device >= 64) return nullptr;
+    cudaMemPool_t p = pools[device].load(std::memory_order_acquire);
+    if (p) return p;
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t fresh = nullptr;
+    if (cudaMemPoolCreate(&fresh, &props) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(fresh, cudaMemPoolAttrReleaseThreshold, &thr);
+    cudaMemPool_t expected = nullptr;
+    if (!pools[device].compare_exchange_strong(expected, fresh, std::memory_order_acq_rel)) {
+        cudaMemPoolDestroy(fresh);              // another thread was first
+        return expected;
     }
-    (void)cudaGetLastError();
-    done.fetch_or(bit, std::memory_order_relaxed);
+    return fresh;
+}
+
+cudaError_t pool_malloc(void** p, size_t bytes, cudaStream_t st) {
+    *p = nullptr;
+    if (bytes == 0) return cudaSuccess;
+    cudaMemPool_t pool = library_pool(-1);
+    return pool ? cudaMallocFromPoolAsync(p, bytes, pool, st) : cudaMallocAsync(p, bytes, st);
 }
 
 }  // namespace bcp

@@ -36,7 +36,6 @@ extern std::atomic<uint64_t> g_kernel_launches;
 
 // RAII device-selection guard: every entry point runs on the handle's device and restores
 // the caller's current device afterwards.
-void keep_pool_memory(int device);
 
 struct DeviceGuard {
     int prev = -1;
@@ -44,7 +43,6 @@ struct DeviceGuard {
         cudaGetDevice(&prev);
         if (prev != dev) cudaSetDevice(dev);
         else prev = -1;
-        keep_pool_memory(dev);
         (void)cudaGetLastError();   // a stale error of another library must not be blamed on our launches
     }
     ~DeviceGuard() {
@@ -59,22 +57,22 @@ static inline cudaError_t dev_alloc(T** p, size_t n) {
     return cudaMalloc((void**)p, n * sizeof(T));
 }
 
-// stream-ordered allocation on the legacy default stream: with the pool's release threshold raised
-// (keep_pool_memory) a create/destroy cycle recycles the same blocks and costs microseconds, where
-// cudaMalloc/cudaFree cost ~0.5 ms each and synchronise the device
+// Stream-ordered allocation from the library's OWN memory pool (one per device, release threshold raised so that a
+// create / destroy cycle recycles the same blocks and costs microseconds, where cudaMalloc / cudaFree cost ~0.5 ms each
+// and synchronise the device).  The process-wide default pool of the device -- shared with torch's cudaMallocAsync
+// backend, CuPy, RMM ... -- is left untouched.
+cudaMemPool_t library_pool(int device);        // current device if device < 0; nullptr on failure (plain cudaMallocAsync is used)
+cudaError_t pool_malloc(void** p, size_t bytes, cudaStream_t st);
+
 template <typename T>
-static inline cudaError_t pool_alloc(T** p, size_t n) {
+static inline cudaError_t pool_alloc(T** p, size_t n, cudaStream_t st = (cudaStream_t)0) {
     *p = nullptr;
     if (n == 0) return cudaSuccess;
-    return cudaMallocAsync((void**)p, n * sizeof(T), (cudaStream_t)0);
+    return pool_malloc((void**)p, n * sizeof(T), st);
 }
-static inline void pool_free(void* p) {
-    if (p) cudaFreeAsync(p, (cudaStream_t)0);
+static inline void pool_free(void* p, cudaStream_t st = (cudaStream_t)0) {
+    if (p) cudaFreeAsync(p, st);
 }
-
-// keep the stream-ordered pool's memory across synchronisations (the default release threshold of 0
-// gives every block back to the driver at each sync, which makes cudaMallocAsync as slow as cudaMalloc)
-void keep_pool_memory(int device);
 
 // K8 on device-resident series (convergence.cu): curves[n_series][max_tau+1], tau[n_series]
 int autocorr_run(const double* d_series, int32_t n_series, int64_t T, int32_t max_tau, int32_t normalize,

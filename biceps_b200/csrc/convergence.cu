@@ -296,8 +296,8 @@ int autocorr_run(const double* d_series, int32_t n_series, int64_t T, int32_t ma
     const int seg_per_chunk = (int)((n_seg + n_chunk - 1) / n_chunk);
     n_chunk = (n_seg + seg_per_chunk - 1) / seg_per_chunk;
     double *z = nullptr, *partial = nullptr;
-    BCP_CUDA(cudaMallocAsync((void**)&z, sizeof(double) * (size_t)n_series * T, st));
-    BCP_CUDA(cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)n_series * n_chunk * n_lags, st));
+    BCP_CUDA(bcp::pool_malloc((void**)&z, sizeof(double) * (size_t)n_series * T, st));
+    BCP_CUDA(bcp::pool_malloc((void**)&partial, sizeof(double) * (size_t)n_series * n_chunk * n_lags, st));
     center_kernel<<<n_series, 256, 0, st>>>(d_series, T, z);
     for (int s0 = 0; s0 < n_series; s0 += 65535) {          // gridDim.z limit
         const int ns = (n_series - s0 < 65535) ? n_series - s0 : 65535;

@@ -470,9 +470,9 @@ static int mbar_work_init(MbarWork& w, int device, int K, long long N, const int
         w.lnN[k] = N_k[k] > 0 ? log((double)N_k[k]) : -INFINITY;
         w.rn[k] = N_k[k] > 0 ? 1.0 / (double)N_k[k] : 0.0;
     }
-    BCP_CUDA(cudaMallocAsync((void**)&w.d_a, K * 8, st)); BCP_CUDA(cudaMallocAsync((void**)&w.d_rn, K * 8, st));
-    BCP_CUDA(cudaMallocAsync((void**)&w.d_partial, std::max((size_t)w.grid * w.n_acc_h, (size_t)w.grid_plain * K) * 8, st));
-    BCP_CUDA(cudaMallocAsync((void**)&w.d_out, (size_t)w.n_acc_h * 8, st));
+    BCP_CUDA(bcp::pool_malloc((void**)&w.d_a, K * 8, st)); BCP_CUDA(bcp::pool_malloc((void**)&w.d_rn, K * 8, st));
+    BCP_CUDA(bcp::pool_malloc((void**)&w.d_partial, std::max((size_t)w.grid * w.n_acc_h, (size_t)w.grid_plain * K) * 8, st));
+    BCP_CUDA(bcp::pool_malloc((void**)&w.d_out, (size_t)w.n_acc_h * 8, st));
     BCP_CUDA(cudaMemcpyAsync(w.d_rn, w.rn.data(), K * 8, cudaMemcpyHostToDevice, st));
     const size_t sm = pass_smem(K, w.n_acc_h);
     BCP_CUDA(cudaFuncSetAttribute(mbar_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -698,8 +698,8 @@ static int mbar_impl(const double* d_u, const int32_t* d_state, const int64_t* N
     if (rc != BCP_OK) return rc;
     if (d_state && S > 0 && (pops || dpops)) {
         double *d_P = nullptr, *d_Q = nullptr;
-        BCP_CUDA(cudaMallocAsync((void**)&d_P, (size_t)K * S * 8, st));          // stream-ordered pool, no device sync
-        cudaError_t e = cudaMallocAsync((void**)&d_Q, (size_t)K * S * 8, st);
+        BCP_CUDA(bcp::pool_malloc((void**)&d_P, (size_t)K * S * 8, st));          // stream-ordered pool, no device sync
+        cudaError_t e = bcp::pool_malloc((void**)&d_Q, (size_t)K * S * 8, st);
         if (e != cudaSuccess) { cudaFreeAsync(d_P, st); set_error("bcp_mbar: cudaMallocAsync: %s", cudaGetErrorString(e)); return BCP_ERR_CUDA; }
         rc = mbar_populations(w, d_u, f_k, d_state, S, d_P, d_Q, st);
         std::vector<double> P((size_t)K * S), Q((size_t)K * S);
@@ -782,8 +782,8 @@ extern "C" int bcp_mbar_pops_dev(const double* d_u_kn, int64_t n_local, int32_t 
     int rc = mbar_work_init(w, device, K, n_local, N_k_global, st);
     if (rc != BCP_OK) return rc;
     double *d_P = nullptr, *d_Q = nullptr;
-    BCP_CUDA(cudaMallocAsync((void**)&d_P, (size_t)K * S * 8, st));
-    cudaError_t e = cudaMallocAsync((void**)&d_Q, (size_t)K * S * 8, st);
+    BCP_CUDA(bcp::pool_malloc((void**)&d_P, (size_t)K * S * 8, st));
+    cudaError_t e = bcp::pool_malloc((void**)&d_Q, (size_t)K * S * 8, st);
     if (e != cudaSuccess) { cudaFreeAsync(d_P, st); set_error("bcp_mbar_pops_dev: cudaMallocAsync: %s", cudaGetErrorString(e)); return BCP_ERR_CUDA; }
     rc = mbar_populations(w, d_u_kn, f_k, d_state_n, S, d_P, d_Q, st);
     if (rc == BCP_OK) {

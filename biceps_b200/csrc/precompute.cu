@@ -238,7 +238,7 @@ struct Scratch {
     cudaStream_t st = nullptr;
     ~Scratch() { for (void* q : p) cudaFreeAsync(q, st); }
     template <typename T> cudaError_t get(T** out, size_t n) {
-        cudaError_t e = cudaMallocAsync((void**)out, (n ? n : 1) * sizeof(T), st);
+        cudaError_t e = bcp::pool_malloc((void**)out, (n ? n : 1) * sizeof(T), st);
         if (e == cudaSuccess) p.push_back(*out);
         return e;
     }

@@ -356,6 +356,12 @@ struct bcp_handle {
     int32_t grid_len[BCP_MAX_PARAMS];
     int32_t p_slot[BCP_MAX_PARAMS];   // where parameter p lives: 0 sigma, 1 gamma, 2 + k PF grid k
     double* d_energy_t = nullptr;     // energy[K][S] transposed to [S][K] for the rescoring kernels (K6)
+    cudaStream_t stream = nullptr;    // the handle's own stream: table uploads, layout kernels, bcp_neglogp
+    // persistent scratch of bcp_neglogp (the reference's Analysis calls neglogP K^2 x nsnaps times, one configuration
+    // per call: Analysis.py:182): device + page-locked host staging for up to NL_CAP configurations
+    static constexpr int NL_CAP = 4096;
+    unsigned char* nl_dev = nullptr;
+    unsigned char* nl_host = nullptr;
 };
 
 struct bcp_chains {
@@ -393,11 +399,11 @@ template <typename T>
 static int upload(bcp_handle* h, const T* host, size_t n, const T** dev) {
     T* d = nullptr;
     if (n == 0) { *dev = nullptr; return BCP_OK; }
-    BCP_CUDA(pool_alloc(&d, n));
+    BCP_CUDA(pool_alloc(&d, n, h->stream));
     h->allocs.push_back(d);
-    // asynchronous on the legacy stream: page-locked caller tables (bcp_host_alloc) stream back to back at the
+    // asynchronous on the handle's stream: page-locked caller tables (bcp_host_alloc) stream back to back at the
     // PCIe rate, pageable ones are staged by the driver before the call returns; bcp_create synchronises once
-    BCP_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, (cudaStream_t)0));
+    BCP_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     *dev = d;
     return BCP_OK;
 }
@@ -416,6 +422,11 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
 
     bcp_handle* h = new bcp_handle();
     h->device = device;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("bcp_create: cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return BCP_ERR_CUDA;
+    }
     SamplerTables& T = h->T;
     T.R = t->n_restraints; T.S = t->n_states; T.K = t->n_lambda;
     T.nuis_thresh = (uint32_t)(((uint64_t)T.R << 32) / (uint64_t)(T.R + 1));
@@ -503,7 +514,7 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
         // derived layouts are built on the device from the uploaded tables (a host-side build of the
         // 2 x 13 MB halo tables dominated bcp_create)
         double* d_rec = nullptr;
-        if (pool_alloc(&d_rec, (size_t)T.S * T.rec_stride) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
+        if (pool_alloc(&d_rec, (size_t)T.S * T.rec_stride, h->stream) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
         h->allocs.push_back(d_rec);
         T.rec = d_rec;
         T.gsse_halo = nullptr; T.gsse_halo4 = nullptr; T.gh4_stride = 0;
@@ -512,7 +523,7 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
         if (T.r[T.R - 1].has_gamma) {
             G = T.r[T.R - 1].n_gamma;
             T.gh4_stride = (G + 9 + 1) & ~1;
-            if (pool_alloc(&d_h2, (size_t)T.S * (G + 4)) != cudaSuccess || pool_alloc(&d_h4, (size_t)T.S * T.gh4_stride) != cudaSuccess) {
+            if (pool_alloc(&d_h2, (size_t)T.S * (G + 4), h->stream) != cudaSuccess || pool_alloc(&d_h4, (size_t)T.S * T.gh4_stride, h->stream) != cudaSuccess) {
                 if (d_h2) h->allocs.push_back(d_h2);
                 set_error("bcp_create: out of device memory");
                 return fail(BCP_ERR_CUDA);
@@ -521,11 +532,11 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
             T.gsse_halo = d_h2; T.gsse_halo4 = d_h4;
         }
         int* d_flag = nullptr;
-        if (pool_alloc(&d_flag, 1) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
+        if (pool_alloc(&d_flag, 1, h->stream) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
         h->allocs.push_back(d_flag);
-        cudaMemsetAsync(d_flag, 0, sizeof(int), 0);
+        cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream);
         const long long work = (long long)T.S * (T.gh4_stride > 2 * T.R ? T.gh4_stride : 2 * T.R);
-        build_layouts_kernel<<<(unsigned)((work + 255) / 256), 256>>>(T, d_rec, d_h2, d_h4, d_flag);
+        build_layouts_kernel<<<(unsigned)((work + 255) / 256), 256, 0, h->stream>>>(T, d_rec, d_h2, d_h4, d_flag);
         BCP_LAUNCHED(1);
         // packed sigma entries for the speculative kernel; 1 / (2 sigma^2) is the correctly rounded
         // IEEE reciprocal (host division), which is what makes the device-side Markstein division exact
@@ -546,7 +557,8 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
         T.sig4_bytes = (int)(sig4.size() * sizeof(double));
         if ((rc = upload(h, sig4.data(), sig4.size(), &T.sig4)) != BCP_OK) return fail(rc);
         int flag = 0;
-        if (cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        if (cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) {
             set_error("bcp_create: layout kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
             return fail(BCP_ERR_CUDA);
         }
@@ -554,11 +566,11 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
     }
     if ((rc = upload(h, t->energy, (size_t)T.K * T.S, &T.energy)) != BCP_OK) return fail(rc);
     if ((rc = upload(h, t->logZ, (size_t)T.K, &T.logZ)) != BCP_OK) return fail(rc);
-    if (pool_alloc(&h->d_energy_t, (size_t)T.K * T.S) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
+    if (pool_alloc(&h->d_energy_t, (size_t)T.K * T.S, h->stream) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
     h->allocs.push_back(h->d_energy_t);
-    transpose_energy_kernel<<<(unsigned)(((long long)T.K * T.S + 255) / 256), 256>>>(T.energy, T.K, T.S, h->d_energy_t);
+    transpose_energy_kernel<<<(unsigned)(((long long)T.K * T.S + 255) / 256), 256, 0, h->stream>>>(T.energy, T.K, T.S, h->d_energy_t);
     BCP_LAUNCHED(1);
-    if (cudaStreamSynchronize((cudaStream_t)0) != cudaSuccess) {       // no caller pointer is kept after the return
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) {       // no caller pointer is kept after the return
         set_error("bcp_create: table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(BCP_ERR_CUDA);
     }
@@ -570,7 +582,11 @@ extern "C" void bcp_destroy(bcp_handle* h) {
     if (!h) return;
     if (--h->refs > 0) return;      // chains still alive: the last bcp_chains_destroy frees the tables
     DeviceGuard guard(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) pool_free(p);
+    pool_free(h->nl_dev);
+    if (h->nl_host) cudaFreeHost(h->nl_host);
+    if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
@@ -634,8 +650,9 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
     TRY_CUDA(pool_alloc(&C.E, n));
     TRY_CUDA(pool_alloc(&C.accepted, n));
     TRY_CUDA(pool_alloc(&C.sep, (size_t)(T.R + 1) * n));
-    TRY_CUDA(pool_alloc(&C.state_counts, (size_t)n_groups * T.S));
-    TRY_CUDA(pool_alloc(&C.param_counts, (size_t)n_groups * T.HB));
+    // both histograms in ONE block, state counts first: a multi-GPU caller all-reduces them with one collective
+    TRY_CUDA(pool_alloc(&C.state_counts, (size_t)n_groups * ((size_t)T.S + T.HB)));
+    C.param_counts = C.state_counts + (size_t)n_groups * T.S;
     TRY_CUDA(pool_alloc(&C.spec_stats, 2));
     TRY_CUDA(cudaMemset(C.spec_stats, 0, 2 * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.accepted, 0, n * sizeof(unsigned long long)));
@@ -668,7 +685,7 @@ extern "C" void bcp_chains_destroy(bcp_chains* c) {
     pool_free(c->d_mt_raw); pool_free(c->d_mt_pos); pool_free(c->d_mt_dry);
     pool_free(c->d_lam); pool_free(c->d_group);
     pool_free(c->C.state); pool_free(c->C.isg); pool_free(c->C.igm); pool_free(c->C.ipf); pool_free(c->C.E);
-    pool_free(c->C.accepted); pool_free(c->C.sep); pool_free(c->C.state_counts); pool_free(c->C.param_counts);
+    pool_free(c->C.accepted); pool_free(c->C.sep); pool_free(c->C.state_counts);      // (param_counts lives in the same block)
     pool_free(c->C.spec_stats);
     pool_free(c->d_traj_E); pool_free(c->d_traj_state); pool_free(c->d_traj_accept); pool_free(c->d_traj_idx);
     pool_free(c->d_trace);
@@ -1071,11 +1088,11 @@ extern "C" int bcp_chains_autocorr(bcp_chains* c, const double* grid_values, int
     int rc = BCP_OK;
     do {
 #define STEP(x) if ((x) != cudaSuccess) { set_error("bcp_chains_autocorr: %s: %s", #x, cudaGetErrorString(cudaGetLastError())); rc = BCP_ERR_CUDA; break; }
-        STEP(cudaMallocAsync((void**)&d_grid, sizeof(double) * (size_t)T.HB, st));
-        STEP(cudaMallocAsync((void**)&d_off, sizeof(int) * (size_t)P, st));
-        STEP(cudaMallocAsync((void**)&d_series, sizeof(double) * n_series * (size_t)ns, st));
-        STEP(cudaMallocAsync((void**)&d_curves, sizeof(double) * n_out, st));
-        STEP(cudaMallocAsync((void**)&d_tau, sizeof(double) * n_series, st));
+        STEP(bcp::pool_malloc((void**)&d_grid, sizeof(double) * (size_t)T.HB, st));
+        STEP(bcp::pool_malloc((void**)&d_off, sizeof(int) * (size_t)P, st));
+        STEP(bcp::pool_malloc((void**)&d_series, sizeof(double) * n_series * (size_t)ns, st));
+        STEP(bcp::pool_malloc((void**)&d_curves, sizeof(double) * n_out, st));
+        STEP(bcp::pool_malloc((void**)&d_tau, sizeof(double) * n_series, st));
         STEP(cudaMemcpyAsync(d_grid, grid_values, sizeof(double) * (size_t)T.HB, cudaMemcpyHostToDevice, st));
         STEP(cudaMemcpyAsync(d_off, off.data(), sizeof(int) * (size_t)P, cudaMemcpyHostToDevice, st));
         const long long work = ns * P * n;
@@ -1199,22 +1216,40 @@ extern "C" int bcp_neglogp(bcp_handle* h, int64_t n, const int32_t* lam, const i
             BCP_REQUIRE(indices[i * T.P + p] >= 0 && indices[i * T.P + p] < h->grid_len[p],
                         "bcp_neglogp: indices[%lld][%d] out of range", (long long)i, p);
     }
-    int *d_lam = nullptr, *d_state = nullptr, *d_idx = nullptr;
-    double* d_out = nullptr;
-    int rc = BCP_OK;
-    do {
-#define STEP(x) if ((x) != cudaSuccess) { set_error("bcp_neglogp: %s: %s", #x, cudaGetErrorString(cudaGetLastError())); rc = BCP_ERR_CUDA; break; }
-        if (lam) { STEP(dev_alloc(&d_lam, (size_t)n)); STEP(cudaMemcpy(d_lam, lam, n * 4, cudaMemcpyHostToDevice)); }
-        STEP(dev_alloc(&d_state, (size_t)n)); STEP(cudaMemcpy(d_state, state, n * 4, cudaMemcpyHostToDevice));
-        STEP(dev_alloc(&d_idx, (size_t)n * T.P)); STEP(cudaMemcpy(d_idx, indices, (size_t)n * T.P * 4, cudaMemcpyHostToDevice));
-        STEP(dev_alloc(&d_out, (size_t)n));
-        if (T.pf.q >= 0) { STEP(launch_energy_pf(T, n, d_lam, d_state, d_idx, d_out, 0, nullptr)); }
-        else neglogp_kernel<<<(unsigned)((n + 255) / 256), 256>>>(T, n, d_lam, d_state, d_idx, d_out);
+    // per configuration: lam (4), state (4), indices (4 P), energy (8); the scratch of the handle is reused from call to
+    // call (no allocation, page-locked staging, ONE synchronisation), larger batches go through it in pieces
+    cudaStream_t st = h->stream;
+    const size_t cap = bcp_handle::NL_CAP;
+    const size_t per = 8 + 4 + 4 + 4 * (size_t)T.P;
+    if (!h->nl_dev) {
+        BCP_CUDA(pool_malloc((void**)&h->nl_dev, cap * per, st));
+        BCP_CUDA(cudaHostAlloc((void**)&h->nl_host, cap * per, cudaHostAllocDefault));
+    }
+    for (int64_t i0 = 0; i0 < n; i0 += (int64_t)cap) {
+        const size_t m = (size_t)std::min<int64_t>((int64_t)cap, n - i0);
+        // layout (device and host alike): energy[m] | lam[m] | state[m] | indices[m][P]
+        double* h_out = (double*)h->nl_host;
+        int32_t* h_lam = (int32_t*)(h->nl_host + 8 * cap);
+        int32_t* h_state = h_lam + cap;
+        int32_t* h_idx = h_state + cap;
+        double* d_out = (double*)h->nl_dev;
+        int* d_lam = (int*)(h->nl_dev + 8 * cap);
+        int* d_state = d_lam + cap;
+        int* d_idx = d_state + cap;
+        if (lam) memcpy(h_lam, lam + i0, m * 4);
+        memcpy(h_state, state + i0, m * 4);
+        memcpy(h_idx, indices + i0 * T.P, m * 4 * (size_t)T.P);
+        // lam | state | indices are contiguous when m == cap; copy the three pieces (a single configuration: 3 small copies)
+        if (lam) BCP_CUDA(cudaMemcpyAsync(d_lam, h_lam, m * 4, cudaMemcpyHostToDevice, st));
+        BCP_CUDA(cudaMemcpyAsync(d_state, h_state, m * 4, cudaMemcpyHostToDevice, st));
+        BCP_CUDA(cudaMemcpyAsync(d_idx, h_idx, m * 4 * (size_t)T.P, cudaMemcpyHostToDevice, st));
+        if (T.pf.q >= 0) BCP_CUDA(launch_energy_pf(T, (long long)m, lam ? d_lam : nullptr, d_state, d_idx, d_out, 0, st));
+        else neglogp_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(T, (long long)m, lam ? d_lam : nullptr, d_state, d_idx, d_out);
         BCP_LAUNCHED(1);
-        STEP(cudaGetLastError());
-        STEP(cudaMemcpy(energy_out, d_out, n * 8, cudaMemcpyDeviceToHost));
-#undef STEP
-    } while (0);
-    cudaFree(d_lam); cudaFree(d_state); cudaFree(d_idx); cudaFree(d_out);
-    return rc;
+        BCP_CUDA(cudaGetLastError());
+        BCP_CUDA(cudaMemcpyAsync(h_out, d_out, m * 8, cudaMemcpyDeviceToHost, st));
+        BCP_CUDA(cudaStreamSynchronize(st));
+        memcpy(energy_out + i0, h_out, m * 8);
+    }
+    return BCP_OK;
 }

@@ -26,14 +26,18 @@ class _DevArray(object):
                                          "version": 2, "strides": None}
 
 
-def device_histograms(block):
-    """torch int64 views [n_groups][S] and [n_groups][param_bins] of a ChainBlock's device histograms."""
+def device_histograms(block, fused=False):
+    """torch int64 views [n_groups][S] and [n_groups][param_bins] of a ChainBlock's device histograms; fused=True
+    returns additionally the flat view over both (they are one block in HBM: one all-reduce sums both)."""
     import torch
     p_sc, p_pc = block.device_hist_ptrs()
     T = block.tables
-    sc = torch.as_tensor(_DevArray(p_sc, (block.n_groups, T.n_states), "<i8"), device="cuda:%d" % T.device)
-    pc = torch.as_tensor(_DevArray(p_pc, (block.n_groups, T.param_bins), "<i8"), device="cuda:%d" % T.device)
-    return sc, pc
+    n_sc, n_pc = block.n_groups * T.n_states, block.n_groups * T.param_bins
+    assert p_pc == p_sc + 8 * n_sc
+    flat = torch.as_tensor(_DevArray(p_sc, (n_sc + n_pc,), "<i8"), device="cuda:%d" % T.device)
+    sc = flat[:n_sc].view(block.n_groups, T.n_states)
+    pc = flat[n_sc:].view(block.n_groups, T.param_bins)
+    return (sc, pc, flat) if fused else (sc, pc)
 
 
 def all_reduce_histograms(state_counts, param_counts, group=None):

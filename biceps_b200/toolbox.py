@@ -46,15 +46,10 @@ def sort_data(dataFiles):
 
 
 def get_files(path):
-    """Globbed files in natural (numeric-aware) order (toolbox.py:66-80)."""
-    def key(s):
-        out = []
-        for p in re.split(r"(\d+(?:\.\d+)?)", s):
-            if p == "":
-                continue
-            out.append((0, float(p), "") if re.fullmatch(r"\d+(?:\.\d+)?", p) else (1, 0.0, p))
-        return out
-    return sorted(glob.glob(path), key=key)
+    """Globbed files in natsort's default order (toolbox.py:66-80 calls natsorted(glob)): the name is split into
+    text and UNSIGNED INTEGER runs -- a decimal point is text -- so `lambda0.5` sorts before `lambda0.25`
+    (5 < 25), exactly like the reference; Analysis takes the order of its lambdas from this list."""
+    return sorted(glob.glob(path), key=_natural_key)
 
 
 def list_res(input_data):
@@ -70,34 +65,26 @@ def list_extensions(input_data):
     return [res.split("_")[-1] for res in list_res(input_data)]
 
 
+def _file_or_array(x, what, loader):
+    """A path is loaded with `loader`; a list / ndarray passes through; anything else is a TypeError
+    (same acceptance rule as the reference's check_* helpers, toolbox.py:152-176)."""
+    if isinstance(x, str):
+        return loader(x)
+    if isinstance(x, (list, np.ndarray)):
+        return x
+    raise TypeError("%s: expected a file path (str) or a list / numpy array, got %s" % (what, type(x).__name__))
+
+
 def check_indices(indices):
-    """toolbox.py:152-159"""
-    if type(indices) == str:
-        indices = np.loadtxt(indices)
-    elif (type(indices) != np.ndarray) and (type(indices) != list):
-        raise TypeError(f"Requires a path to a file (str) OR data as \
-                list/np.ndarray object. You provides {type(indices)}.")
-    return np.array(indices).astype(int)
+    return np.array(_file_or_array(indices, "indices", np.loadtxt)).astype(int)
 
 
 def check_exp_data(exp_data):
-    """toolbox.py:161-167"""
-    if type(exp_data) == str:
-        exp_data = np.loadtxt(exp_data)
-    elif (type(exp_data) != np.ndarray) and (type(exp_data) != list):
-        raise TypeError(f"Requires a path to a file (str) OR data as \
-                list/np.ndarray object. You provides {type(exp_data)}.")
-    return exp_data
+    return _file_or_array(exp_data, "exp_data", np.loadtxt)
 
 
 def check_model_data(model_data):
-    """toolbox.py:169-176"""
-    if type(model_data) == str:
-        model_data = get_files(model_data)
-    elif (type(model_data) != np.ndarray) and (type(model_data) != list):
-        raise TypeError(f"Requires a path to glob files (str) OR data as \
-                list/np.ndarray object. You provides {type(model_data)}.")
-    return model_data
+    return _file_or_array(model_data, "model_data", get_files)
 
 
 def get_state_populations(file):

@@ -181,7 +181,9 @@ int bcp_chains_fetch(bcp_chains* c, bcp_sample_out* out);
  * does when sample() is called a second time (indices jump back to int(len/2) while state and E
  * persist, PosteriorSampler.py:271-278, 294). */
 int bcp_chains_set_state(bcp_chains* c, const int32_t* state, const int32_t* indices, const double* energy);
-/* device views of the cumulative histograms, for an NCCL all-reduce by the caller */
+/* device views of the cumulative histograms, for an NCCL all-reduce by the caller; the two arrays are ONE block
+ * (d_param_counts == d_state_counts + n_groups * n_states), so one collective over n_groups * (n_states +
+ * bcp_param_bins) int64 sums both (replaces the per-process histograms of PosteriorSampler.py:339-358) */
 int bcp_chains_device_hist(bcp_chains* c, int64_t** d_state_counts, int64_t** d_param_counts);
 /* elapsed device time (ms, CUDA events on the launch stream) of the last sample launch */
 int bcp_chains_last_kernel_ms(bcp_chains* c, float* ms, int32_t* n_launches);

@@ -12,7 +12,7 @@ left-to-right fp64 summation order of the reference's Python loops is preserved.
   sigma / gamma grids                       /root/reference/biceps/Restraint.py:235-241, 502-507
   equivalency-group weights                 /root/reference/biceps/Restraint.py:418-442, 527-549
 
-Pinned by tests/test_precompute_oracle.py against tables the live reference produced
+Pinned by tests/test_oracle_golden.py and tests/test_oracle_vs_reference.py against tables the live reference produced
 (tests/golden/cineromycin_tables.npz, apomyoglobin_tables.npz).
 """
 import math

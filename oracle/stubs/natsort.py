@@ -1,15 +1,11 @@
-"""Import shim: numeric-aware sort standing in for natsort.natsorted."""
+"""Import shim standing in for natsort.natsorted with natsort's DEFAULT algorithm (ns.INT, unsigned): a name is
+split into text and unsigned-integer runs, a decimal point is text ('lambda0.5' < 'lambda0.25' because 5 < 25)."""
 import re
 
-_tok = re.compile(r'(\d+(?:\.\d+)?)')
 
 def _key(s):
-    out = []
-    for p in _tok.split(str(s)):
-        if p == '':
-            continue
-        out.append((0, float(p), '') if _tok.fullmatch(p) else (1, 0.0, p))
-    return out
+    return [int(p) if i % 2 else p for i, p in enumerate(re.split(r'(\d+)', str(s)))]
+
 
 def natsorted(seq):
     return sorted(seq, key=_key)

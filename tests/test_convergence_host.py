@@ -32,13 +32,3 @@ def test_exponential_fit_recovers_tau():
     y2 = 0.7 * np.exp(-x / 80.0) + 0.3 * np.exp(-x / 5.0)
     fit2, tau2 = BC.exponential_fit(y2, exp_function="double", v0=[0.0, 0.8, 0.2, 60.0, 8.0])
     assert abs(tau2 - 80.0) < 1e-4
-
-
-def test_multiprocess_decorator_runs_every_item_in_order():
-    import biceps_b200 as biceps
-    seen = []
-
-    @biceps.multiprocess(iterable=[0.0, 0.5, 1.0])
-    def run(lam):
-        seen.append(lam)
-    assert seen == [0.0, 0.5, 1.0] and run is None

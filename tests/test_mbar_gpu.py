@@ -125,3 +125,62 @@ def test_independent_runs_agree_with_the_reference_tutorial_score():
     assert float(np.sum(p[m] * np.log(p[m] / q[m]))) < 1e-3
     # the most populated states are the reference's
     assert list(np.argsort(-p)[:5]) == list(np.argsort(-z["populations"][:, 1])[:5])
+
+
+def test_sample_shards_through_the_pass_entry_equal_the_single_solve():
+    """The multi-GPU building block: two shards of the samples through bcp_mbar_pass_dev, their s / M summed
+    (what the NCCL all-reduce does, Analysis.py:192-223 over shards) == one bcp_mbar over everything
+    (f to 1e-12, theta to 1e-10); and distributed.mbar_solve over the shards converges to the same f."""
+    import ctypes as C
+    import torch
+    from biceps_b200 import _cabi as A, distributed, mbar
+    lib = A.lib()
+    K, n = 11, 6000
+    rng = np.random.default_rng(5)
+    kspring = np.linspace(1.0, 3.0, K)
+    N_k = np.array([n + 13 * k for k in range(K)], dtype=np.int64)
+    x = np.concatenate([rng.normal(0.1 * k, 1 / np.sqrt(ks), m) for k, (ks, m) in enumerate(zip(kspring, N_k))])
+    u_kn = np.ascontiguousarray(0.5 * kspring[:, None] * (x[None, :] - 0.1 * np.arange(K)[:, None]) ** 2)
+    N = u_kn.shape[1]
+    want = mbar.mbar(u_kn, N_k)
+    cut = N // 3 + 7                                        # ragged shards, cutting through a run
+    shards = [torch.from_numpy(np.ascontiguousarray(u_kn[:, :cut])).cuda(), torch.from_numpy(np.ascontiguousarray(u_kn[:, cut:])).cuda()]
+
+    def pass_all(f, hess):
+        s = np.zeros(K); Mm = np.zeros((K, K))
+        for sh in shards:
+            si = np.zeros(K); Mi = np.zeros((K, K))
+            A.check(lib.bcp_mbar_pass_dev(C.c_void_p(sh.data_ptr()), sh.shape[1], K, A.i64ptr(N_k), A.dptr(A.f64(f)), int(hess), 0,
+                                          C.c_void_p(0), A.dptr(si), A.dptr(Mi)), "pass")
+            s += si; Mm += Mi
+        return s, Mm
+
+    s, Mm = pass_all(want["f"], True)
+    assert np.allclose(s, 1.0, atol=1e-10)                  # fixed point of the MBAR equations at the single-GPU solution
+    assert np.allclose(Mm, want["theta"], rtol=1e-10, atol=1e-14)
+    f, theta, it = distributed.mbar_solve(pass_all, N_k, reduce=False)
+    assert np.max(np.abs(f - want["f"])) < 1e-12 and it < 20
+    assert np.allclose(theta, want["theta"], rtol=1e-10, atol=1e-14)
+
+
+def test_score_chains_of_one_block_equals_bcp_chains_score():
+    """distributed.score_chains (u_kn shard on the device + pass entry + weighted histograms, no collective for a
+    single block) against bcp_chains_score on the same snapshots."""
+    from biceps_b200 import distributed, engine, synthetic
+    from oracle import precompute_oracle as PO
+    ens = synthetic.make_ensemble("C2", seed=4, n_states=60, n_lambda=3)
+    tabs = PO.build_tables(ens["energies"], ens["lambdas"], ens["restraints"], exact_pow=False)
+    T = engine.DeviceTables(tabs)
+    n = 3 * 5 + 2
+    lam = (np.arange(n) % 3).astype(np.int32)
+    blk = T.chains(n, 11, chain_lambda=lam)
+    blk.launch(4000, burn=200, traj_every=10)
+    want = blk.score(populations=True)
+    got = distributed.score_chains(blk, populations=True, reduce=False)
+    assert np.array_equal(got["N_k"], want["N_k"])
+    assert np.max(np.abs(got["f"] - want["f"])) < 1e-12
+    assert np.allclose(got["theta"], want["theta"], rtol=1e-10, atol=1e-15)
+    assert np.allclose(got["P"], want["P"], rtol=1e-10, atol=1e-15)
+    ok = ~np.isnan(want["dP"])
+    assert np.array_equal(np.isnan(got["dP"]), np.isnan(want["dP"]))
+    assert np.allclose(got["dP"][ok], want["dP"][ok], rtol=1e-8)

@@ -51,7 +51,7 @@ def test_errors_like_the_reference(tmp_path):
     p = Preparation(nstates=S, outdir=str(tmp_path))
     with pytest.raises(ValueError, match="does not match the number of restraints"):
         p.prepare_noe(x["exp"][:-1], x["noe"], x["noe_ind"])
-    with pytest.raises(TypeError, match="Requires a path"):
+    with pytest.raises(TypeError, match="expected a file path"):
         p.prepare_noe(x["exp"], x["noe"], 5)
 
 
@@ -100,3 +100,19 @@ def test_identical_to_the_reference_files(tmp_path):
     for f in names:
         a, b = pd.read_pickle(tmp_path / "ref" / f), pd.read_pickle(tmp_path / "mine" / f)
         assert list(a.columns) == list(b.columns) and (a.dtypes == b.dtypes).all() and a.equals(b), f
+
+
+def test_get_files_uses_natsorts_integer_order(tmp_path):
+    """natsort's default algorithm splits on unsigned integers (a decimal point is text): the reference's Analysis
+    therefore orders lambdas 0.0, 0.5, 0.25, 0.75, 1.0 (toolbox.py:66-80, Analysis.py:112-116); same here, and the
+    import shim used to run the live reference does the same."""
+    import biceps_b200 as biceps
+    from oracle.stubs import natsort
+    names = ["traj_lambda%s.npz" % x for x in ("0.75", "1.00", "0.25", "0.00", "0.5", "10.0", "2.0")]
+    for nm in names:
+        (tmp_path / nm).write_text("")
+    got = [os.path.basename(f) for f in biceps.toolbox.get_files(str(tmp_path / "traj_lambda*.npz"))]
+    want = ["traj_lambda0.00.npz", "traj_lambda0.5.npz", "traj_lambda0.25.npz", "traj_lambda0.75.npz",
+            "traj_lambda1.00.npz", "traj_lambda2.0.npz", "traj_lambda10.0.npz"]
+    assert got == want
+    assert [os.path.basename(f) for f in natsort.natsorted(str(tmp_path / nm) for nm in names)] == want
