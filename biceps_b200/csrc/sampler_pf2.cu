@@ -25,8 +25,10 @@ __device__ __forceinline__ int p2wrap(int v, int n) {      // v in [-1, n]
     return v < 0 ? v + n : (v >= n ? v - n : v);
 }
 
+// resident CTAs per SM asked of ptxas: 4 (128 registers) while the chain's scalar restraints fit, 3 (168 registers) from
+// three scalar restraints on -- the reference's apomyoglobin shape (cs_H, cs_Ca, cs_N + PF) spilled 40-176 bytes at 128
 #ifndef PF2_MIN_BLOCKS
-#define PF2_MIN_BLOCKS 4
+#define PF2_MIN_BLOCKS(R) ((R) <= 2 ? 4 : 3)
 #endif
 
 struct Pf2Prop {            // proposal of one step, decoded from its Philox block (warp-uniform)
@@ -38,7 +40,7 @@ struct Pf2Prop {            // proposal of one step, decoded from its Philox blo
 };
 
 template <int R, int NJ>
-__global__ void __launch_bounds__(128, PF2_MIN_BLOCKS)
+__global__ void __launch_bounds__(128, PF2_MIN_BLOCKS(R))
 mcmc_pf2_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                 const __grid_constant__ LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -54,12 +54,12 @@ __device__ __forceinline__ double div_markstein(double a, double b, double y) {
 
 __device__ __forceinline__ double lds64(uint32_t addr) {
     double v;
-    SPEC_ASM("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    SPEC_ASM("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
     double2 v;
-    SPEC_ASM("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    SPEC_ASM("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, double2 v) {
