@@ -8,9 +8,14 @@
 //   compute_logZ                              /root/reference/biceps/PosteriorSampler.py:64-71
 //
 // All kernels are HBM-bound streaming reductions over model[S][J] (fp64, row-major):
-//   row kernels   : L lanes per state row (L = 4..32 chosen from J), 16-byte double2 loads,
-//                   shuffle reduction, one result (or G results for the gamma grid) per row;
-//   column kernels: deterministic two-stage reduction (row-chunk partials, then a fixed-order sum).
+//   row kernel    : L lanes per state row (L = 4..32 chosen from J), 16-byte double2 loads, shuffle reduction, one
+//                   result (or G results for the gamma grid) per row, and in the SAME sweep the row's
+//                   reference-potential sum;
+//   column kernels: deterministic two-stage reduction (row-chunk partials, then a fixed-order combination); the
+//                   Gaussian reference's mean and variance come out of ONE sweep (shifted sums per chunk, chunks
+//                   combined with the pairwise-variance formula).
+// An ensemble's restraint therefore costs at most two passes over model[S][J] (was 3 for the exponential and 4 for the
+// Gaussian reference).
 // The gamma-grid SSE uses the moment expansion  sum_j w (g e - m)^2 = g^2 Swee - 2 g Swem + Swmm
 // (log-normal: d = ln(m/e), sum_j w (d - ln g)^2 = Swdd - 2 ln g Swd + ln^2 g Sw), so the kernel
 // reads model once and writes sse[S][G] once instead of doing S*J*G fp64 operations.
@@ -32,14 +37,21 @@ enum RowMode { ROW_SSE = 0, ROW_LIN = 1, ROW_GAMMA = 2, ROW_GAMMA_LOG = 3 };
 // out[i] = c0 + sum_j a[j] * model[i][j]                     (ROW_LIN)
 // out[i][g] = gam2[g]*Swee - 2*gam1[g]*Swem_i + Swmm_i       (ROW_GAMMA;   a = w, b = exp)
 // out[i][g] = Swdd_i - 2*gam1[g]*Swd_i + gam2[g]*Sw          (ROW_GAMMA_LOG; gam1 = ln g, gam2 = ln^2 g)
-template <int MODE>
+// REF fuses the reference-potential sum of the same row into the sweep (one pass over model for both tables):
+//   REF_LIN : ref_out[i] = rc0 + sum_j ra[j] * model[i][j]                   (exponential reference)
+//   REF_SQ  : ref_out[i] = rc0 + sum_j ra[j] * (model[i][j] - rb[j])^2       (Gaussian reference)
+enum RefMode { REF_NONE = 0, REF_LIN = 1, REF_SQ = 2 };
+template <int MODE, int REF>
 __global__ void __launch_bounds__(256)
 row_kernel(const double* __restrict__ model, const double* __restrict__ a, const double* __restrict__ b,
            const double* __restrict__ c0_ptr, int S, int J, int L, const double* __restrict__ gam1,
-           const double* __restrict__ gam2, int G, const double* __restrict__ see_ptr, double* __restrict__ out) {
+           const double* __restrict__ gam2, int G, const double* __restrict__ see_ptr, double* __restrict__ out,
+           const double* __restrict__ ra, const double* __restrict__ rb, const double* __restrict__ rc0_ptr,
+           double* __restrict__ ref_out) {
     // scalars produced by the preceding tiny kernels stay on the device (no host round trip)
     const double c0 = c0_ptr ? *c0_ptr : 0.0;
     const double see = see_ptr ? *see_ptr : 0.0;
+    const double rc0 = (REF != REF_NONE && rc0_ptr) ? *rc0_ptr : 0.0;
     const int lane = threadIdx.x & 31;
     const int sub = lane / L;                 // which row of this warp's pass
     const int l = lane - sub * L;
@@ -49,7 +61,7 @@ row_kernel(const double* __restrict__ model, const double* __restrict__ a, const
     const bool vec2 = ((J & 1) == 0);         // rows stay 16-byte aligned only for even J
     for (long long base = (long long)warp * rows_per_warp; base < S; base += (long long)n_warps * rows_per_warp) {
         const long long i = base + sub;
-        double s0 = 0.0, s1 = 0.0;
+        double s0 = 0.0, s1 = 0.0, sr = 0.0;
         if (i < S) {
             const double* row = model + (size_t)i * J;
             if (vec2) {
@@ -59,6 +71,15 @@ row_kernel(const double* __restrict__ model, const double* __restrict__ a, const
                 for (int j = l; j < (J >> 1); j += L) {
                     const double2 m = __ldcs(row2 + j);       // streamed once: evict-first
                     const double2 av = __ldg(a2 + j);
+                    if (REF == REF_LIN) {
+                        const double2 rv = __ldg(reinterpret_cast<const double2*>(ra) + j);
+                        sr += rv.x * m.x + rv.y * m.y;
+                    } else if (REF == REF_SQ) {
+                        const double2 rv = __ldg(reinterpret_cast<const double2*>(ra) + j);
+                        const double2 cv = __ldg(reinterpret_cast<const double2*>(rb) + j);
+                        const double f0 = m.x - cv.x, f1 = m.y - cv.y;
+                        sr += rv.x * f0 * f0 + rv.y * f1 * f1;
+                    }
                     if (MODE == ROW_LIN) {
                         s0 += av.x * m.x + av.y * m.y;
                     } else {
@@ -80,6 +101,8 @@ row_kernel(const double* __restrict__ model, const double* __restrict__ a, const
                 for (int j = l; j < J; j += L) {
                     const double m = __ldcs(row + j);
                     const double av = __ldg(a + j);
+                    if (REF == REF_LIN) sr += __ldg(ra + j) * m;
+                    else if (REF == REF_SQ) { const double f0 = m - __ldg(rb + j); sr += __ldg(ra + j) * f0 * f0; }
                     if (MODE == ROW_LIN) {
                         s0 += av * m;
                     } else {
@@ -101,6 +124,10 @@ row_kernel(const double* __restrict__ model, const double* __restrict__ a, const
         }
         s0 = group_sum(s0, L);
         if (MODE >= ROW_GAMMA) s1 = group_sum(s1, L);
+        if (REF != REF_NONE) {
+            sr = group_sum(sr, L);
+            if (i < S && l == 0) ref_out[i] = rc0 + sr;
+        }
         if (i < S) {
             if (MODE == ROW_SSE || MODE == ROW_LIN) {
                 if (l == 0) out[i] = c0 + s0;
@@ -115,46 +142,66 @@ row_kernel(const double* __restrict__ model, const double* __restrict__ a, const
     }
 }
 
-// stage 1 of the column reduction: partial[chunk][j] = sum over the chunk's rows of f(model[i][j]),
-// f = identity (center == nullptr) or (x - center[j])^2.  Thread = one column, coalesced over j.
+// Column statistics in ONE sweep over model (stage 1: per row-chunk partials, thread = one column, coalesced over j):
+//   psum[chunk][j] = sum of the chunk's rows;   VAR: pm2[chunk][j] = sum of squared deviations from the chunk's own
+//   mean, accumulated against a shift (the chunk's first row) so that nothing cancels.
+template <bool VAR>
 __global__ void __launch_bounds__(256)
-col_partial_kernel(const double* __restrict__ model, const double* __restrict__ center, int S, int J,
-                   int rows_per_chunk, double* __restrict__ partial) {
+col_stats_kernel(const double* __restrict__ model, int S, int J, int rows_per_chunk, double* __restrict__ psum,
+                 double* __restrict__ pm2) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = blockIdx.y;
     if (j >= J) return;
     const long long r0 = (long long)chunk * rows_per_chunk;
     const long long r1 = r0 + rows_per_chunk < S ? r0 + rows_per_chunk : S;
-    const double c = center ? center[j] : 0.0;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    const double shift = VAR ? model[(size_t)r0 * J + j] : 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
     long long i = r0;
-    for (; i + 3 < r1; i += 4) {                   // 4 independent loads in flight per thread
-        double v0 = model[(size_t)i * J + j], v1 = model[(size_t)(i + 1) * J + j];
-        double v2 = model[(size_t)(i + 2) * J + j], v3 = model[(size_t)(i + 3) * J + j];
-        if (center) { v0 -= c; v1 -= c; v2 -= c; v3 -= c; v0 *= v0; v1 *= v1; v2 *= v2; v3 *= v3; }
-        acc0 += v0; acc1 += v1; acc2 += v2; acc3 += v3;
+    const double* __restrict__ col = model + j;
+    for (; i + 7 < r1; i += 8) {                   // 8 independent loads in flight per thread (64 B; ~48 KB per SM)
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = col[(size_t)(i + k) * J];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] -= shift;
+        a0 += v[0] + v[4]; a1 += v[1] + v[5]; a2 += v[2] + v[6]; a3 += v[3] + v[7];
+        if (VAR) {
+            q0 += v[0] * v[0] + v[4] * v[4]; q1 += v[1] * v[1] + v[5] * v[5];
+            q2 += v[2] * v[2] + v[6] * v[6]; q3 += v[3] * v[3] + v[7] * v[7];
+        }
     }
     for (; i < r1; ++i) {
-        double v = model[(size_t)i * J + j];
-        if (center) { v -= c; v *= v; }
-        acc0 += v;
+        const double v = col[(size_t)i * J] - shift;
+        a0 += v;
+        if (VAR) q0 += v * v;
     }
-    partial[(size_t)chunk * J + j] = (acc0 + acc1) + (acc2 + acc3);
+    const double n = (double)(r1 - r0);
+    const double sd = (a0 + a1) + (a2 + a3);       // sum of (x - shift)
+    psum[(size_t)chunk * J + j] = n * shift + sd;
+    if (VAR) pm2[(size_t)chunk * J + j] = ((q0 + q1) + (q2 + q3)) - sd * sd / n;
 }
 
-// stage 2: fixed-order sum over chunks, then the per-observable reference-potential parameters.
-//   kind 1 (exponential): p0[j] = beta_j = colsum/(S+1); coef[j] = w_j/beta_j; c0 += w_j ln beta_j
-//   kind 2 (gaussian) pass A: p0[j] = mean_j = colsum/S
-//   kind 3 (gaussian) pass B: p1[j] = sqrt(colsum/(S+1))
-__global__ void col_finish_kernel(const double* __restrict__ partial, int n_chunks, int S, int J, int kind,
-                                  double* __restrict__ p) {
+// stage 2: fixed-order combination of the chunks, then the per-observable reference-potential parameters.
+//   kind 1 (exponential): p0[j] = beta_j = colsum / (S + 1)
+//   kind 2 (gaussian)   : p0[j] = mean_j = colsum / S;  p1[j] = sqrt(M2_j / (S + 1)) with the chunks' M2 combined by
+//                         M2 = sum_c M2_c + sum_c n_c (mean_c - mean)^2  (Chan et al.; PosteriorSampler.py:128-137)
+__global__ void col_finish_kernel(const double* __restrict__ psum, const double* __restrict__ pm2, int n_chunks,
+                                  int rows_per_chunk, int S, int J, int kind, double* __restrict__ p0, double* __restrict__ p1) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= J) return;
     double s = 0.0;
-    for (int c = 0; c < n_chunks; ++c) s += partial[(size_t)c * J + j];
-    if (kind == 1) p[j] = s / ((double)S + 1.0);
-    else if (kind == 2) p[j] = s / (double)S;
-    else p[j] = sqrt(s / ((double)S + 1.0));
+    for (int c = 0; c < n_chunks; ++c) s += psum[(size_t)c * J + j];
+    if (kind == 1) { p0[j] = s / ((double)S + 1.0); return; }
+    const double mean = s / (double)S;
+    double m2 = 0.0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const long long r0 = (long long)c * rows_per_chunk;
+        const double n = (double)((r0 + rows_per_chunk < S ? r0 + rows_per_chunk : S) - r0);
+        const double dm = psum[(size_t)c * J + j] / n - mean;
+        m2 += pm2[(size_t)c * J + j] + n * dm * dm;
+    }
+    p0[j] = mean;
+    p1[j] = sqrt(m2 / ((double)S + 1.0));
 }
 
 // single small block: turns per-observable parameters into the row-kernel coefficient vectors.
@@ -256,21 +303,8 @@ static int precompute_device(const bcp_obs& o, int S, int device, cudaStream_t s
     const int grid = (int)(blocks < cap ? blocks : cap);
     int launches = 0;
 
-    if (o.kind == BCP_KIND_SCALAR) {
-        row_kernel<ROW_SSE><<<grid, 256, 0, st>>>(o.model, o.weight, o.exp, nullptr, S, J, L, nullptr, nullptr, 1, nullptr, d_sse);
-        ++launches;
-    } else {
-        double *g1, *g2, *see;
-        BCP_CUDA(scr.get(&g1, o.n_gamma)); BCP_CUDA(scr.get(&g2, o.n_gamma)); BCP_CUDA(scr.get(&see, 1));
-        gamma_prep_kernel<<<1, 256, 0, st>>>(J, o.weight, o.exp, o.log_normal, o.n_gamma, o.gamma, g1, g2, see);
-        if (o.log_normal)
-            row_kernel<ROW_GAMMA_LOG><<<grid, 256, 0, st>>>(o.model, o.weight, o.exp, nullptr, S, J, L, g1, g2, o.n_gamma, see, d_sse);
-        else
-            row_kernel<ROW_GAMMA><<<grid, 256, 0, st>>>(o.model, o.weight, o.exp, nullptr, S, J, L, g1, g2, o.n_gamma, see, d_sse);
-        launches += 2;
-    }
-    BCP_CUDA(cudaGetLastError());
-
+    // reference potential first: column statistics in one sweep, then the coefficient vectors (tiny kernels)
+    double *coef = nullptr, *c0 = nullptr;
     if (o.ref_kind != 0) {
         BCP_REQUIRE(d_refsum && d_par0 && (o.ref_kind == 1 || d_par1), "bcp_precompute: reference potential needs refsum/par outputs");
         // chunking: enough CTAs to fill the machine, chunks of >= 64 rows
@@ -280,25 +314,39 @@ static int precompute_device(const bcp_obs& o, int S, int device, cudaStream_t s
         if (n_chunks < 1) n_chunks = 1;
         const int rows_per_chunk = (S + n_chunks - 1) / n_chunks;
         n_chunks = (S + rows_per_chunk - 1) / rows_per_chunk;
-        double *partial, *coef, *c0;
-        BCP_CUDA(scr.get(&partial, (size_t)n_chunks * J)); BCP_CUDA(scr.get(&coef, J)); BCP_CUDA(scr.get(&c0, 1));
+        double *psum, *pm2 = nullptr;
+        BCP_CUDA(scr.get(&psum, (size_t)n_chunks * J)); BCP_CUDA(scr.get(&coef, J)); BCP_CUDA(scr.get(&c0, 1));
         dim3 cgrid(col_blocks, n_chunks);
-        col_partial_kernel<<<cgrid, 256, 0, st>>>(o.model, nullptr, S, J, rows_per_chunk, partial);
-        col_finish_kernel<<<col_blocks, 256, 0, st>>>(partial, n_chunks, S, J, o.ref_kind == 1 ? 1 : 2, d_par0);
-        launches += 2;
         if (o.ref_kind == 2) {
-            col_partial_kernel<<<cgrid, 256, 0, st>>>(o.model, d_par0, S, J, rows_per_chunk, partial);
-            col_finish_kernel<<<col_blocks, 256, 0, st>>>(partial, n_chunks, S, J, 3, d_par1);
-            launches += 2;
+            BCP_CUDA(scr.get(&pm2, (size_t)n_chunks * J));
+            col_stats_kernel<true><<<cgrid, 256, 0, st>>>(o.model, S, J, rows_per_chunk, psum, pm2);
+        } else {
+            col_stats_kernel<false><<<cgrid, 256, 0, st>>>(o.model, S, J, rows_per_chunk, psum, nullptr);
         }
+        col_finish_kernel<<<col_blocks, 256, 0, st>>>(psum, pm2, n_chunks, rows_per_chunk, S, J, o.ref_kind, d_par0, d_par1);
         ref_coef_kernel<<<1, 256, 0, st>>>(o.ref_kind, J, o.weight, d_par0, d_par1, o.use_global_ref_sigma, coef, c0);
-        if (o.ref_kind == 1)
-            row_kernel<ROW_LIN><<<grid, 256, 0, st>>>(o.model, coef, nullptr, c0, S, J, L, nullptr, nullptr, 1, nullptr, d_refsum);
-        else
-            row_kernel<ROW_SSE><<<grid, 256, 0, st>>>(o.model, coef, d_par0, c0, S, J, L, nullptr, nullptr, 1, nullptr, d_refsum);
-        launches += 2;
+        launches += 3;
         BCP_CUDA(cudaGetLastError());
     }
+    // one sweep over model for the SSE table AND the reference-potential sums
+    double *g1 = nullptr, *g2 = nullptr, *see = nullptr;
+    if (o.kind != BCP_KIND_SCALAR) {
+        BCP_CUDA(scr.get(&g1, o.n_gamma)); BCP_CUDA(scr.get(&g2, o.n_gamma)); BCP_CUDA(scr.get(&see, 1));
+        gamma_prep_kernel<<<1, 256, 0, st>>>(J, o.weight, o.exp, o.log_normal, o.n_gamma, o.gamma, g1, g2, see);
+        ++launches;
+    }
+    const int G = o.kind == BCP_KIND_SCALAR ? 1 : o.n_gamma;
+#define BCP_ROW(MODE, REF) row_kernel<MODE, REF><<<grid, 256, 0, st>>>(o.model, o.weight, o.exp, nullptr, S, J, L, g1, g2, G, see, d_sse, \
+                                                                      coef, d_par0, c0, d_refsum)
+#define BCP_ROW_REF(MODE) do { if (o.ref_kind == 0) BCP_ROW(MODE, REF_NONE); else if (o.ref_kind == 1) BCP_ROW(MODE, REF_LIN); \
+                               else BCP_ROW(MODE, REF_SQ); } while (0)
+    if (o.kind == BCP_KIND_SCALAR) BCP_ROW_REF(ROW_SSE);
+    else if (o.log_normal) BCP_ROW_REF(ROW_GAMMA_LOG);
+    else BCP_ROW_REF(ROW_GAMMA);
+#undef BCP_ROW_REF
+#undef BCP_ROW
+    ++launches;
+    BCP_CUDA(cudaGetLastError());
     BCP_LAUNCHED(launches);
     return BCP_OK;
 }

@@ -41,6 +41,14 @@
 
 namespace bcp {
 
+#ifndef SPEC_REGCACHE
+#define SPEC_REGCACHE 0            // 1: the words a lane's term depends on (sigma entry of its index, its record, the gamma value) are kept
+                                   // in registers and shared memory is read -- with predicated loads -- only by the lanes whose inputs
+                                   // change in the evaluated proposal: 4 warps per SM otherwise keep the SM's shared-memory pipe ~70 %
+                                   // busy (bank conflicts of 32 random addresses per load included), which is what stretches every
+                                   // dependent load of a step
+#endif
+
 
 template <int L, int R, bool HG, bool TRACE>
 __global__ void __launch_bounds__(256, SPEC_MINBLOCKS)
@@ -226,8 +234,13 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
             const bool out = (unsigned)(wi - 1) > 7u;        // wi +- 1 must stay inside the 10-wide window
             const int ia = nuis_n ? gm + 4 + k.g1 : (out ? 4 : wi);
             const uint32_t na = glane ? (nuis_n ? cur_row : slot + ly.slot_win) + 8u * (uint32_t)ia : recaddr;
+#if SPEC_PRED_GAMMA
+            numA = lds64_if(glane, na, numA);
+            numB = lds64_if(glane, na + (uint32_t)(8 * g0_), numB);
+#else
             numA = lds64(na);
             numB = lds64(na + (uint32_t)(glane ? 8 * g0_ : 0));
+#endif
             k.miss = glane && !nuis_n && out;
         }
         double Cn = Cst;
@@ -242,6 +255,94 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         k.xB = __dadd_rn(t, Cn);
         return k;
     };
+#if SPEC_REGCACHE
+    // register copies (valid inside fast batches; reloaded after every careful batch):
+    //   c_*  entry / record / gamma value of the committed indices,   p_*  of the committed indices shifted by the
+    //   pending step (d0, g0) -- the pending step's own evaluation loaded them one step earlier
+    double c_nl = 0.0, c_dv = 1.0, c_y = 1.0, c_sse = 0.0, c_ref = 0.0, c_num = 0.0;
+    double p_nl = 0.0, p_dv = 1.0, p_y = 1.0, p_num = 0.0;
+    double a_nl, a_dv, a_y, a_num, b_nl, b_dv, b_y, b_num;      // entries of the two candidates of the step being evaluated
+    auto reload_cache = [&](int d0_, int g0_) {
+        const uint32_t e0 = ent_base + (uint32_t)(SPEC_ENT_BYTES * sg), e1 = e0 + (uint32_t)(SPEC_ENT_BYTES * d0_);
+        c_nl = lds64(e0); c_dv = lds64(e0 + 8); c_y = lds64(e0 + 16);
+        p_nl = lds64(e1); p_dv = lds64(e1 + 8); p_y = lds64(e1 + 16);
+        const double2 rv = lds128(cur_rec);
+        c_sse = rv.x; c_ref = rv.y;
+        if (HG) {
+            c_num = glane ? lds64(cur_row + 8u * (uint32_t)(gm + 4)) : 0.0;
+            p_num = glane ? lds64(cur_row + 8u * (uint32_t)(gm + 4 + g0_)) : 0.0;
+        }
+    };
+    auto evaluate_rc = [&](uint32_t dn, uint32_t slot, int wofs, int d0_, int g0_) {
+        Cand k;
+        const bool nuis_n = (int)dn < 0;
+        k.own = (dn & own_mask) != 0u;
+        k.d1 = (int)((dn >> fsh) & 3u) - 1;
+        k.g1 = (int)((dn >> 16) & 3u) - 1;
+        // sigma entries: A at sg + d1, B at sg + d0 + d1; every case but "d != 0 and not the pending index" is in registers
+        const uint32_t eA = ent_base + (uint32_t)(SPEC_ENT_BYTES * (sg + k.d1));
+        const uint32_t eB = eA + (uint32_t)(SPEC_ENT_BYTES * d0_);
+        const bool ldA = k.d1 != 0;
+        const bool ldB = d0_ != 0 && k.d1 == d0_;                  // sg + 2 d0: the only B index that is neither A's, the pending nor the current one
+        a_nl = lds64_if(ldA, eA, c_nl); a_dv = lds64_if(ldA, eA + 8, c_dv); a_y = lds64_if(ldA, eA + 16, c_y);
+        b_nl = lds64_if(ldB, eB, a_nl); b_dv = lds64_if(ldB, eB + 8, a_dv); b_y = lds64_if(ldB, eB + 16, a_y);
+        if (d0_ != 0 && k.d1 == 0) { b_nl = p_nl; b_dv = p_dv; b_y = p_y; }             // B == the pending index
+        if (d0_ != 0 && k.d1 == -d0_) { b_nl = c_nl; b_dv = c_dv; b_y = c_y; }          // B == the current index
+        // record: the current state's (registers) or the proposed state's (slot)
+        double sse = c_sse, ref = c_ref;
+        {
+            double2 rv = make_double2(c_sse, c_ref);
+            rv = lds128_if(!nuis_n, slot + 16 * qr, rv);
+            sse = rv.x; ref = rv.y;
+        }
+        a_num = sse; b_num = sse;
+        k.miss = false;
+        if (HG) {
+            const int wi = wofs + pg;                        // window index of the current position (state move)
+            const bool out = (unsigned)(wi - 1) > 7u;        // wi +- 1 must stay inside the 10-wide window
+            const bool gl_n = glane && nuis_n, gl_s = glane && !nuis_n;
+            // nuisance proposal: values of the current row at gm + g1 (A) and gm + g0 + g1 (B)
+            const uint32_t rA = cur_row + 8u * (uint32_t)(gm + 4 + k.g1);
+            const bool ldgA = gl_n && k.g1 != 0;
+            const bool ldgB = gl_n && g0_ != 0 && k.g1 == g0_;
+            double nA = glane ? c_num : sse;
+            nA = lds64_if(ldgA, rA, nA);
+            double nB = nA;
+            nB = lds64_if(ldgB, rA + (uint32_t)(8 * g0_), nB);
+            if (gl_n && g0_ != 0 && k.g1 == 0) nB = p_num;
+            if (gl_n && g0_ != 0 && k.g1 == -g0_) nB = c_num;
+            // state-move proposal: the slot's window at the current gamma position (A) and shifted by g0 (B)
+            const uint32_t wA = slot + ly.slot_win + 8u * (uint32_t)(out ? 4 : wi);
+            nA = lds64_if(gl_s, wA, nA);
+            nB = gl_s ? nA : nB;
+            nB = lds64_if(gl_s && g0_ != 0, wA + (uint32_t)(8 * g0_), nB);
+            a_num = nA; b_num = nB;
+            k.miss = gl_s && out;
+        }
+        double Cn = Cst;
+        if (!nuis_n && q == 0) Cn = __dadd_rn(lds64(slot + ly.slot_c), logZ);
+        double t = __dadd_rn(a_nl, div_markstein(a_num, a_dv, a_y));
+        t = __dadd_rn(t, cnorm);
+        t = __dsub_rn(t, ref);
+        k.xA = __dadd_rn(t, Cn);
+        t = __dadd_rn(b_nl, div_markstein(b_num, b_dv, b_y));
+        t = __dadd_rn(t, cnorm);
+        t = __dsub_rn(t, ref);
+        k.xB = __dadd_rn(t, Cn);
+        return k;
+    };
+    // after the decision on the pending step: the committed copies follow an accepted move (state moves roll the batch
+    // back), the candidate whose history came true becomes the new pending copy.  nuis_n: the evaluated step is a nuisance move
+    auto advance_cache = [&](bool acc, bool nuis_n) {
+        c_nl = acc ? p_nl : c_nl; c_dv = acc ? p_dv : c_dv; c_y = acc ? p_y : c_y;
+        p_nl = acc ? b_nl : a_nl; p_dv = acc ? b_dv : a_dv; p_y = acc ? b_y : a_y;
+        if (HG) {
+            c_num = acc ? p_num : c_num;
+            // the pending copy of the gamma value only matters for a nuisance pending step (an accepted state move rolls back)
+            p_num = nuis_n ? (acc ? b_num : a_num) : c_num;
+        }
+    };
+#endif
     // the same on the committed state only; the gamma value of a proposed state (i2) is read from global memory
     auto evaluate_exact = [&](uint32_t dn, uint32_t slot, uint32_t i2) {
         const bool nuis_n = (int)dn < 0;
@@ -332,6 +433,9 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         x_prop = evaluate_exact(dw_s, slot_of(0, 0), bcast_u(gen[0][0].istate, 0));
     }
 
+#if SPEC_REGCACHE
+    bool cache_stale = true;
+#endif
     for (int s0 = 0; s0 < s_end; s0 += BL) {
         const int sb1 = sb0 + 1 == SpecCfg<L>::NBATCH ? 0 : sb0 + 1;         // slot batch of the next batch
         const int sb2 = sb0 + D >= SpecCfg<L>::NBATCH ? sb0 + D - SpecCfg<L>::NBATCH : sb0 + D;   // ... of the batch generated now
@@ -348,6 +452,12 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
         //      written); anything rare only raises a flag and the batch is then redone carefully -------
         bool careful = (unsigned)(next_ev - s0) < (unsigned)BL;         // a snapshot falls into it
         if (!careful) {
+#if SPEC_REGCACHE
+            if (cache_stale) {                                           // (warp-uniform) after a careful batch
+                reload_cache(d0, g0);
+                cache_stale = false;
+            }
+#endif
             const double sv_E = E, sv_x = x_prop;
             const int sv_sg = sg, sv_gm = gm, sv_pg = pg, sv_ssg = since_sg, sv_sgm = since_gm, sv_d0 = d0, sv_g0 = g0;
             const unsigned int sv_at = acc_total, sv_ao = acc_own;
@@ -373,7 +483,7 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 const int jn = nb ? 0 : j + 1;
                 const uint32_t dw_n = bcast_u(nb ? gen[1][0].dw : gen[0][jn / L].dw, jn % L);
                 const float lu_n = bcast_f(nb ? gen[1][0].lu : gen[0][jn / L].lu, jn % L);
-#if SPEC_EVAL_FIRST
+#if SPEC_EVAL_FIRST && !SPEC_REGCACHE
                 const Cand k = evaluate(dw_n, slot_of(nb ? sb1 : sb0, jn), nb ? wofs[1] : wofs[0], d0, g0);
 #endif
                 // (1) resolve step s: energy in the reference's summation order, accept in the log domain
@@ -385,12 +495,17 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
                 const bool acc = tt > SPEC_MARGIN;
                 const bool unsure = !acc && !(tt < -SPEC_MARGIN);        // guard band, also NaN
                 // (2) contributions to step s+1 under both outcomes of step s
-#if !SPEC_EVAL_FIRST
+#if SPEC_REGCACHE
+                const Cand k = evaluate_rc(dw_n, slot_of(nb ? sb1 : sb0, jn), nb ? wofs[1] : wofs[0], d0, g0);
+#elif !SPEC_EVAL_FIRST
                 const Cand k = evaluate(dw_n, slot_of(nb ? sb1 : sb0, jn), nb ? wofs[1] : wofs[0], d0, g0);
 #endif
                 rare = rare || unsure || (acc && (int)dw_s >= 0) || k.miss;
                 // (3) commit
                 commit(acc, s, En, ev_bin[j], ev_cnt[j]);
+#if SPEC_REGCACHE
+                advance_cache(acc, (int)dw_n < 0);
+#endif
                 x_prop = acc ? k.xB : k.xA;
                 dw_s = dw_n; lu_s = lu_n; d0 = k.d1; g0 = k.g1; own_s = k.own;
 #if SPEC_STEP_FENCE
@@ -410,6 +525,9 @@ mcmc_spec_kernel(const __grid_constant__ SamplerTables T, const __grid_constant_
 
         // ---- careful batch: step by step, every rare case handled exactly -----------------------------
         if (careful) {
+#if SPEC_REGCACHE
+            cache_stale = true;
+#endif
             // generating lane and block of batch position jj (compile-time select chain: no dynamic register index)
             auto g_dw = [&](int jj) { uint32_t v = gen[0][0].dw; _Pragma("unroll") for (int m = 1; m < NB; ++m) v = jj / L == m ? gen[0][m].dw : v; return v; };
             auto g_lu = [&](int jj) { float v = gen[0][0].lu; _Pragma("unroll") for (int m = 1; m < NB; ++m) v = jj / L == m ? gen[0][m].lu : v; return v; };

@@ -11,6 +11,10 @@ namespace bcp {
 #ifndef SPEC_EVAL_FIRST
 #define SPEC_EVAL_FIRST 0          // source order inside a step: candidates of step s+1 before / after resolving step s
 #endif
+#ifndef SPEC_PRED_GAMMA
+#define SPEC_PRED_GAMMA 0          // 1: only the gamma lane issues the two gamma-value loads (predicated LDS: the other lanes' dummy
+                                   // re-reads of their own record cost bank-conflict wavefronts on the SM's shared-memory pipe)
+#endif
 #ifndef SPEC_BL
 #define SPEC_BL(L) ((L) == 8 ? 8 : 4)     // steps per batch as a function of the lanes per chain
 #endif
@@ -55,6 +59,15 @@ __device__ __forceinline__ double div_markstein(double a, double b, double y) {
 __device__ __forceinline__ double lds64(uint32_t addr) {
     double v;
     SPEC_ASM("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+// v = on ? [addr] : v -- a predicated load: lanes with on == false generate no shared-memory traffic
+__device__ __forceinline__ double lds64_if(bool on, uint32_t addr, double v) {
+    SPEC_ASM("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p ld.shared.f64 %0, [%1];\n}" : "+d"(v) : "r"(addr), "r"((uint32_t)on));
+    return v;
+}
+__device__ __forceinline__ double2 lds128_if(bool on, uint32_t addr, double2 v) {
+    SPEC_ASM("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\n@p ld.shared.v2.f64 {%0, %1}, [%2];\n}" : "+d"(v.x), "+d"(v.y) : "r"(addr), "r"((uint32_t)on));
     return v;
 }
 __device__ __forceinline__ double2 lds128(uint32_t addr) {

@@ -94,3 +94,31 @@ def test_two_ranks_gloo(oracle_lib):
     f, W, it = M.mbar_solve(u_kn, np.full(K, m))
     assert np.allclose(got["f"], f, atol=1e-10)
     assert np.allclose(got["theta"], W.T @ W, rtol=1e-9)
+
+
+def test_finish_populations_matches_the_oracle():
+    """distributed.finish_populations (the arithmetic after the all-reduce of the weighted histograms P, Q) against
+    the numpy MBAR oracle's populations and their 'approximate' uncertainties, never-sampled states included."""
+    from biceps_b200 import distributed as D
+    from oracle import mbar_oracle as M
+    rng = np.random.default_rng(3)
+    K, m, S = 4, 800, 9
+    ks = np.linspace(1.0, 2.5, K)
+    x = np.concatenate([rng.normal(0, 1 / np.sqrt(k), m) for k in ks])
+    u_kn = 0.5 * ks[:, None] * x[None, :] ** 2
+    N_k = np.full(K, m)
+    states = (np.abs(x) * 3).astype(np.int64) % (S - 2)          # the last two states are never sampled
+    f, W, it = M.mbar_solve(u_kn, N_k)
+    Df, dDf, theta = M.free_energy_differences(f, W)
+    P_want, dP_want = M.populations(W, theta, states, S)
+    # what two ranks would hand to the all-reduce: P[K][S] = sum_n W_nl [s_n = i], Q = sum_n W_nl^2 [s_n = i]
+    P = np.zeros((K, S)); Q = np.zeros((K, S))
+    for half in (slice(0, 1500), slice(1500, None)):
+        for l in range(K):
+            np.add.at(P[l], states[half], W[half, l])
+            np.add.at(Q[l], states[half], W[half, l] ** 2)
+    pops, dpops = D.finish_populations(P, Q, theta)
+    assert np.allclose(pops, P_want, rtol=1e-12, atol=1e-15)
+    ok = ~np.isnan(dP_want)
+    assert np.array_equal(np.isnan(dpops), np.isnan(dP_want)) and not ok[-1].any()
+    assert np.allclose(dpops[ok], dP_want[ok], rtol=1e-9)
