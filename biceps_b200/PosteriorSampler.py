@@ -132,6 +132,11 @@ class PosteriorSampler(object):
         k = 0
         if getattr(self, "_columns", None) is None:
             raise RuntimeError("build_*_ref needs the raw observables: not available on an unpickled sampler")
+        if getattr(self, "_calls", 0) > 0:
+            # the rebuild replaces the device tables and with them the chains' state, energy and histograms, which the
+            # reference keeps across this call (PosteriorSampler.py:74-150 only touches the restraints)
+            raise RuntimeError("build_*_ref after sample(): rebuild the reference potentials before the first sample() "
+                               "call (or on a new PosteriorSampler)")
         for c in self._columns:
             if k == rest_index:
                 col = c

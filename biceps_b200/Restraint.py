@@ -566,6 +566,12 @@ Dictionary keys for {R.__name__} are any of: {possible_args}")
         for k, R0 in enumerate(self.ensemble[0]):
             objs = [s[k] for s in self.ensemble]
             w = R0.weights
+            # the tables take exp / weights / Ndof from state 0: the reference reads every state's own file
+            # (Restraint.py:344-353), so states whose experimental columns differ must not pass silently
+            for i, o in enumerate(objs):
+                if not (np.array_equal(np.asarray(o._exp), np.asarray(R0._exp)) and np.array_equal(np.asarray(o.weights), np.asarray(w))):
+                    raise ValueError("state %d: the experimental values / restraint_index groups of its %s file differ from "
+                                     "state 0's -- every state must carry the same experimental data" % (i, R0.extension))
             if R0.kind == "pfgrid":
                 col = dict(kind="pfgrid", name="pf", extension=R0.extension, ref=R0.ref, ndof=R0.Ndof, sigma=R0.allowed_sigma,
                            grids=R0._pf_grids(), prior=R0.pf_prior, exp=R0._exp, weight=w,

@@ -197,7 +197,7 @@ class ChainBlock(object):
         used = self.mt_consumed()
         rs.set_state(st0)
         if used:
-            rs._bit_generator.random_raw(used)
+            rs._bit_generator.random_raw(used, output=False)       # advance only
         np.random.set_state(rs.get_state())
         return o
 
