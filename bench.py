@@ -388,9 +388,17 @@ def run_ours(args, rank, world, local_rank):
             b2c.sync()
             ms2.append(b2c.last_kernel_ms()[0])
         b2c.close(); T2c.close()
+        rate2 = n2 * steps2 / (min(ms2) * 1e-3)
+        bps2 = bytes_per_chain_step(tabs2)
+        peak2, _ = measured_peak_hbm()
         c2 = {"workload": "C2: 1000 states, R=5 (cs_H, cs_Ca, cs_N, J, NOE), 8 lambdas x 1024 chains, 20000 steps",
-              "value": n2 * steps2 / (min(ms2) * 1e-3), "unit": "chain-steps/s",
-              "kernel": "auto-selected (speculative 8-lane kernel, two waves of 8-warp CTAs)"}
+              "value": rate2, "unit": "chain-steps/s",
+              "kernel": "auto-selected (speculative 8-lane kernel, two waves of 8-warp CTAs)",
+              "roofline": {"bound": "hbm", "achieved": rate2 * bps2 / 1e9, "peak": peak2, "unit": "GB/s",
+                           "frac": rate2 * bps2 / 1e9 / peak2, "algorithmic_bytes_per_chain_step": bps2, "traffic": None,
+                           "cycles_per_chain_step_per_warp": min(ms2) * 1e-3 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / steps2,
+                           "note": "tables L2-resident (2 MB); 2048 warps = 3.5 per SM sub-partition, 4 chains per warp: "
+                                   "issue-bound (DESIGN.md section 8 item 5), the HBM fraction is reported as required"}}
 
     # ---- C4 (BASELINE configs[3]): HDX protection factors on the 6-D grid, 1e5 states (1.3 GB of <N_c>/<N_h>
     #      counts in HBM), warp-per-chain kernel evaluating the term on the fly: the one HBM-bound sampler ----
@@ -496,12 +504,11 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "bcp::mcmc_spec_kernel<4,4,true> (auto-selected for <= 8192 chains)", "kernel_ms_per_launch": k_ms,
                 "cycles_per_chain_step": k_ms * 1e-3 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / N_MCMC,
-                "latency_floor_cycles_per_chain_step": 110,
-                "latency_floor_note": "a chain is serial: select -> 8 SHFL (26 cycles) -> 3+1 DADD (8.4 each) -> F2F/FADD/"
-                                      "FSETP for the accept, overlapped with the next candidate's LDS (31.5) + 5-op "
-                                      "division (40) + 4 DADD; measured latencies in profiles/r01_microbench.json. The "
-                                      "kernel issues 209 warp instructions per step at 0.40 IPC (profiles/"
-                                      "r01_mcmc_spec_4096.summary.txt)",
+                "cost_model_cycles_per_chain_step": 4.5 * 41 + 1.5 * 150,
+                "cost_model_note": "fits every Metropolis kernel variant measured (DESIGN.md section 4): one warp issues a "
+                                   "shared-memory / shuffle / cp.async instruction every ~4.5 cycles and any other every ~1.5; "
+                                   "the spec kernel executes 41 + 150 per step (profiles/r02_mcmc_spec_4096.lines.txt); the "
+                                   "dependency cycle alone would allow ~155 cycles (latencies: profiles/r01_microbench.json)",
                 "algorithmic_bytes_per_chain_step": bps, "peak_source": peak_src,
                 "note": "latency/issue-bound by construction (SURVEY 8d): the useful table words are L2-resident "
                         "gathers (measured L2 random-gather peak 2.9e11 8-B words/s, profiles/r01_microbench.json: "
