@@ -177,3 +177,27 @@ def test_pf_grid_reference_trajectory_bit_for_bit():
     assert np.array_equal(o["state_counts"][0] + 1, g["t_state_counts"])
     assert np.array_equal(o["param_counts"][0], g["t_sampled_parameters"])
     assert int(o["accepted"][0]) == int(g["t_accepted"]) and o["energy"][0] == g["t_final_E"]
+
+
+def test_pf_full_default_grid_reference_trajectory_bit_for_bit():
+    """The same on the reference's FULL default 6-D grid (20 x 26 x 50 x 7 x 8 x 1 = 1 456 000 cells, the grid of
+    BASELINE configs[3]): tests/golden/pf_full_grid.npz is the trajectory of the live reference (dense tables of
+    11.6 MB per state, MT19937 seed 11, tests/golden/make_golden_pf_full.py); here the term is evaluated on the
+    fly from the raw <N_c>/<N_h> counts.  761 of the 3000 steps are accepted, so the six grid indices, sigma and
+    the state all move."""
+    g = load_npz("pf_full_grid.npz")
+    grids = [g["grid%d" % k] for k in range(int(g["n_grids"]))]
+    assert [len(x) for x in grids] == [20, 26, 50, 7, 8, 1]
+    rt = dict(kind="pfgrid", name="pf", ref="exponential", ndof=float(g["ndof"]), sigma=g["sigma"], nlsig=g["nlsig"],
+              two_sig2=g["two_sig2"], cnorm=float(g["cnorm"]), grids=grids, prior=None,
+              pf=dict(Nc=g["Nc"], Nh=g["Nh"], exp=g["exp"], weight=g["weight"]), refsum=None, sse=None)
+    raw = dict(n_states=int(g["energy"].shape[0]), energy=g["energy"], logZ=float(g["logZ"]), restraints=[rt])
+    T, blk, o, _ = _run(raw, int(g["t_seed"]), int(g["t_nsteps"]), 0)
+    assert T.n_params == 7
+    assert np.array_equal(o["traj_energy"][:, 0].view(np.int64), g["t_E"].view(np.int64))
+    assert np.array_equal(o["traj_indices"][:, :, 0], g["t_indices"])
+    assert np.array_equal(o["traj_state"][:, 0], g["t_state"].reshape(-1))
+    assert np.array_equal(o["state_trace"][:, 0], g["t_state_trace"].reshape(-1))
+    assert np.array_equal(o["state_counts"][0] + 1, g["t_state_counts"])
+    assert np.array_equal(o["param_counts"][0], g["t_sampled_parameters"])
+    assert int(o["accepted"][0]) == int(g["t_accepted"]) == 761 and o["energy"][0] == g["t_final_E"]
