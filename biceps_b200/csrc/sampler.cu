@@ -779,6 +779,14 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     // bookkeeping in producer warps: sampler_ws.cu; bit-identical, selectable with BCP_KERNEL=ws -- measured on C3 / 4096
     // chains: 6.9 ms per 20 000 steps against 4.6 ms for spec, DESIGN.md section 4, so spec stays the automatic choice)
     int which = !T.canonical ? 0 : (n * lanes <= spec_threads ? 3 : 1);
+    // few chains (at most two consumer warps per SM, e.g. the 704 chains of a BICePs-score run): the warp-specialised
+    // kernel keeps every consumer warp alone on its SM sub-partition and is 1.2-1.3x faster than spec there
+    // (704 chains x 20 000 steps: 3.30 ms against 4.28 ms); BCP_WS_MAX_WARPS_PER_SM overrides the limit (0 = never)
+    {
+        const char* wl = getenv("BCP_WS_MAX_WARPS_PER_SM");
+        const long long lim = wl ? atoll(wl) : 2;
+        if (which == 3 && n * lanes <= lim * sms * 32) which = 4;
+    }
     if (kern && T.canonical)
         which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : (!strcmp(kern, "ws") ? 4 : 2)));
     if (force && force[0] == '1') which = 0;
@@ -814,7 +822,7 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     // 100-state ensemble with 16 chains per warp: 28 %).  Acceptance is a property of the ensemble, so a
     // long auto-selected run starts with a short pilot launch whose rollback fraction decides; the verdict
     // sticks to the chain block.  Every kernel produces the same bits, so this is invisible in the results.
-    const bool spec_auto = which == 3 && !(kern && T.canonical) && T.pf.q < 0;
+    const bool spec_auto = (which == 3 || which == 4) && !(kern && T.canonical) && T.pf.q < 0;
     if (spec_auto && c->spec_verdict < 0) which = 1;
     const long long pilot = (spec_auto && c->spec_verdict == 0 && total >= 8192) ? 1024 : 0;
     for (long long s0 = 0, s1 = 0; s0 < total; s0 = s1) {

@@ -1,55 +1,49 @@
-// K5, warp-specialised speculative Metropolis kernel (the headline kernel for few chains per GPU).
+// K5, warp-specialised speculative Metropolis kernel.
 //
-// With 4096 chains per GPU a step costs the time ONE warp needs to issue its instruction stream in order
-// (sampler_spec.cu).  Only a part of that stream is the chain's critical path -- resolve the pending step,
-// evaluate the next proposal under both outcomes, commit.  Everything else is independent of the chain's
-// energy and is moved to a second warp of the same CTA (same SM sub-partition: it issues in the first warp's
-// dependency stalls):
+// With 4096 chains per GPU a step costs the time ONE warp needs for its dependent instruction stream
+// (sampler_spec.cu; DESIGN.md section 4: ~4.5 cycles per shared-memory / shuffle instruction, ~1.5 per other
+// instruction).  Only a part of that stream is the chain's critical path -- resolve the pending step, evaluate the
+// next proposal under both outcomes, commit.  Everything else is moved to a second warp of the same CTA (same SM
+// sub-partition: it issues in the first warp's stalls):
 //
 //   consumer warp (one per 32 / L chains, L lanes per chain, one lane per restraint)
-//       resolve -> evaluate -> commit, with the speculation, the exact reciprocal-table division, the log-domain
-//       accept test (exact rule inside the guard band) and the rollback of a batch to a careful step-by-step
-//       path of sampler_spec.cu.  It reads PRE-DECODED per-lane step words from a shared-memory ring -- the
-//       shared-memory addresses of the record / gamma value to read, the sigma-entry and gamma offsets already
-//       scaled to bytes, ln u -- and publishes, per batch of BL steps, the BL accept bits and the energy.
-//       Indices are kept scaled (24 sigma_index, 8 gamma_index) so that an address is one add.
-//   producer warp (one per consumer warp)
-//       generates the Philox blocks of the steps NS batches ahead (one block per lane and batch), decodes
-//       them into the per-lane words, requests the proposed states' records / gamma windows with cp.async into
-//       the ring's slots, and REPLAYS the batches the consumer has finished from {proposal word, accept bit}:
-//       index updates, run-length histograms (compacted per batch, one RED per event), acceptance counters,
-//       state trace and the snapshots that fall on the last step of a batch (the kernel front-pads the first
-//       batch so that they do whenever traj_every is a multiple of BL) -- none of this is on the consumer's
-//       instruction stream.
+//       resolve -> evaluate -> commit, with the speculation, the exact reciprocal-table division and the rollback of
+//       a batch to a careful step-by-step path of sampler_spec.cu.  It reads PRE-DECODED per-lane step words from a
+//       shared-memory ring -- the shared-memory addresses of the record / gamma value to read, the sigma-entry and
+//       gamma offsets already scaled to bytes -- decides in fp64 against thresholds the producer prepared
+//       (E - (ln u +- margin): one DSETP after the energy sum), keeps its indices scaled (24 sigma_index,
+//       8 gamma_index) so that an address is one add, and publishes per step its packed indices and per batch the
+//       accept bits and the energy.
+//   generator warp (one per consumer warp)
+//       generates the Philox blocks of the next batch (one block per lane and L steps), decodes them into the
+//       per-lane words, requests the proposed states' records / gamma windows with cp.async into the ring's slots.
+//   accounting warp (one per consumer warp)
+//       turns the batches the consumer has finished into the bookkeeping: run-length histograms from the
+//       published indices (compacted per batch, one RED per event), acceptance counters from {proposal word, accept
+//       bit}, state trace, and the snapshots that fall on the last step of a batch (the kernel front-pads the first
+//       batch so that they do whenever traj_every is a multiple of BL) -- none of this is on the consumer's stream.
 //
-// Hand-off: per consumer warp a ring of NS stages (one stage = one batch), two mbarriers per stage.
-// full[stage]: 32 producer lanes arrive after their stores + 32 cp.async-completion arrivals (cp.async.mbarrier.
+// Hand-off: per consumer warp a ring of NS stages (one stage = one batch of BL steps), three mbarriers per stage.
+// full[stage]: 32 generator lanes arrive after their stores + 32 cp.async-completion arrivals (cp.async.mbarrier.
 // arrive.noinc), so a completed phase means the ring words AND the prefetched slots have landed.  empty[stage]:
-// the 32 consumer lanes arrive when the batch is done.  The consumer waits for the stage after the current one at
-// the top of a batch (its last step evaluates the first step of the next batch).
+// the 32 consumer lanes arrive when the batch is done.  free[stage]: the accountant has copied the batch's words
+// into registers (it then works from the copy while the generator refills the stage).  The consumer needs the stage after the current one only
+// for the LAST step of a batch (it evaluates the first step of the next batch) and waits for it there, so two
+// stages are enough for the two warps to overlap.
 // Same RNG stream, same fp64 operation order, same outputs as every other Metropolis kernel (bit for bit).
 #include "spec_common.cuh"
 
 namespace bcp {
 
 #ifndef WS_NS
-#define WS_NS 4                    // ring stages (batches in flight between the two warps)
+#define WS_NS 4                    // ring stages
 #endif
-#ifndef WS_ORDER
-#define WS_ORDER 0                 // source order of a fast step: 0 resolve, evaluate; 1 evaluate, resolve; 2 evaluate's loads, resolve,
-                                   // evaluate's arithmetic; 3 shuffles, evaluate's loads, the two arithmetic chains side by side (the
-                                   // division's operands are tied to a shuffle result, so that ptxas cannot issue it ahead of the shuffles)
+#ifndef WS_BLV
+#define WS_BLV 4                   // steps per batch (a multiple of L, at most 8: the accept bits of a batch are one byte)
 #endif
-#ifndef WS_ACC64
-#define WS_ACC64 0                 // fast accept test in fp64 against thresholds prepared by the producer: En < E - (ln u + margin) accepts,
-                                   // En > E - (ln u - margin) rejects (one DSETP after the energy sum instead of DSUB, F2F, FADD, FSETP)
-#endif
+#define WS_BL(L) ((L) > WS_BLV ? (L) : WS_BLV)
 #ifndef WS_ROLLED
-#define WS_ROLLED 0                // 1: the steps of a fast batch as a rolled loop (every step its own basic block: ptxas schedules the
-                                   // two dependency chains of ONE step against each other instead of sinking work across steps)
-#endif
-#ifndef WS_LOAD_FENCE
-#define WS_LOAD_FENCE 0            // 1: bar.warp.sync after a step's shared-memory loads (ptxas must not sink them below it)
+#define WS_ROLLED 0                // 1: the steps of a fast batch as a rolled loop (every step its own basic block)
 #endif
 #ifndef WS_TIMING_NO_REPLAY
 #define WS_TIMING_NO_REPLAY 0      // 1: timing experiments only (scripts/tune_ws.sh) -- the producer skips the bookkeeping, results are WRONG
@@ -57,20 +51,22 @@ namespace bcp {
 
 template <int L>
 struct WsCfg {
-    static constexpr int BL = SPEC_BL(L);        // steps per batch = per ring stage
+    static constexpr int BL = WS_BL(L);          // steps per batch = per ring stage
     static constexpr int NB = BL / L;            // Philox blocks a producer lane generates per batch
     static constexpr int NS = WS_NS;
     static constexpr int CPW = 32 / L;           // chains per consumer warp
     static constexpr int NSLOT = NS * BL;        // proposal slots per chain
+    static_assert(BL % L == 0 && BL <= 8 && NS >= 2, "batch / ring shape");
     // byte offsets inside a ring stage (per consumer warp)
     static constexpr int O_LW = 0;                           // [BL][32] per-LANE step words {w, recaddr, nbase, ln u}
     static constexpr int O_TH = BL * 512;                    // [BL][CPW] {ln u + margin, ln u - margin} as doubles (fast accept test)
     static constexpr int O_U = O_TH + BL * CPW * 16;         // [BL][CPW] Metropolis uniform (careful path)
-    static constexpr int O_E = O_U + BL * CPW * 8;           // [CPW] energy after the batch        (consumer -> producer)
-    static constexpr int O_DW = O_E + CPW * 8;               // [BL][CPW] raw proposal word (replay, careful path)
+    static constexpr int O_E = O_U + BL * CPW * 8;           // [CPW] energy after the batch                 (consumer -> producer)
+    static constexpr int O_IDX = O_E + CPW * 8;              // [BL][32] 24 sigma_index | 8 gamma_index << 16 after each step (consumer -> producer)
+    static constexpr int O_DW = O_IDX + BL * 128;            // [BL][CPW] raw proposal word (bookkeeping, careful path)
     static constexpr int O_IST = O_DW + BL * CPW * 4;        // [BL][CPW] proposed state
-    static constexpr int O_WLO = O_IST + BL * CPW * 4;       // [CPW] 8 (window offset - 1) of the stage's gamma windows
-    static constexpr int O_ACC = O_WLO + CPW * 4;            // [CPW] accept bits of the batch       (consumer -> producer)
+    static constexpr int O_WB = O_IST + BL * CPW * 4;        // [CPW] 8 x first gamma-row entry of the stage's prefetched windows
+    static constexpr int O_ACC = O_WB + CPW * 4;             // [CPW] accept bits of the batch               (consumer -> producer)
     static constexpr int STAGE = O_ACC + CPW * 4;
     static constexpr int EVQ = BL * 32 * 8;                  // per producer warp: histogram events of one batch
 };
@@ -138,21 +134,35 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
     constexpr int EB = SPEC_ENT_BYTES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t tma_bar;
-    __shared__ __align__(8) uint64_t bars[8][2][NS];         // [consumer warp][0 full, 1 empty][stage]
+    __shared__ __align__(8) uint64_t bars[8][3][NS];         // [consumer warp][0 full, 1 empty, 2 free][stage]
 
-    const int NW = (int)(blockDim.x >> 6);                   // consumer warps; warps NW .. 2 NW - 1 are their producers
+    // Warp roles (0 consumer, 1 generator, 2 accountant, 3 idle).  A warp runs on SM sub-partition warp % 4, and a consumer
+    // that has its sub-partition to itself is 25 % faster than one that shares it with its two helpers (measured: 704
+    // chains 3.30 ms against 4.28 ms for the spec kernel, 4096 chains 4.72 against 4.59), so:
+    //   1 consumer warp per CTA :  C G A                      (three sub-partitions)
+    //   2 consumer warps        :  C0 C1 G0 A0 -  -  G1 A1    (256 threads, two idle warps: the helpers share 2 and 3)
+    //   3, 4 consumer warps     :  C0.. G0.. A0..             (every sub-partition hosts a consumer and its helpers)
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
-    const bool is_producer = warp >= NW;
-    const int cw = is_producer ? warp - NW : warp;
+    const int NW = blockDim.x == 256 ? 2 : (int)(blockDim.x / 96);
+    int role, cw;
+    if (NW == 2) {
+        role = warp < 2 ? 0 : ((warp == 4 || warp == 5) ? 3 : 1 + (warp & 1));
+        cw = warp < 2 ? warp : (warp >> 2) & 1;
+    } else {
+        role = warp / NW;
+        cw = warp - role * NW;
+    }
     if ((int)threadIdx.x < NW) {
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            mbar_init(smem_u32(&bars[threadIdx.x][0][k]), 64);
-            mbar_init(smem_u32(&bars[threadIdx.x][1][k]), 32);
+            mbar_init(smem_u32(&bars[threadIdx.x][0][k]), 64);   // generator: 32 arrivals + 32 cp.async completions
+            mbar_init(smem_u32(&bars[threadIdx.x][1][k]), 32);   // consumer: batch done
+            mbar_init(smem_u32(&bars[threadIdx.x][2][k]), 32);   // accountant: the stage's words are copied out, it may be refilled
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     stage_sigma_table(reinterpret_cast<double*>(smem_raw), T.sig4, T.sig4_bytes, &tma_bar);     // has the block barrier
+    if (role == 3) return;
 
     const long long n = C.n_chains;
     const int q = lane & (L - 1);                            // lane within the chain's group
@@ -202,36 +212,23 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
     const uint32_t slots = chain_base + ly.slot0;
     const uint32_t ring = smem0 + (uint32_t)T.sig4_bytes + (uint32_t)(NW * CPW) * (uint32_t)ly.chain_bytes +
                           (uint32_t)(cw * NS) * (uint32_t)W::STAGE;
-    const uint32_t bar_full = smem_u32(&bars[cw][0][0]), bar_empty = smem_u32(&bars[cw][1][0]);
+    const uint32_t bar_full = smem_u32(&bars[cw][0][0]), bar_empty = smem_u32(&bars[cw][1][0]), bar_free = smem_u32(&bars[cw][2][0]);
     auto slot_of = [&](int stage, int j) { return slots + (uint32_t)(stage * BL + j) * (uint32_t)ly.slot_bytes; };
     auto ring_of = [&](int stage) { return ring + (uint32_t)stage * (uint32_t)W::STAGE; };
+    const uint32_t idx_glane = W::O_IDX + 4u * (uint32_t)(jg * L + (HG ? R - 1 : 0));   // the chain's gamma lane in an IDX row
 
-    if (is_producer) {
+    if (role == 1) {
         // =====================================================================================
-        // producer: Philox + decode + prefetch NS batches ahead, replay of the finished batches
+        // generator: Philox + decode + prefetch, one batch ahead of the consumer
         // =====================================================================================
-        const int grp = C.group[c];
         const unsigned long long chain_id = C.chain_id0 + (unsigned long long)c;
-        unsigned long long* g_state_counts = C.state_counts + (size_t)grp * T.S;
-        const uint32_t sbin0 = (uint32_t)grp * (uint32_t)T.HB + (uint32_t)T.r[qr].hist_sigma;
-        const uint32_t gbin0 = (uint32_t)grp * (uint32_t)T.HB + (uint32_t)(HG ? T.r[R - 1].hist_gamma : 0);
         const uint32_t S = (uint32_t)T.S;
         const uint32_t thresh = T.nuis_thresh;
         const unsigned long long ctr0 = A.step0 + (unsigned long long)A.s_begin;
         const uint32_t seed_lo = (uint32_t)C.seed, seed_hi = (uint32_t)(C.seed >> 32);
         const uint32_t ch_lo = (uint32_t)chain_id, ch_hi = (uint32_t)(chain_id >> 32);
-        const bool tracing = A.state_trace != nullptr;
-        const bool traced = tracing && lead && c < A.trace_n;
-        const uint32_t evq = smem0 + (uint32_t)T.sig4_bytes + (uint32_t)(NW * CPW) * (uint32_t)ly.chain_bytes +
-                             (uint32_t)(NW * NS) * (uint32_t)W::STAGE + (uint32_t)cw * (uint32_t)W::EVQ;
-        const uint32_t lane_lt = (1u << lane) - 1u;
 
-        int state = C.state[c];
-        int sg = C.isg[(size_t)qr * n + c];
-        int gm = HG ? C.igm[(size_t)(R - 1) * n + c] : 0;
-        int pg = gm;
-        int since_sg = burn, since_gm = burn, since_state = burn;
-        unsigned int acc_own = 0, acc_state = 0, acc_total = 0;
+        uint32_t gm8 = HG ? (uint32_t)(8 * C.igm[(size_t)(R - 1) * n + c]) : 0u;   // the chain's scaled gamma index (every lane)
 
         uint32_t rk0[10], rk1[10];
 #pragma unroll
@@ -240,6 +237,9 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
             rk1[i] = seed_hi + (uint32_t)i * BCP_PHILOX_W1;
             asm volatile("" : "+r"(rk0[i]), "+r"(rk1[i]));
         }
+        // per-lane constants of the step words: w = nuis | ((glane ? 8 f_gamma : 8) << 8) | 24 f_sigma, f = delta + 1
+        const uint32_t wg_mul = glane ? 2048u : 0u, wg_add = glane ? 0u : 2048u;
+        const uint32_t nb_row = cur_row + 24u;               // + 8 f_gamma: entry of gamma index + (delta) in the halo-4 row
 
         // one batch: lane (chain jg, position q + m L) generates that step; then every lane writes ITS words of
         // every step of the batch
@@ -247,7 +247,7 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
             const uint32_t rs = ring_of(stage);
             uint32_t g_dw[NB];
             float g_lu[NB];
-            const int wofs = (gm & 1) + 4 - pg;      // smem window index of the unwrapped gamma position p: wofs + p
+            const uint32_t wbase = (gm8 >> 3) & ~1u;         // first halo-4 row entry of this stage's prefetched windows
 #pragma unroll
             for (int m = 0; m < NB; ++m) {
                 const int t = m * L + q;
@@ -289,32 +289,71 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
                     for (int k = 0; k < R; ++k) cp_async16(slot + 16 * k, r2 + 2 * k);
                     cp_async8(slot + ly.slot_c, energy + hi);
                     if (HG) {
-                        const double* w = gh4 + (size_t)hi * GS + (gm & ~1);
+                        const double* w = gh4 + (size_t)hi * GS + wbase;
 #pragma unroll
                         for (int k = 0; k < 5; ++k) cp_async16(slot + ly.slot_win + 16 * k, w + 2 * k);
                     }
                 }
             }
+            const uint32_t slot_q = slot_of(stage, 0) + 16u * (uint32_t)qr;
+            // window entry of halo-4 row entry k: k - wbase  ->  value of gamma index gm: slot_win + 8 (gm + 4 - wbase)
+            const uint32_t nb_win = slot_of(stage, 0) + (uint32_t)ly.slot_win + 32u - 8u * wbase;
 #pragma unroll
             for (int t = 0; t < BL; ++t) {
                 const uint32_t dwt = __shfl_sync(SPEC_FULL, g_dw[t / L], t % L, L);
                 const float lut = __shfl_sync(SPEC_FULL, g_lu[t / L], t % L, L);
                 const bool nuis = (int)dwt < 0;
-                const int d1 = (int)((dwt >> fsh) & 3u) - 1, g1 = (int)((dwt >> 16) & 3u) - 1;
-                const uint32_t slot = slot_of(stage, t);
-                const uint32_t recaddr = nuis ? cur_rec : slot + 16 * qr;
+                const uint32_t fs = (dwt >> fsh) & 3u, fg = (dwt >> 16) & 3u;
+                const uint32_t so = (uint32_t)t * (uint32_t)ly.slot_bytes;
+                const uint32_t recaddr = nuis ? cur_rec : slot_q + so;
                 uint32_t nbase = recaddr;
-                if (glane) nbase = nuis ? cur_row + 8u * (uint32_t)(4 + g1) : slot + (uint32_t)ly.slot_win + 8u * (uint32_t)wofs;
-                const uint32_t w = (dwt & 0x80000000u) | ((uint32_t)(glane ? 8 * (g1 + 1) : 8) << 8) | (uint32_t)(EB * (d1 + 1));
+                if (glane) nbase = nuis ? nb_row + 8u * fg : nb_win + so;
+                const uint32_t w = (dwt & 0x80000000u) | (fs * (uint32_t)EB + fg * wg_mul + wg_add);
                 sts128u(rs + W::O_LW + 512u * (uint32_t)t + 16u * (uint32_t)lane, w, recaddr, nbase, __float_as_uint(lut));
             }
-            if (q == 0) sts32(rs + W::O_WLO + 4u * (uint32_t)jg, (uint32_t)(8 * wofs - 8));
+            if (q == 0) sts32(rs + W::O_WB + 4u * (uint32_t)jg, 8u * wbase);
             mbar_arrive_cp_async(bar_full + 8u * (uint32_t)stage);
             mbar_arrive(bar_full + 8u * (uint32_t)stage);
         };
 
-        // accepted state move of a replayed step (rare on large ensembles)
-        auto replay_state = [&](int s, int i2) {
+        // batch i goes into stage i mod NS once the accountant has copied the words of batch i - NS out of it (which implies
+        // that the consumer is done with it).  Batch nbatch is generated too: the consumer's last step evaluates its first
+        // proposal (padding).  The gamma window of the prefetches is placed around the chain's gamma index at the end of
+        // the stage's previous batch (the consumer's published indices are still there).
+        int stage = 0, round = 0;                             // i == round * NS + stage
+        for (int i = 0; i <= nbatch; ++i) {
+            if (i >= NS) {
+                mbar_wait(bar_free + 8u * (uint32_t)stage, (uint32_t)(round - 1) & 1u);
+                if (HG) gm8 = lds32(ring_of(stage) + idx_glane + 128u * (uint32_t)(BL - 1)) >> 16;
+            }
+            generate(i, stage);
+            if (++stage == NS) { stage = 0; ++round; }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        return;
+    }
+    if (role == 2) {
+        // =====================================================================================
+        // accountant: the bookkeeping of the batches the consumer has finished
+        // =====================================================================================
+        const int grp = C.group[c];
+        unsigned long long* g_state_counts = C.state_counts + (size_t)grp * T.S;
+        const uint32_t sbin0 = (uint32_t)grp * (uint32_t)T.HB + (uint32_t)T.r[qr].hist_sigma;
+        const uint32_t gbin0 = (uint32_t)grp * (uint32_t)T.HB + (uint32_t)(HG ? T.r[R - 1].hist_gamma : 0);
+        const bool tracing = A.state_trace != nullptr;
+        const bool traced = tracing && lead && c < A.trace_n;
+        const uint32_t evq = smem0 + (uint32_t)T.sig4_bytes + (uint32_t)(NW * CPW) * (uint32_t)ly.chain_bytes +
+                             (uint32_t)(NW * NS) * (uint32_t)W::STAGE + (uint32_t)cw * (uint32_t)W::EVQ;
+        const uint32_t lane_lt = (1u << lane) - 1u;
+
+        int state = C.state[c];
+        uint32_t sg24 = (uint32_t)(EB * C.isg[(size_t)qr * n + c]);     // this lane's scaled sigma index as last published
+        uint32_t gm8 = HG ? (uint32_t)(8 * C.igm[(size_t)(R - 1) * n + c]) : 0u;   // the chain's scaled gamma index (every lane)
+        int since_sg = burn, since_gm = burn, since_state = burn;
+        unsigned int acc_own = 0, acc_state = 0, acc_total = 0;
+
+        // accepted state move of a finished step (rare on large ensembles)
+        auto account_state = [&](int s, int i2) {
             ++acc_state;
             if (i2 != state) {
                 if (s > burn && lead) atomicAdd(g_state_counts + state, (unsigned long long)(s - since_state));
@@ -322,67 +361,70 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
                 state = i2;
             }
         };
-        auto store_snapshot = [&](uint32_t rs, bool acc) {
-            const size_t o = (size_t)snap_idx * n + c;
-            if (lead) {
-                A.traj_E[o] = lds64(rs + W::O_E + 8u * (uint32_t)jg);
-                A.traj_state[o] = state;
-                A.traj_accept[o] = acc ? 1 : 0;
-            }
-            if (owner) A.traj_idx[((size_t)snap_idx * T.P + q) * n + c] = sg;
-            if (HG && glane && live) A.traj_idx[((size_t)snap_idx * T.P + R) * n + c] = gm;
-        };
         auto next_snapshot = [&]() {
             ++snap_idx;
             const long long ns = (long long)next_snap + A.traj_every;
             next_snap = ns < s_end ? (int)ns : -1;
         };
 
-        // the bookkeeping of a finished batch from {proposal word, accept bit}: branch-free per step, the
-        // histogram events of the batch compacted into a per-warp queue and flushed with one RED each
-        auto replay = [&](int b, int stage) {
+        // the bookkeeping of a finished batch: run lengths of the indices the consumer published after every step,
+        // counters from {proposal word, accept bit}; the batch's histogram events are compacted into a per-warp queue
+        // and flushed with one RED each
+        auto account = [&](int b, int stage) {
             const uint32_t rs = ring_of(stage);
+            // copy the batch's words out of the stage, then hand the stage back to the generator
+            uint32_t w_own[BL], w_gam[BL], w_dw[BL], w_ist[BL];
             const uint32_t accb = lds32(rs + W::O_ACC + 4u * (uint32_t)jg);
+            const double E_end = lds64(rs + W::O_E + 8u * (uint32_t)jg);
+#pragma unroll
+            for (int t = 0; t < BL; ++t) {
+                w_own[t] = lds32(rs + W::O_IDX + 128u * (uint32_t)t + 4u * (uint32_t)lane);
+                w_gam[t] = HG ? lds32(rs + idx_glane + 128u * (uint32_t)t) : 0u;
+                w_dw[t] = lds32(rs + W::O_DW + 4u * (uint32_t)(t * CPW + jg));
+                w_ist[t] = lds32(rs + W::O_IST + 4u * (uint32_t)(t * CPW + jg));
+            }
+            mbar_arrive(bar_free + 8u * (uint32_t)stage);
+#ifdef WS_TIMING_ACC_COPY_ONLY
+            {   // timing experiment: keep the loads alive, skip the bookkeeping
+                uint32_t x = accb ^ (uint32_t)__double2loint(E_end);
+#pragma unroll
+                for (int t = 0; t < BL; ++t) x ^= w_own[t] ^ w_gam[t] ^ w_dw[t] ^ w_ist[t];
+                if (x == 0x12345678u) acc_total++;
+                return;
+            }
+#endif
             const int sb = b * BL - pad;
             uint32_t evn = 0;
 #pragma unroll
             for (int t = 0; t < BL; ++t) {
                 const int s = sb + t;
-                const uint32_t dw = lds32(rs + W::O_DW + 4u * (uint32_t)(t * CPW + jg));
+                const uint32_t dw = w_dw[t];
+                const uint32_t mine = w_own[t] & 0xffffu;
                 const bool acc = (accb >> t) & 1u;
                 const bool rec_on = s > burn;
-                const int d0 = (int)((dw >> fsh) & 3u) - 1, g0 = (int)((dw >> 16) & 3u) - 1;   // 0 for a state move
                 acc_total += acc ? 1u : 0u;
                 acc_own += (acc && (dw & own_mask)) ? 1u : 0u;
-                int v = sg + d0;
-                v += v < 0 ? nsig : 0;
-                v -= v >= nsig ? nsig : 0;
-                const int sg_new = acc ? v : sg;
-                const bool chs = rec_on && sg_new != sg;
-                uint32_t bin = sbin0 + (uint32_t)sg;
+                const bool chs = rec_on && mine != sg24;
+                uint32_t bin = sbin0 + sg24 / (uint32_t)EB;
                 int since = since_sg;
                 bool ev = chs && owner;
                 since_sg = chs ? s : since_sg;
-                sg = sg_new;
+                sg24 = mine;
                 if (HG) {
-                    int w = gm + g0;
-                    w += w < 0 ? G : 0;
-                    w -= w >= G ? G : 0;
-                    const int gm_new = acc ? w : gm;
-                    const bool chg = rec_on && gm_new != gm;
+                    const uint32_t gnow = w_gam[t] >> 16;
+                    const bool chg = rec_on && gnow != gm8;
                     const bool evg = chg && ghist;
-                    bin = evg ? gbin0 + (uint32_t)gm : bin;
+                    bin = evg ? gbin0 + (gm8 >> 3) : bin;
                     since = evg ? since_gm : since;
                     ev = ev || evg;
                     since_gm = chg ? s : since_gm;
-                    gm = gm_new;
-                    pg += acc ? g0 : 0;
+                    gm8 = gnow;
                 }
                 const uint32_t cnt = ev ? (uint32_t)(s - since) : 0u;
                 const uint32_t m = __ballot_sync(SPEC_FULL, cnt != 0u);
                 if (cnt != 0u) sts64u(evq + 8u * (evn + (uint32_t)__popc(m & lane_lt)), bin, cnt);
                 evn += (uint32_t)__popc(m);
-                if (acc && (int)dw >= 0) replay_state(s, (int)lds32(rs + W::O_IST + 4u * (uint32_t)(t * CPW + jg)));
+                if (acc && (int)dw >= 0) account_state(s, (int)w_ist[t]);
                 if (tracing) {
                     if (traced && s >= burn && s < s_end) A.state_trace[(size_t)(A.s_begin + s - A.burn) * A.trace_n + c] = state;
                 }
@@ -392,26 +434,32 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
                 const uint2 e = lds64u(evq + 8u * k);
                 atomicAdd(C.param_counts + e.x, (unsigned long long)e.y);
             }
-            // snapshots of this batch: the one on the last step is stored here (state == the batch's final state),
-            // the others were stored by the consumer's careful path
+            __syncwarp();
+            // snapshots of this batch: the one on the last step is stored here (indices and state == the batch's final
+            // ones), the others were stored by the consumer's careful path
             while (next_snap >= 0 && next_snap < sb + BL) {
-                if (next_snap == sb + BL - 1) store_snapshot(rs, (accb >> (BL - 1)) & 1u);
+                if (next_snap == sb + BL - 1) {
+                    const size_t o = (size_t)snap_idx * n + c;
+                    if (lead) {
+                        A.traj_E[o] = E_end;
+                        A.traj_state[o] = state;
+                        A.traj_accept[o] = (accb >> (BL - 1)) & 1u;
+                    }
+                    if (owner) A.traj_idx[((size_t)snap_idx * T.P + q) * n + c] = (int)(sg24 / (uint32_t)EB);
+                    if (HG && glane && live) A.traj_idx[((size_t)snap_idx * T.P + R) * n + c] = (int)(gm8 >> 3);
+                }
                 next_snapshot();
             }
         };
 
-        // iteration i: replay batch i - NS (once the consumer has released its stage), then generate batch i into the
-        // same stage.  Batch nbatch is generated too: the consumer's last step evaluates its first proposal (padding).
-        int stage = 0, round = 0;                             // i == round * NS + stage
-        for (int i = 0; i < nbatch + NS; ++i) {
-            if (i >= NS) {
-                mbar_wait(bar_empty + 8u * (uint32_t)stage, (uint32_t)(round - 1) & 1u);      // phase round - 1 == batch i - NS
-#if !WS_TIMING_NO_REPLAY
-                replay(i - NS, stage);
+        int stage = 0, round = 0;                             // b == round * NS + stage
+        for (int b = 0; b < nbatch; ++b) {
+            mbar_wait(bar_empty + 8u * (uint32_t)stage, (uint32_t)round & 1u);
+#if WS_TIMING_NO_REPLAY
+            mbar_arrive(bar_free + 8u * (uint32_t)stage);
+#else
+            account(b, stage);
 #endif
-                __syncwarp();
-            }
-            if (i <= nbatch) generate(i, stage);
             if (++stage == NS) { stage = 0; ++round; }
         }
         // ---- flush run-length counters, persist the chain (E is persisted by the consumer) ----
@@ -422,15 +470,14 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
             C.sep[(size_t)R * n + c] += acc_state;
         }
         if (owner) {
-            if (s_end > since_sg) atomicAdd(C.param_counts + sbin0 + sg, (unsigned long long)(s_end - since_sg));
-            C.isg[(size_t)q * n + c] = sg;
+            if (s_end > since_sg) atomicAdd(C.param_counts + sbin0 + sg24 / (uint32_t)EB, (unsigned long long)(s_end - since_sg));
+            C.isg[(size_t)q * n + c] = (int)(sg24 / (uint32_t)EB);
             C.sep[(size_t)q * n + c] += acc_own;
         }
         if (ghist) {
-            if (s_end > since_gm) atomicAdd(C.param_counts + gbin0 + gm, (unsigned long long)(s_end - since_gm));
-            C.igm[(size_t)(R - 1) * n + c] = gm;
+            if (s_end > since_gm) atomicAdd(C.param_counts + gbin0 + (gm8 >> 3), (unsigned long long)(s_end - since_gm));
+            C.igm[(size_t)(R - 1) * n + c] = (int)(gm8 >> 3);
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
         return;
     }
 
@@ -443,14 +490,13 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
     const double cnorm = T.r[qr].cnorm;
     const int nsig24 = EB * nsig, G8 = 8 * G;
     const uint32_t lw_lane = W::O_LW + 16u * (uint32_t)lane;
+    const uint32_t idx_lane = W::O_IDX + 4u * (uint32_t)lane;
     auto bcast_d = [&](double v, int src) { return __shfl_sync(SPEC_FULL, v, src, L); };
-    const uint32_t zero = (uint32_t)((unsigned long long)A.n_snap >> 63);      // 0 at run time, opaque to the compiler (WS_ORDER 3)
 
     int state = C.state[c];
     double E = C.E[c];
     int sg24 = EB * C.isg[(size_t)qr * n + c];               // 24 x this lane's sigma index
     int gm8 = glane ? 8 * C.igm[(size_t)(R - 1) * n + c] : 0;  // 8 x gamma index, in the gamma lane only (0 elsewhere)
-    int pg8 = gm8;                                           // 8 x unwrapped gamma position (window bookkeeping)
     // lane 0 adds energy + logZ to its term (reference order (C + t_0) + t_1 ...); x + (-0.0) == x bitwise
     double Cst = q == 0 ? __dadd_rn(energy[state], logZ) : -0.0;
     unsigned int n_batches = 0, n_rollbacks = 0;
@@ -465,45 +511,41 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
     // ---- this lane's contribution to the energy of a proposal (per-lane step words lw): its restraint term, plus
     //      energy + logZ in lane 0.  A: on the committed state, B: on the committed state shifted by the pending
     //      step (a0 = 24 dsigma, g0x = 8 dgamma).  Window misses are only flagged (the careful path re-evaluates).
+    //      wb8 = 8 x first row entry of the proposal's prefetched gamma window (24 outside the gamma lane: never a miss).
     struct Cand { double xA, xB; int a1, g1x; bool miss; };
-    struct EvalIn { double nlA, dvA, yA, nlB, dvB, yB, numA, numB, ref, Cn; int a1, g1x; bool miss; };
-    auto evaluate_load = [&](const uint4& lw, int wlo8, int a0_, int g0x_) {
-        EvalIn k;
+    auto evaluate = [&](const uint4& lw, int wb8, int a0_, int g0x_) {
+        Cand k;
         const bool nuis_n = (int)lw.x < 0;
         const uint32_t ab = lw.x & 0xffu;
         k.a1 = (int)ab - EB;
         k.g1x = (int)((lw.x >> 8) & 0xffu) - 8;
         const uint32_t eA = entm + (uint32_t)sg24 + ab;      // unwrapped: entries carry a halo of 2
         const uint32_t eB = eA + (uint32_t)a0_;
-        k.nlA = lds64(eA); k.dvA = lds64(eA + 8); k.yA = lds64(eA + 16);
-        k.nlB = lds64(eB); k.dvB = lds64(eB + 8); k.yB = lds64(eB + 16);
+        const double nlA = lds64(eA), dvA = lds64(eA + 8), yA = lds64(eA + 16);
+        const double nlB = lds64(eB), dvB = lds64(eB + 8), yB = lds64(eB + 16);
         const uint32_t recaddr = lw.y;
         const double2 rv = lds128(recaddr);
-        k.numA = rv.x; k.numB = rv.x; k.ref = rv.y;
+        double numA = rv.x, numB = rv.x;
         k.miss = false;
         if (HG) {
-            // the other lanes re-read their own sse word: nbase == recaddr, gm8 == pg8 == g0x == wlo8 == 0 there
-            k.miss = !nuis_n && (uint32_t)(pg8 + wlo8) > 56u;    // window index +- 1 must stay inside the 10-wide window
-            uint32_t na = lw.z + (uint32_t)(nuis_n ? gm8 : pg8);
+            // the other lanes re-read their own sse word: nbase == recaddr, gm8 == g0x == 0 there.  A state-move proposal
+            // reads the window entry of the current gamma index; its neighbours (+- 1) must be inside the 10-wide window
+            k.miss = !nuis_n && (uint32_t)(gm8 + 24 - wb8) > 56u;
+            uint32_t na = lw.z + (uint32_t)gm8;
             na = k.miss ? recaddr : na;
-            k.numA = lds64(na);
-            k.numB = lds64(na + (uint32_t)g0x_);
+            numA = lds64(na);
+            numB = lds64(na + (uint32_t)g0x_);
         }
-        k.Cn = Cst;
-        if (!nuis_n && q == 0) k.Cn = __dadd_rn(lds64(recaddr + 16 * R), logZ);
-        return k;
-    };
-    auto evaluate_math = [&](const EvalIn& in) {
-        Cand k;
-        k.a1 = in.a1; k.g1x = in.g1x; k.miss = in.miss;
-        double t = __dadd_rn(in.nlA, div_markstein(in.numA, in.dvA, in.yA));
+        double Cn = Cst;
+        if (!nuis_n && q == 0) Cn = __dadd_rn(lds64(recaddr + 16 * R), logZ);
+        double t = __dadd_rn(nlA, div_markstein(numA, dvA, yA));
         t = __dadd_rn(t, cnorm);
-        t = __dsub_rn(t, in.ref);
-        k.xA = __dadd_rn(t, in.Cn);
-        t = __dadd_rn(in.nlB, div_markstein(in.numB, in.dvB, in.yB));
+        t = __dsub_rn(t, rv.y);
+        k.xA = __dadd_rn(t, Cn);
+        t = __dadd_rn(nlB, div_markstein(numB, dvB, yB));
         t = __dadd_rn(t, cnorm);
-        t = __dsub_rn(t, in.ref);
-        k.xB = __dadd_rn(t, in.Cn);
+        t = __dsub_rn(t, rv.y);
+        k.xB = __dadd_rn(t, Cn);
         return k;
     };
     // the same on the committed state only, from the raw proposal word; the gamma value of a proposed state (i2)
@@ -539,12 +581,14 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
             w += w < 0 ? G8 : 0;
             w -= w >= G8 ? G8 : 0;
             gm8 = acc ? w : gm8;
-            pg8 += acc ? g0x : 0;
         }
     };
     auto pending_from_raw = [&](uint32_t dn) {
         a0 = EB * ((int)((dn >> fsh) & 3u) - 1);
         g0x = glane ? 8 * ((int)((dn >> 16) & 3u) - 1) : 0;
+    };
+    auto publish_step = [&](uint32_t rs, int j) {             // this lane's indices after step j (the producer's bookkeeping)
+        sts32(rs + idx_lane + 128u * (uint32_t)j, (uint32_t)sg24 | ((uint32_t)gm8 << 16));
     };
 
     // ---- prologue: the first pending step ----------------------------------------------------------
@@ -559,8 +603,8 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
         pending_from_raw(dw0);
         x_prop = evaluate_exact(dw0, slot_of(0, 0), lds32(ring_of(0) + W::O_IST + 4u * (uint32_t)jg));
     }
-    auto wlo_of = [&](uint32_t rs) { return glane ? (int)lds32(rs + W::O_WLO + 4u * (uint32_t)jg) : 0; };
-    int wlo_cur = wlo_of(ring_of(0));
+    auto wb_of = [&](uint32_t rs) { return glane ? (int)lds32(rs + W::O_WB + 4u * (uint32_t)jg) : 24; };
+    int wb_cur = wb_of(ring_of(0));
 
     int stage = 0;
     uint32_t par = 0;                                         // parity of the current stage's full phase
@@ -569,96 +613,61 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
         const int stage_n = stage + 1 == NS ? 0 : stage + 1;
         const uint32_t par_n = stage_n == 0 ? par ^ 1u : par;
         const uint32_t rs = ring_of(stage), rn = ring_of(stage_n);
-        mbar_wait(bar_full + 8u * (uint32_t)stage_n, par_n);  // the last step of this batch evaluates the next batch's first step
-        const int wlo_n = wlo_of(rn);
+        // the last step of a batch evaluates the next batch's first step: the next stage is waited for only there
+        bool have_next = false;
+        int wb_n = 24;
+        auto need_next = [&]() {
+            if (!have_next) {
+                mbar_wait(bar_full + 8u * (uint32_t)stage_n, par_n);
+                wb_n = wb_of(rn);
+                have_next = true;
+            }
+        };
         uint32_t accb = 0;
 
-        // ---- fast batch: BL steps as ONE basic block on registers only (shared memory is read, never written);
+        // ---- fast batch: BL steps on registers only (shared memory is read; written only to publish the indices);
         //      anything rare only raises a flag and the batch is then redone carefully ------------------------
         bool careful = (unsigned)(next_snap - s0) < (unsigned)(BL - 1);   // a snapshot before the batch's last step
         if (!careful) {
-            // the step words of the proposals evaluated in this batch: positions 1 .. BL-1 and the next batch's first
-#if WS_ROLLED
-            uint32_t lw_addr = rs + 512u + lw_lane;          // words of position 1; the last step reads the next stage's position 0
-#else
-            uint4 lw[BL];
-#pragma unroll
-            for (int j = 0; j < BL; ++j) lw[j] = lds128u((j + 1 == BL ? rn : rs + 512u * (uint32_t)(j + 1)) + lw_lane);
-#endif
             const double sv_E = E, sv_x = x_prop;
-            const int sv_sg = sg24, sv_gm = gm8, sv_pg = pg8, sv_a0 = a0, sv_g0 = g0x;
+            const int sv_sg = sg24, sv_gm = gm8, sv_a0 = a0, sv_g0 = g0x;
             const bool sv_nuis = nuis_s;
             const float sv_lu = lu_s;
             bool rare = false;
 #if WS_ROLLED
 #pragma unroll 1
-            for (int j = 0; j < BL; ++j) {
-                const bool last = j + 1 == BL;
-                const uint4 lwj = lds128u(last ? rn + lw_lane : lw_addr);
-                lw_addr += 512u;
-                const int wlo_j = last ? wlo_n : wlo_cur;
 #else
 #pragma unroll
+#endif
             for (int j = 0; j < BL; ++j) {
-                const uint4 lwj = lw[j];
-                const int wlo_j = j + 1 == BL ? wlo_n : wlo_cur;
-#endif
-                // (1) resolve the pending step: energy in the reference's summation order, accept in the log domain.
-                // (2) contributions to the next step under both outcomes of the pending one: they depend on the commit of
-                //     the step BEFORE the pending one only, so the two dependency chains (shuffles -> 3 adds -> accept;
-                //     loads -> division -> 4 adds) can run side by side.  ptxas serialises them when left alone (it issues
-                //     the division ahead of the shuffles: 460 cycles per step); WS_ORDER 3 issues the shuffles first and ties
-                //     the division's numerators to the last shuffle's result (x ^ (v & 0), one LOP3 each).
-#if WS_ORDER == 1
-                const Cand k = evaluate_math(evaluate_load(lwj, wlo_j, a0, g0x));
-#elif WS_ORDER == 2
-                const EvalIn ein = evaluate_load(lwj, wlo_j, a0, g0x);
-#endif
+                const bool last = j + 1 == BL;
+                if (last) need_next();
+                // the step words of the proposal evaluated in this step (position j + 1, or the next batch's first)
+                const uint4 lwj = lds128u((last ? rn : rs + 512u * (uint32_t)(j + 1)) + lw_lane);
+                // thresholds of the pending step (position j of this stage) against the committed energy
+                const double2 th = lds128(rs + W::O_TH + 16u * (uint32_t)jg + (uint32_t)(16 * CPW) * (uint32_t)j);
+                // (1) resolve the pending step: energy in the reference's summation order, accept against E - (ln u +- margin)
                 double xv[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) xv[r] = bcast_d(x_prop, r);
-#if WS_ACC64
-                // thresholds of the pending step (position j of this stage) against the committed energy
-                const double2 th = lds128(rs + W::O_TH + 16u * (uint32_t)jg + (uint32_t)(16 * CPW) * (uint32_t)j);
                 const double Ahi = __dsub_rn(E, th.x), Alo = __dsub_rn(E, th.y);
-#endif
-#if WS_ORDER == 3
-                EvalIn ein = evaluate_load(lwj, wlo_j, a0, g0x);
-#if WS_LOAD_FENCE
-                asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
-#endif
-                {
-                    const uint32_t tie = (uint32_t)__double2loint(xv[R - 1]) & zero;
-                    ein.numA = __hiloint2double(__double2hiint(ein.numA), (int)((uint32_t)__double2loint(ein.numA) ^ tie));
-                    ein.numB = __hiloint2double(__double2hiint(ein.numB), (int)((uint32_t)__double2loint(ein.numB) ^ tie));
-                }
-#endif
                 double En = xv[0];
 #pragma unroll
                 for (int r = 1; r < R; ++r) En = __dadd_rn(En, xv[r]);
-#if WS_ACC64
                 const bool acc = En < Ahi;
                 const bool unsure = !acc && !(En > Alo);                 // guard band, also NaN
-#else
-                const double d = __dsub_rn(E, En);
-                const float tt = (float)d - lu_s;
-                const bool acc = tt > SPEC_MARGIN;
-                const bool unsure = !acc && !(tt < -SPEC_MARGIN);        // guard band, also NaN
-#endif
-#if WS_ORDER == 0
-                const Cand k = evaluate_math(evaluate_load(lwj, wlo_j, a0, g0x));
-#elif WS_ORDER >= 2
-                const Cand k = evaluate_math(ein);
-#endif
+                // (2) contributions to the next step under both outcomes of the pending one
+                const Cand k = evaluate(lwj, last ? wb_n : wb_cur, a0, g0x);
                 rare = rare || unsure || (acc && !nuis_s) || k.miss;
-                // (3) commit
+                // (3) commit, publish the indices
                 commit(acc, En);
+                publish_step(rs, j);
                 accb |= acc ? (1u << j) : 0u;
                 x_prop = acc ? k.xB : k.xA;
                 nuis_s = (int)lwj.x < 0; lu_s = __uint_as_float(lwj.w); a0 = k.a1; g0x = k.g1x;
             }
             if (__any_sync(SPEC_FULL, rare)) {               // roll the batch back
-                E = sv_E; x_prop = sv_x; sg24 = sv_sg; gm8 = sv_gm; pg8 = sv_pg; a0 = sv_a0; g0x = sv_g0;
+                E = sv_E; x_prop = sv_x; sg24 = sv_sg; gm8 = sv_gm; a0 = sv_a0; g0x = sv_g0;
                 nuis_s = sv_nuis; lu_s = sv_lu;
                 accb = 0;
                 careful = true;
@@ -673,6 +682,7 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
             for (int j = 0; j < BL; ++j) {
                 const int s = s0 + j;
                 const bool nb = j + 1 == BL;
+                if (nb) need_next();
                 const int jn = nb ? 0 : j + 1;
                 const uint32_t en = (uint32_t)(CPW * jn + jg), ej = (uint32_t)(CPW * j + jg);
                 const uint32_t rsn = nb ? rn : rs;
@@ -693,6 +703,7 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
                     acc = unsure ? exact : acc;
                 }
                 commit(acc, En);
+                publish_step(rs, j);
                 accb |= acc ? (1u << j) : 0u;
                 const bool accst = acc && !nuis_s;
                 if (__any_sync(SPEC_FULL, accst)) {
@@ -741,7 +752,7 @@ mcmc_ws_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ 
             sts32(rs + W::O_ACC + 4u * (uint32_t)jg, accb);
         }
         mbar_arrive(bar_empty + 8u * (uint32_t)stage);
-        stage = stage_n; par = par_n; wlo_cur = wlo_n;
+        stage = stage_n; par = par_n; wb_cur = wb_n;
     }
 
     if (lane == 0 && n_batches) {
@@ -758,7 +769,7 @@ static cudaError_t launch_ws_one(const SamplerTables& T, const ChainBuffers& C, 
     const long long threads = C.n_chains * L;
     const long long n_warps = (threads + 31) / 32;
     int wpb = (int)((n_warps + sms - 1) / sms);
-    wpb = wpb < 1 ? 1 : (wpb > 8 ? 8 : wpb);
+    wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);         // consumer warps per CTA (x 3 warps)
     int dev = 0, max_optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -770,22 +781,19 @@ static cudaError_t launch_ws_one(const SamplerTables& T, const ChainBuffers& C, 
     }
     if (wpb < 1) return cudaErrorNotSupported;
     const int grid = (int)((n_warps + wpb - 1) / wpb);
-    // up to 4 consumer + 4 producer warps: no register cap (255); the 8 + 8 shape (two waves) is capped at 128
-    if (wpb <= 4) {
-        cudaError_t e = cudaFuncSetAttribute(mcmc_ws_kernel<L, R, HG, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        mcmc_ws_kernel<L, R, HG, 256><<<grid, 64 * wpb, smem, st>>>(T, C, A);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(mcmc_ws_kernel<L, R, HG, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        mcmc_ws_kernel<L, R, HG, 512><<<grid, 64 * wpb, smem, st>>>(T, C, A);
-    }
+    // 4 consumer + 4 generator + 4 accounting warps: 384 threads, up to 170 registers
+    cudaError_t e = cudaFuncSetAttribute(mcmc_ws_kernel<L, R, HG, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mcmc_ws_kernel<L, R, HG, 384><<<grid, wpb == 2 ? 256 : 96 * wpb, smem, st>>>(T, C, A);
     return cudaGetLastError();
 }
 
 cudaError_t launch_mcmc_ws(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms) {
     if (!T.canonical || !T.div_safe || T.R < 1 || T.R > 8 || T.S < 1) return cudaErrorNotSupported;
     const bool hg = T.r[T.R - 1].has_gamma != 0;
+    // the consumer publishes 24 sigma_index | 8 gamma_index << 16 in one word
+    for (int q = 0; q < T.R; ++q)
+        if (SPEC_ENT_BYTES * T.r[q].n_sigma >= 65536 || 8 * T.r[q].n_gamma >= 65536) return cudaErrorNotSupported;
 #define BCP_WS(l, r) \
     case r: return hg ? launch_ws_one<l, r, true>(T, C, A, st, sms) : launch_ws_one<l, r, false>(T, C, A, st, sms);
     switch (T.R) {          // L = smallest of 2, 4, 8 that holds one lane per restraint

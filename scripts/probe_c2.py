@@ -6,7 +6,7 @@ from biceps_b200 import engine, synthetic, precompute
 ens = synthetic.make_ensemble("C2", seed=0, n_lambda=8)
 tabs = precompute.build_tables(ens["energies"], ens["lambdas"], ens["restraints"])
 T = engine.DeviceTables(tabs, device=0)
-for kern in ("spec", "coop", "fast"):
+for kern in ("ws", "spec", "coop", "fast"):
     os.environ["BCP_KERNEL"] = kern
     for n_chains, n_steps in [(1024, 20000), (8192, 20000), (65536, 4000)]:
         lam = (np.arange(n_chains) % 8).astype(np.int32)
