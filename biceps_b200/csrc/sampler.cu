@@ -301,6 +301,30 @@ __global__ void build_layouts_kernel(const SamplerTables T, double* rec, double*
     if (flag) *bad = 1;
 }
 
+// lower bound of -log P of every state over all nuisance parameters (sampler_tab.cu rejects state-move proposals with it):
+// per restraint min over the sigma grid of Ndof ln sigma + m / 2 sigma^2 with m = min over gamma of the sse, plus the
+// state-dependent constants, minus a safety of 1e-9 (1 + sum of the magnitudes) -- rounding of either side is ~1e-16 relative
+__global__ void build_lb_kernel(const SamplerTables T, double* lb) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)T.K * T.S) return;
+    const int l = (int)(idx / T.S);
+    const long long i = idx - (long long)l * T.S;
+    double sum = T.energy[idx] + T.logZ[l];
+    double mag = fabs(T.energy[idx]) + fabs(T.logZ[l]);
+    for (int q = 0; q < T.R; ++q) {
+        const RestraintDev& rd = T.r[q];
+        double m = rd.sse[i * rd.n_gamma];
+        for (int g = 1; g < rd.n_gamma; ++g) m = fmin(m, rd.sse[i * rd.n_gamma + g]);
+        const double* sig = T.sig_tab + rd.sig_off;
+        double best = sig[0] + m / sig[rd.n_sigma];
+        for (int k = 1; k < rd.n_sigma; ++k) best = fmin(best, sig[k] + m / sig[rd.n_sigma + k]);
+        const double ref = rd.refsum ? rd.refsum[i] : 0.0;
+        sum += best + rd.cnorm - ref;
+        mag += fabs(best) + fabs(rd.cnorm) + fabs(ref);
+    }
+    lb[idx] = sum - 1e-9 * (1.0 + mag);
+}
+
 // K6 on the device-resident snapshots of a sample() call (bcp_chains_score): snapshot m of chain c is
 // sample pos0[c] + m of its lambda run (the chains of a run are concatenated, kln_to_kn order).  The
 // restraint terms do not depend on lambda: evaluated once, K energies written in
@@ -566,6 +590,15 @@ extern "C" int bcp_create(const bcp_tables* t, int device, bcp_handle** out) {
     }
     if ((rc = upload(h, t->energy, (size_t)T.K * T.S, &T.energy)) != BCP_OK) return fail(rc);
     if ((rc = upload(h, t->logZ, (size_t)T.K, &T.logZ)) != BCP_OK) return fail(rc);
+    T.lb = nullptr;
+    if (T.canonical && T.div_safe) {
+        double* d_lb = nullptr;
+        if (pool_alloc(&d_lb, (size_t)T.K * T.S, h->stream) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
+        h->allocs.push_back(d_lb);
+        build_lb_kernel<<<(unsigned)(((long long)T.K * T.S + 127) / 128), 128, 0, h->stream>>>(T, d_lb);
+        BCP_LAUNCHED(1);
+        T.lb = d_lb;
+    }
     if (pool_alloc(&h->d_energy_t, (size_t)T.K * T.S, h->stream) != cudaSuccess) { set_error("bcp_create: out of device memory"); return fail(BCP_ERR_CUDA); }
     h->allocs.push_back(h->d_energy_t);
     transpose_energy_kernel<<<(unsigned)(((long long)T.K * T.S + 255) / 256), 256, 0, h->stream>>>(T.energy, T.K, T.S, h->d_energy_t);
@@ -653,8 +686,8 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
     // both histograms in ONE block, state counts first: a multi-GPU caller all-reduces them with one collective
     TRY_CUDA(pool_alloc(&C.state_counts, (size_t)n_groups * ((size_t)T.S + T.HB)));
     C.param_counts = C.state_counts + (size_t)n_groups * T.S;
-    TRY_CUDA(pool_alloc(&C.spec_stats, 2));
-    TRY_CUDA(cudaMemset(C.spec_stats, 0, 2 * sizeof(unsigned long long)));
+    TRY_CUDA(pool_alloc(&C.spec_stats, 8));
+    TRY_CUDA(cudaMemset(C.spec_stats, 0, 8 * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.accepted, 0, n * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.sep, 0, (size_t)(T.R + 1) * n * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.state_counts, 0, (size_t)n_groups * T.S * sizeof(unsigned long long)));
@@ -788,7 +821,7 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
         if (which == 3 && n * lanes <= lim * sms * 32) which = 4;
     }
     if (kern && T.canonical)
-        which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : (!strcmp(kern, "ws") ? 4 : 2)));
+        which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : (!strcmp(kern, "ws") ? 4 : (!strcmp(kern, "tab") ? 5 : 2))));
     if (force && force[0] == '1') which = 0;
     int fgrid = grid, fblock = block;
     {                                                        // launch shape of the thread-per-chain kernel
@@ -822,7 +855,7 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     // 100-state ensemble with 16 chains per warp: 28 %).  Acceptance is a property of the ensemble, so a
     // long auto-selected run starts with a short pilot launch whose rollback fraction decides; the verdict
     // sticks to the chain block.  Every kernel produces the same bits, so this is invisible in the results.
-    const bool spec_auto = (which == 3 || which == 4) && !(kern && T.canonical) && T.pf.q < 0;
+    const bool spec_auto = (which == 3 || which == 4 || which == 5) && !(kern && T.canonical) && T.pf.q < 0;
     if (spec_auto && c->spec_verdict < 0) which = 1;
     const long long pilot = (spec_auto && c->spec_verdict == 0 && total >= 8192) ? 1024 : 0;
     for (long long s0 = 0, s1 = 0; s0 < total; s0 = s1) {
@@ -848,6 +881,12 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
             const char* pk = getenv("BCP_PF_KERNEL");
             e = (pk && !strcmp(pk, "generic")) ? cudaErrorNotSupported : launch_mcmc_pf2(T, c->C, A, st);
             if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_pf(T, c->C, A, st); }
+        }
+        else if (which == 5) {
+            e = launch_mcmc_tab(T, c->C, A, st);
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_ws(T, c->C, A, st, sms); }
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_spec(T, c->C, A, st, sms); }
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); }
         }
         else if (which == 4) {
             e = launch_mcmc_ws(T, c->C, A, st, sms);
@@ -938,6 +977,12 @@ extern "C" int bcp_chains_sync(bcp_chains* c) {
     BCP_REQUIRE(c, "bcp_chains_sync: NULL argument");
     DeviceGuard guard(c->h->device);
     BCP_CUDA(cudaStreamSynchronize(c->last_stream));
+    if (getenv("BCP_SPEC_STATS")) {       // diagnostics: batches run / rolled back by the speculative kernels so far
+        unsigned long long stats[8] = {0};
+        BCP_CUDA(cudaMemcpy(stats, c->C.spec_stats, sizeof(stats), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "bcp spec stats: %llu batches, %llu rolled back (guard band %llu, window %llu, state move %llu)\n", stats[0], stats[1],
+                stats[2], stats[3], stats[4]);
+    }
     return BCP_OK;
 }
 

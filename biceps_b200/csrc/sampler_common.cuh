@@ -101,6 +101,9 @@ cudaError_t launch_mcmc_spec(const SamplerTables& T, const ChainBuffers& C, cons
 // warp-specialised speculative kernel (sampler_ws.cu): the spec kernel's critical path in a consumer warp, Philox /
 // prefetch / histogram bookkeeping in a producer warp; same qualification rules as launch_mcmc_spec
 cudaError_t launch_mcmc_ws(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st, int sms);
+// table-driven kernel (sampler_tab.cu): one thread per chain on per-chain tables of the restraint terms, helper warps for
+// everything else; canonical layouts with at most four scalar restraints, grids of at least 32 values
+cudaError_t launch_mcmc_tab(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st);
 // warp-per-chain kernel for ensembles with a PFGRID restraint (sampler_pf.cu); any layout
 cudaError_t launch_mcmc_pf(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st);
 // tuned variant for scalar restraints + one PFGRID restraint (sampler_pf2.cu); cudaErrorNotSupported otherwise

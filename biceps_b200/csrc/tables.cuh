@@ -74,6 +74,9 @@ struct SamplerTables {
     int pad2;
     int rec_stride;         // 2 * R doubles
     int canonical;          // 1 if the specialised kernel applies
+    // table-driven kernel (sampler_tab.cu): lb[l][i] <= -log P(state i, any nuisance parameters) under lambda l, minus a
+    // safety far above the rounding of either side (canonical layouts with div_safe only, else nullptr)
+    const double* lb;       // [K][S]
 };
 
 const SamplerTables& handle_tables(const bcp_handle* h);
