@@ -31,6 +31,7 @@
 //                  snapshots (the batches are cut so that a snapshot is the last step of its batch).
 //   (warp 4 exits: it would share the consumer's SM sub-partition.)
 // Same RNG stream, same fp64 operation order, same outputs as every other Metropolis kernel (bit for bit).
+#include <type_traits>
 #include "spec_common.cuh"
 
 namespace bcp {
@@ -48,8 +49,11 @@ namespace tabk {
 #ifndef TAB_MRGMIN
 #define TAB_MRGMIN 4               // the tabulator extends a window when the walker is closer than this to its edge ...
 #endif
-#ifndef TAB_MRG
-#define TAB_MRG 6                  // ... to this distance
+#ifndef TAB_MRG_S
+#define TAB_MRG_S 9                // ... to this distance (scalar restraints: 32 slots, windows of up to 31 positions)
+#endif
+#ifndef TAB_MRG_N
+#define TAB_MRG_N 6                // ... (gamma restraint: 16 x 16 slots, windows of up to 15 x 15 positions)
 #endif
 // timing experiments only (scripts/tune_tab.sh): results are WRONG with any of these set
 #ifndef TAB_T_NOACC
@@ -58,8 +62,32 @@ namespace tabk {
 #ifndef TAB_T_NOTAB
 #define TAB_T_NOTAB 0              // the tabulator never extends a window; the consumer ignores the window check
 #endif
+#ifndef TAB_SPIN
+#define TAB_SPIN 0                 // 1: the consumer polls its barriers (test_wait) instead of try_wait; 2: every warp does
+#endif
+#ifndef TAB_DBG
+#define TAB_DBG 0                  // debugging: 1 no self-proposal shortcut, 2 the careful path evaluates every term exactly, 4 no lower-bound resolution
+#endif
+#ifndef TAB_INPLACE
+#define TAB_INPLACE 0              // 1: a proposal outside its tabulated window is evaluated in place (a vote per step); 0: the batch rolls back
+#endif
+#ifndef TAB_TRACE
+#define TAB_TRACE 0                // 1: CTA 0 records clock values of its warps' hand-offs for batches 1000 .. 1039 into spec_stats[8 ...]
+#endif
+#ifndef TAB_T_AFREE
+#define TAB_T_AFREE 0              // the accountants do not hold the ring's stages (they may read overwritten words)
+#endif
 #ifndef TAB_T_NOGEN
 #define TAB_T_NOGEN 0              // two Philox rounds instead of ten
+#endif
+#ifndef TAB_GU
+#define TAB_GU 2                   // unroll factor of the generators' step loop (2: two independent Philox chains in flight)
+#endif
+#ifndef TAB_NG
+#define TAB_NG 3                   // generator warps (3 or 4: warp 11 joins)
+#endif
+#ifndef TAB_CU
+#define TAB_CU 1                   // unroll factor of the consumer's step loop (1: the body stays in the 6 KB L0 instruction cache)
 #endif
 #ifndef TAB_STATS
 #define TAB_STATS 0                // 1: the consumer counts the reasons of its rollbacks into spec_stats[2..4] (diagnostics)
@@ -82,6 +110,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
         "@p bra TB_DONE_%=;\n"
         "bra TB_WAIT_%=;\n"
         "TB_DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+// the same as a polling loop (mbarrier.test_wait does not suspend the warp)
+__device__ __forceinline__ void mbar_spin(uint32_t a, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TB_SPIN_%=:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TB_SPUN_%=;\n"
+        "bra TB_SPIN_%=;\n"
+        "TB_SPUN_%=:\n"
         "}\n" ::"r"(a), "r"(parity)
         : "memory");
 }
@@ -123,21 +164,22 @@ struct TabCfg {
     static constexpr int BL = TAB_BL, NS = TAB_NS;
     static constexpr int RS = HG ? R - 1 : R;               // scalar restraints
     static constexpr int NF = RS + (HG ? 2 : 0);            // position fields: sigma of every restraint, then gamma
-    static constexpr int NE = RS * 16 + (HG ? 256 : 0);     // table entries per chain, stored [entry][chain]
+    static constexpr int NE = RS * 32 + (HG ? 256 : 0);     // table entries per chain, stored [entry][chain]
     // byte offsets inside a ring stage
     static constexpr int O_W = 0;                           // [BL][32] uint4 {delta scalars, delta gamma restraint, selector | r << 16, table offset}
     static constexpr int O_TX = O_W + BL * 512;             // [BL][32] double2 {ln u + margin | +inf, lb + ln u - 2 margin | +inf}
-    static constexpr int O_U = O_TX + BL * 512;             // [BL][32] double  Metropolis uniform (careful path)
-    static constexpr int O_DW = O_U + BL * 256;             // [BL][32] raw proposal word (accountant, careful path)
-    static constexpr int O_PS = O_DW + BL * 128;            // [32] packed positions after the batch     (consumer -> tabulator)
+    static constexpr int O_DW = O_TX + BL * 512;            // [BL][32] raw proposal word (accountant, careful path)
+    static constexpr int O_MK = O_DW + BL * 128;            // [4]{[32] uint4 + [32] u32}: the batch's proposal masks, one part per generator
+    static constexpr int O_PS = O_MK + 4 * (512 + 128);     // [32] packed positions after the batch     (consumer -> tabulator)
     static constexpr int O_PN = O_PS + 128;
     static constexpr int O_ACC = O_PN + 128;                // [32] accept bits | rebuilt << 16          (consumer -> helpers)
     static constexpr int O_E = O_ACC + 128;                 // [32] energy after the batch               (consumer -> accountant)
     static constexpr int STAGE = O_E + 256;
-    static_assert(BL == 8 && NS >= 2 && RS <= 4, "batch / ring / field shape");
+    static_assert(BL == 8 && NS >= 2 && RS <= 4 && TAB_MRGMIN <= TAB_MRG0, "batch / ring / field shape");
 };
 // raw proposal word: bit 31 nuisance move {bits 1:0 dsigma + 1, 3:2 dgamma + 1, 6:4 restraint}, else the proposed state;
-// packed positions: 7-bit fields in bytes (mod 128; a table slot is position & 15), scalars in bytes 0..RS-1 of the first
+// packed positions: 7-bit fields in bytes (mod 128; a table slot is position & 31 for a scalar restraint, & 15 in either
+// dimension of the gamma restraint), scalars in bytes 0..RS-1 of the first
 // word, the gamma restraint's sigma / gamma in bytes 0 / 1 of the second.
 
 // the batches of a launch: BL positions each, cut so that every snapshot step (and the last step) is the LAST position of
@@ -168,7 +210,7 @@ struct BatchIter {
 };
 
 template <int R, bool HG>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                 const __grid_constant__ LaunchArgs A) {
     using F = TabCfg<R, HG>;
@@ -183,9 +225,9 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            mbar_init(smem_u32(&bars[0][k]), 32);            // one generator warp
+            mbar_init(smem_u32(&bars[0][k]), 128);           // four generator warps
             mbar_init(smem_u32(&bars[1][k]), 32);            // consumer
-            mbar_init(smem_u32(&bars[2][k]), 96);            // tabulator + both accountants have copied the stage's words
+            mbar_init(smem_u32(&bars[2][k]), TAB_T_AFREE ? 32 : 160);           // tabulator + four accountants have copied the stage's words
         }
         mbar_init(smem_u32(&bars_tab[0]), 32);
         mbar_init(smem_u32(&bars_tab[1]), 32);
@@ -193,11 +235,16 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     stage_sigma_table(reinterpret_cast<double*>(smem_raw), T.sig4, T.sig4_bytes, &tma_bar);     // has the block barrier
-    if (warp == 4) return;
+    if (warp == 4 || warp == 8) return;                      // (they would share the consumer's SM sub-partition)
 
     const long long n = C.n_chains;
     long long c = (long long)blockIdx.x * 32 + lane;
     const bool live = c < n;                                 // dead lanes shadow the last chain, no stores
+    // (diagnostics) event e of warp `warp` at batch b: spec_stats[8 + ((b - 1000) * 12 + warp) * 4 + e]
+    auto trace = [&](int b, int e) {
+        if (TAB_TRACE && blockIdx.x == 0 && lane == 0 && b >= 1000 && b < 1040)
+            C.spec_stats[8 + ((b - 1000) * 12 + warp) * 4 + e] = (unsigned long long)clock64();
+    };
     if (!live) c = n - 1;
     const int lam = C.lam[c];
     const double* __restrict__ energy = T.energy + (size_t)lam * T.S;
@@ -230,7 +277,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     const uint32_t idxp0 = rect0 + 2u * 6u * 128u;                           // [2][R + 1][32] true indices after a batch
     const uint32_t q10 = idxp0 + 2u * (uint32_t)(R + 1) * 128u;              // 64 scalar cells to fill
     const uint32_t q20 = q10 + 256u;                                         // 64 row / column segments to fill
-    const uint32_t evq0 = q20 + 512u;                                        // BL x 64 histogram events
+    const uint32_t acc0 = q20 + 512u;                                        // accountants: [R + 1][16][32] histogram windows, 32 dummy words
     const uint32_t lane8 = 8u * (uint32_t)lane, lane4 = 4u * (uint32_t)lane;
     auto ring_of = [&](int stage) { return ring0 + (uint32_t)stage * (uint32_t)F::STAGE; };
     const uint32_t b_full = smem_u32(&bars[0][0]), b_empty = smem_u32(&bars[1][0]), b_free = smem_u32(&bars[2][0]);
@@ -250,8 +297,8 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         if (k == 0) t = __dadd_rn(t, lds64(cst0 + 8u * (uint32_t)L));
         return t;
     };
-    auto cell_addr = [&](int L, int k, int slot) {           // slot: position & 15, or (sigma & 15) | (gamma & 15) << 4
-        const int e = (HG && k == QG) ? 16 * RS + slot : 16 * k + slot;
+    auto cell_addr = [&](int L, int k, int slot) {           // slot: position & 31, or (sigma & 15) | (gamma & 15) << 4
+        const int e = (HG && k == QG) ? 32 * RS + slot : 32 * k + slot;
         return tab0 + (uint32_t)e * 256u + 8u * (uint32_t)L;
     };
     // the windows of chain L around positions (ps, pn) whose true indices are idx[] / gi: all lanes of the warp
@@ -265,7 +312,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 int ik = 0;
 #pragma unroll
                 for (int q = 0; q < RS; ++q) ik = q == k ? idx[q] : ik;
-                sts64d(cell_addr(L, k, (p + d) & 15), cell_value(L, k, wrap1(ik + d, T.r[k].n_sigma), 0));
+                sts64d(cell_addr(L, k, (p + d) & 31), cell_value(L, k, wrap1(ik + d, T.r[k].n_sigma), 0));
             } else if (HG) {
                 const int e2 = e - RS * W0;
                 const int dg = e2 / W0 - TAB_MRG0, dp = e2 - (e2 / W0) * W0 - TAB_MRG0;
@@ -284,11 +331,12 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             for (int k = lane; k < GS; k += 32) sts64d(row0 + ((uint32_t)L * (uint32_t)GS + (uint32_t)k) * 8u, gh4[(size_t)st * GS + k]);
     };
 
-    if (warp >= 1 && warp <= 3) {
+    if ((warp >= 1 && warp <= 3) || warp == 11) {
         // =====================================================================================
-        // generators: Philox + decode, batch b by generator b % 3
+        // generators: Philox + decode.  EVERY batch is generated by all four warps, two steps each: what the ring's depth has to
+        // cover is the latency of a batch, not the throughput
         // =====================================================================================
-        const int g = warp - 1;
+        const int g = warp == 11 ? 3 : warp - 1;
         const unsigned long long chain_id = C.chain_id0 + (unsigned long long)c;
         const uint32_t S = (uint32_t)T.S;
         const uint32_t thresh = T.nuis_thresh;
@@ -304,19 +352,25 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             asm volatile("" : "+r"(rk0[i]), "+r"(rk1[i]));
         }
         const double inf = __longlong_as_double(0x7ff0000000000000ll);
-        for (int b = 0, bg = 0; !it.done(); ++b, it.advance(), bg = bg == 2 ? 0 : bg + 1) {
-            if (bg != g) continue;
+        for (int b = 0; !it.done(); ++b, it.advance()) {
             const int stage = b % NS, fill = b / NS;
-            if (fill >= 1) mbar_wait(b_free + 8u * (uint32_t)stage, (uint32_t)(fill - 1) & 1u);
+            trace(b, 0);
+            if (fill >= 1) { if (TAB_SPIN >= 2) mbar_spin(b_free + 8u * (uint32_t)stage, (uint32_t)(fill - 1) & 1u); else mbar_wait(b_free + 8u * (uint32_t)stage, (uint32_t)(fill - 1) & 1u); }
+            trace(b, 1);
             int s0, pad;
             bool snap_last;
             it.get(s0, pad, snap_last);
             const uint32_t rs = ring_of(stage);
-            // all BL steps into registers first (the lower-bound gathers of the state moves are in flight together), then the stores
-            uint32_t g_ds[BL], g_dn[BL], g_sel[BL], g_off[BL], g_dw[BL];
-            double g_th[BL], g_xs[BL], g_lu[BL], g_u[BL];
+            // a ROLLED loop over the steps (the body stays in the instruction cache; the helper warps of an SM run five different
+            // code paths): the lower-bound gather of step j is issued in iteration j and consumed in iteration j + 1
+            // the batch's proposals as masks (bit 8 r + j: step j proposes a move of restraint r < 4): any nuisance move / a non-null
+            // sigma move / its direction; m_g: non-null gamma moves, their directions << 8, state moves << 16, real positions << 24;
+            // m_4: the same three masks of restraint 4 in bits 0-7, 8-15, 16-23
+            uint32_t m_nm = 0, m_fm = 0, m_up = 0, m_g = 0, m_4 = 0;
+            double p_th = inf, p_lb = inf, p_lu = inf;       // step j - 1: threshold, gathered lower bound, ln u - 2 margin
 #pragma unroll
-            for (int j = 0; j < BL; ++j) {
+            for (int jj = 0; jj < BL / 4; ++jj) {
+                const int j = (BL / 4) * g + jj;
                 const bool real = j >= pad;
                 const int s = real ? s0 + j - pad : s0;
                 const unsigned long long ctr = ctr0 + (unsigned long long)(long long)s;
@@ -332,6 +386,9 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 const bool nuis = pc0 < thresh;
                 const uint64_t pr = (uint64_t)pc1 * (nuis ? (uint32_t)R : S);
                 const uint32_t hi = (uint32_t)(pr >> 32);
+                const bool nu = real && nuis, sm = real && !nuis;
+                // lb + ln u - 2 margin for a state move (the gather is issued for every lane: L2-resident table)
+                const double lbv = __ldg(lb + (sm ? hi : 0u));
                 const uint64_t z1 = (uint64_t)(uint32_t)pr * 3u;
                 const uint64_t z2 = (uint64_t)(uint32_t)z1 * 3u;
                 const uint32_t a = (uint32_t)(z1 >> 32);                                     // dsigma + 1
@@ -342,33 +399,45 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 const double lud = u < 4.656612873077393e-10 ? __longlong_as_double(0x7ff8000000000000ll)
                                                              : __dmul_rn((double)__log2f((float)u), 0.6931471805599453);
                 // branch-free step words; a state move and a padding position leave the chain where it is on the fast path
-                const bool nu = real && nuis, sm = real && !nuis;
                 const bool scal = !HG || hi < (uint32_t)RS;
                 const uint32_t cs = (a - 1u) & 127u, cg = (bb - 1u) & 127u;
-                g_ds[j] = (nu && scal) ? cs << (8u * (hi & 3u)) : 0u;
-                g_dn[j] = (nu && !scal) ? (cs | (cg << 8)) : 0u;
-                g_sel[j] = nu ? ((scal ? (0x7760u | hi) : 0x7754u) | (hi << 16)) : (0x7760u | (7u << 16));
-                g_off[j] = nu ? (scal ? hi : (uint32_t)RS) * 4096u : 0u;
-                g_dw[j] = !real ? TAB_PAD : (nuis ? (0x80000000u | (hi << 4) | (bb << 2) | a) : hi);
-                g_th[j] = nu ? __dadd_rn(lud, TAB_MARGIN) : inf;
-                // lb + ln u - 2 margin for a state move (the gather is issued for every lane: L2-resident table)
-                g_xs[j] = __ldg(lb + (sm ? hi : 0u));
-                g_lu[j] = sm ? __dsub_rn(lud, 2.0 * TAB_MARGIN) : inf;
-                g_u[j] = real ? u : 1.0;
+                const uint32_t w_ds = (nu && scal) ? cs << (8u * (hi & 3u)) : 0u;
+                const uint32_t w_dn = (nu && !scal) ? (cs | (cg << 8)) : 0u;
+                const uint32_t w_sel = nu ? ((scal ? (0x00107760u | hi) : 0x7754u) | (hi << 16)) : (0x00107760u | (7u << 16));   // bit 20: 32-slot table
+                const uint32_t w_off = nu ? (scal ? hi : (uint32_t)RS) * 8192u : 0u;
+                const uint32_t w_dw = !real ? TAB_PAD : (nuis ? (0x80000000u | (hi << 4) | (bb << 2) | a) : hi);
+                sts128u(rs + F::O_W + 512u * (uint32_t)j + 16u * (uint32_t)lane, w_ds, w_dn, w_sel, w_off);
+                sts32(rs + F::O_DW + 128u * (uint32_t)j + lane4, w_dw);
+                {
+                    // bit 8 r + j of m_nm / m_fm / m_up: step j proposes a move / a non-null sigma move / an upward one of restraint
+                    // r < 4; m_g: non-null gamma proposals, their directions << 8, state-move proposals << 16; m_4: the three
+                    // masks of restraint 4 in bits 0-7, 8-15, 16-23
+                    const bool lo4 = R <= 4 || hi < 4u;
+                    const uint32_t bit = 1u << (8u * (hi & 3u) + (uint32_t)j), bj = 1u << j;
+                    m_nm |= (nu && lo4) ? bit : 0u;
+                    m_fm |= (nu && lo4 && a != 1u) ? bit : 0u;
+                    m_up |= (nu && lo4 && a == 2u) ? bit : 0u;
+                    if (R > 4) m_4 |= (nu && !lo4) ? (bj | (a != 1u ? bj << 8 : 0u) | (a == 2u ? bj << 16 : 0u)) : 0u;
+                    m_g |= sm ? bj << 16 : 0u;
+                    if (HG) m_g |= (nu && hi == (uint32_t)QG) ? ((bb != 1u ? bj : 0u) | (bb == 2u ? bj << 8 : 0u)) : 0u;
+                }
+                // thresholds of the previous step (its gather has had an iteration to land), then this step's become pending
+                if (jj > 0) sts128(rs + F::O_TX + 512u * (uint32_t)(j - 1) + 16u * (uint32_t)lane, make_double2(p_th, __dadd_rn(p_lb, p_lu)));
+                p_th = nu ? __dadd_rn(lud, TAB_MARGIN) : inf;
+                p_lb = lbv;
+                p_lu = sm ? __dsub_rn(lud, 2.0 * TAB_MARGIN) : inf;
             }
-#pragma unroll
-            for (int j = 0; j < BL; ++j) {
-                sts128u(rs + F::O_W + 512u * (uint32_t)j + 16u * (uint32_t)lane, g_ds[j], g_dn[j], g_sel[j], g_off[j]);
-                sts128(rs + F::O_TX + 512u * (uint32_t)j + 16u * (uint32_t)lane, make_double2(g_th[j], __dadd_rn(g_xs[j], g_lu[j])));
-                sts64d(rs + F::O_U + 256u * (uint32_t)j + lane8, g_u[j]);
-                sts32(rs + F::O_DW + 128u * (uint32_t)j + lane4, g_dw[j]);
-            }
+            sts128(rs + F::O_TX + 512u * (uint32_t)((BL / 4) * g + BL / 4 - 1) + 16u * (uint32_t)lane, make_double2(p_th, __dadd_rn(p_lb, p_lu)));
+            // (the masks of this warp's two steps; the accountants OR the four parts)
+            sts128u(rs + F::O_MK + 640u * (uint32_t)g + 16u * (uint32_t)lane, m_nm, m_fm, m_up, m_g);
+            if (R > 4) sts32(rs + F::O_MK + 640u * (uint32_t)g + 512u + lane4, m_4);
+            trace(b, 2);
             mbar_arrive(b_full + 8u * (uint32_t)stage);
         }
         return;
     }
 
-    if (warp == 7) {
+    if (warp == 10) {
         // =====================================================================================
         // tabulator: keeps every chain's windows around its walkers
         // =====================================================================================
@@ -404,7 +473,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             __syncwarp();
             for (uint32_t i = (uint32_t)lane; i < n1; i += 32) {
                 const uint32_t w = lds32(q10 + 4u * i);
-                const int L = (int)(w & 31u), k = (int)((w >> 5) & 7u), slot = (int)((w >> 8) & 15u), ii = (int)(w >> 12);
+                const int L = (int)(w & 31u), k = (int)((w >> 5) & 7u), slot = (int)((w >> 8) & 31u), ii = (int)(w >> 13);
                 sts64d(cell_addr(L, k, slot), cell_value(L, k, ii, 0));
             }
             __syncwarp();
@@ -440,258 +509,294 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             if (n2 >= 32u) process2();
         };
 
+        constexpr uint32_t MS = 0x7f7f7f7fu, MN = 0x00007f7fu, HS = 0x80808080u, HN = 0x00008080u;
+        // packed per-field words: the published windows {-lo, 127 - width} and the trigger windows [lo + MRGMIN, hi - MRGMIN]
+        uint32_t nls, mgs, nln, mgn, tls, tgs, tln, tgn;
+        auto pack = [&]() {
+            nls = 0; mgs = 0; nln = 0; mgn = 0; tls = 0; tgs = 0; tln = 0; tgn = 0;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const uint32_t nl = (uint32_t)(-lo[f]) & 127u, mg = (uint32_t)(127 - (hi[f] - lo[f]));
+                const uint32_t tl = (uint32_t)(-(lo[f] + TAB_MRGMIN)) & 127u, tg = (uint32_t)(127 - (hi[f] - lo[f] - 2 * TAB_MRGMIN));
+                if (f < RS) { nls |= nl << (8 * f); mgs |= mg << (8 * f); tls |= tl << (8 * f); tgs |= tg << (8 * f); }
+                else { nln |= nl << (8 * (f - RS)); mgn |= mg << (8 * (f - RS)); tln |= tl << (8 * (f - RS)); tgn |= tg << (8 * (f - RS)); }
+            }
+#pragma unroll
+            for (int f = RS; f < 4; ++f) { mgs |= 127u << (8 * f); tgs |= 127u << (8 * f); }     // unused fields: position 0 in window [0, 0]
+            if (!HG) { mgn = 127u | (127u << 8); tgn = mgn; }
+        };
+        pack();
+        uint32_t ckps = 0u, ckpn = 0u;                       // the positions pfull / ifull belong to (a checkpoint, refreshed below)
+
         for (int b = 0; !it.done(); ++b, it.advance()) {
             const int stage = b % NS, fill = b / NS;
             const uint32_t rs = ring_of(stage);
-            mbar_wait(b_empty + 8u * (uint32_t)stage, (uint32_t)fill & 1u);
+            trace(b, 0);
+            if (TAB_SPIN >= 2) mbar_spin(b_empty + 8u * (uint32_t)stage, (uint32_t)fill & 1u); else mbar_wait(b_empty + 8u * (uint32_t)stage, (uint32_t)fill & 1u);
+            trace(b, 1);
             const uint32_t ps = lds32(rs + F::O_PS + lane4), pn = lds32(rs + F::O_PN + lane4);
             const bool reb = (lds32(rs + F::O_ACC + lane4) >> 16) & 1u;
             mbar_arrive(b_free + 8u * (uint32_t)stage);
-            int lo_n[NF > 0 ? NF : 1], hi_n[NF > 0 ? NF : 1];
             if (TAB_T_NOTAB) { mbar_arrive(b_tab + 8u * (uint32_t)(b & 1)); continue; }
+            // walkers that left their trigger window (packed test, like the consumer's), chains rebuilt by the careful path
+            const bool trig_s = reb || ((((ps + tls) & MS) + tgs) & HS) != 0u;
+            const bool trig_n = HG && (reb || ((((pn + tln) & MN) + tgn) & HN) != 0u);
+            const bool any_s = RS > 0 && __any_sync(SPEC_FULL, trig_s), any_n = HG && __any_sync(SPEC_FULL, trig_n);
+            if (any_s || any_n || (b & 3) == 3) {
+                // checkpoint: unwrapped positions and true indices at the end of this batch (at most 4 batches = 32 steps on)
 #pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                const uint32_t pm = f < RS ? (ps >> (8 * f)) & 127u : (pn >> (8 * (f - RS))) & 127u;
-                const int d = (int)((pm - (uint32_t)pfull[f] + 64u) & 127u) - 64;    // |d| <= BL
-                pfull[f] += d;
-                ifull[f] = wrap1(ifull[f] + d, nf[f]);
-                const int p = pfull[f];
-                int l = lo[f], h = hi[f];
-                if (reb) { l = p - TAB_MRG0; h = p + TAB_MRG0; lo[f] = l; hi[f] = h; }    // rebuilt by the consumer's careful path
-                else {
-                    // extend towards the walker; old and new window together span at most 16 positions, so a slot that the
-                    // consumer may still read (it works with the previous rectangle) is never rewritten
-                    if (hi[f] - p < TAB_MRGMIN) h = imax(hi[f], imin(p + TAB_MRG, lo[f] + 15));
-                    if (p - lo[f] < TAB_MRGMIN) l = imin(lo[f], imax(p - TAB_MRG, hi[f] - 15));
-                    if (h - l > 14) { if (p - l > h - p) l = h - 14; else h = l + 14; }
+                for (int f = 0; f < NF; ++f) {
+                    const uint32_t pm = f < RS ? (ps >> (8 * f)) & 127u : (pn >> (8 * (f - RS))) & 127u;
+                    const int d = (int)((pm - (uint32_t)pfull[f] + 64u) & 127u) - 64;
+                    pfull[f] += d;
+                    ifull[f] = wrap1(ifull[f] + d, nf[f]);
                 }
-                lo_n[f] = l; hi_n[f] = h;
+                ckps = ps; ckpn = pn;
             }
-            // ---- new cells: scalars ----
+            if (any_s || any_n) {
+                int lo_n[NF > 0 ? NF : 1], hi_n[NF > 0 ? NF : 1];
 #pragma unroll
-            for (int f = 0; f < RS; ++f) {
-                // positions hi+1 .. hi_n, then lo_n .. lo-1 (either range may be empty)
-                const int up0 = imax(hi[f] + 1, lo_n[f]), nup = imax(hi_n[f] - up0 + 1, 0);
-                const int dn1 = imin(lo[f] - 1, hi_n[f]), ndn = imax(dn1 - lo_n[f] + 1, 0);
-                const int cnt = nup + ndn;
-                for (int i = 0; __any_sync(SPEC_FULL, i < cnt); ++i) {
-                    const int q = i < nup ? up0 + i : lo_n[f] + (i - nup);
-                    const int ii = wrap1(ifull[f] + (q - pfull[f]), nf[f]);
-                    emit1(i < cnt, (uint32_t)lane | ((uint32_t)f << 5) | ((uint32_t)(q & 15) << 8) | ((uint32_t)ii << 12));
-                }
-            }
-            if (n1) process1();
-            // ---- new cells: the gamma restraint (new sigma columns over the new gamma range, new gamma rows over the new
-            //      sigma range; cells in both are filled twice with the same value) ----
-            if (HG) {
-                constexpr int fs = RS, fg = RS + 1;
-#pragma unroll
-                for (int dim = 0; dim < 2; ++dim) {
-                    const int ff = dim ? fg : fs, fv = dim ? fs : fg;          // fixed / varying field of a segment
-                    const int up0 = imax(hi[ff] + 1, lo_n[ff]), nup = imax(hi_n[ff] - up0 + 1, 0);
-                    const int dn1 = imin(lo[ff] - 1, hi_n[ff]), ndn = imax(dn1 - lo_n[ff] + 1, 0);
-                    const int cnt = nup + ndn;
-                    const int len = hi_n[fv] - lo_n[fv] + 1;                   // 1 .. 15
-                    const int vidx0 = wrap1(ifull[fv] + (lo_n[fv] - pfull[fv]), nf[fv]);
-                    for (int i = 0; __any_sync(SPEC_FULL, i < cnt); ++i) {
-                        const int q = i < nup ? up0 + i : lo_n[ff] + (i - nup);
-                        const int fi = wrap1(ifull[ff] + (q - pfull[ff]), nf[ff]);
-                        emit2(i < cnt, (uint32_t)lane | ((uint32_t)dim << 5) | ((uint32_t)(q & 15) << 6) | ((uint32_t)len << 10) | ((uint32_t)fi << 14),
-                              (uint32_t)(lo_n[fv] & 15) | ((uint32_t)vidx0 << 4));
+                for (int f = 0; f < NF; ++f) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int span = f < RS ? 31 : 15, mrg = f < RS ? TAB_MRG_S : TAB_MRG_N;     // slots - 1
+                    const int p = pfull[f];
+                    int l = lo[f], h = hi[f];
+                    if (reb) { l = p - TAB_MRG0; h = p + TAB_MRG0; lo[f] = l; hi[f] = h; }        // rebuilt by the consumer's careful path
+                    else {
+                        // extend towards the walker; old and new window together span at most `slots` positions, so a slot that the
+                        // consumer may still read (it works with the previous window) is never rewritten
+                        if (hi[f] - p < TAB_MRGMIN) h = imax(hi[f], imin(p + mrg, lo[f] + span));
+                        if (p - lo[f] < TAB_MRGMIN) l = imin(lo[f], imax(p - mrg, hi[f] - span));
+                        if (h - l > span - 1) { if (p - l > h - p) l = h - (span - 1); else h = l + (span - 1); }
                     }
+                    lo_n[f] = l; hi_n[f] = h;
                 }
-                if (n2) process2();
-            }
-            // ---- publish the rectangles (valid two batches on) and the true indices after this batch ----
-            uint32_t nls = 0, mgs = 0, nln = 0, mgn = 0;
+                // ---- new cells: scalars ----
+                if (any_s) {
 #pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                lo[f] = lo_n[f]; hi[f] = hi_n[f];
-                const uint32_t nl = (uint32_t)(-lo[f]) & 127u, mg = (uint32_t)(127 - (hi[f] - lo[f]));
-                if (f < RS) { nls |= nl << (8 * f); mgs |= mg << (8 * f); }
-                else { nln |= nl << (8 * (f - RS)); mgn |= mg << (8 * (f - RS)); }
-            }
+                    for (int f = 0; f < RS; ++f) {
+                        // positions hi+1 .. hi_n, then lo_n .. lo-1 (either range may be empty)
+                        const int up0 = imax(hi[f] + 1, lo_n[f]), nup = imax(hi_n[f] - up0 + 1, 0);
+                        const int dn1 = imin(lo[f] - 1, hi_n[f]), ndn = imax(dn1 - lo_n[f] + 1, 0);
+                        const int cnt = nup + ndn;
+                        for (int i = 0; __any_sync(SPEC_FULL, i < cnt); ++i) {
+                            const int q = i < nup ? up0 + i : lo_n[f] + (i - nup);
+                            const int ii = wrap1(ifull[f] + (q - pfull[f]), nf[f]);
+                            emit1(i < cnt, (uint32_t)lane | ((uint32_t)f << 5) | ((uint32_t)(q & 31) << 8) | ((uint32_t)ii << 13));
+                        }
+                    }
+                    if (n1) process1();
+                }
+                // ---- new cells: the gamma restraint (new sigma columns over the new gamma range, new gamma rows over the new
+                //      sigma range; cells in both are filled twice with the same value) ----
+                if (HG && any_n) {
+                    constexpr int fs = RS, fg = RS + 1;
 #pragma unroll
-            for (int f = RS; f < 4; ++f) mgs |= 127u << (8 * f);              // unused fields: position 0 in window [0, 0]
-            if (!HG) mgn = 127u | (127u << 8);
+                    for (int dim = 0; dim < 2; ++dim) {
+                        const int ff = dim ? fg : fs, fv = dim ? fs : fg;          // fixed / varying field of a segment
+                        const int up0 = imax(hi[ff] + 1, lo_n[ff]), nup = imax(hi_n[ff] - up0 + 1, 0);
+                        const int dn1 = imin(lo[ff] - 1, hi_n[ff]), ndn = imax(dn1 - lo_n[ff] + 1, 0);
+                        const int cnt = nup + ndn;
+                        const int len = hi_n[fv] - lo_n[fv] + 1;                   // 1 .. 15
+                        const int vidx0 = wrap1(ifull[fv] + (lo_n[fv] - pfull[fv]), nf[fv]);
+                        for (int i = 0; __any_sync(SPEC_FULL, i < cnt); ++i) {
+                            const int q = i < nup ? up0 + i : lo_n[ff] + (i - nup);
+                            const int fi = wrap1(ifull[ff] + (q - pfull[ff]), nf[ff]);
+                            emit2(i < cnt, (uint32_t)lane | ((uint32_t)dim << 5) | ((uint32_t)(q & 15) << 6) | ((uint32_t)len << 10) | ((uint32_t)fi << 14),
+                                  (uint32_t)(lo_n[fv] & 15) | ((uint32_t)vidx0 << 4));
+                        }
+                    }
+                    if (n2) process2();
+                }
+#pragma unroll
+                for (int f = 0; f < NF; ++f) { lo[f] = lo_n[f]; hi[f] = hi_n[f]; }
+                pack();
+            }
+            // ---- publish: the windows (valid two batches on), the checkpoint {positions, true indices} ----
             const uint32_t rb = rect0 + (uint32_t)(b & 1) * 768u + lane4;
             sts32(rb, nls); sts32(rb + 128u, mgs); sts32(rb + 256u, nln); sts32(rb + 384u, mgn);
-            sts32(rb + 512u, ps); sts32(rb + 640u, pn);                       // the positions the true indices below belong to
+            sts32(rb + 512u, ckps); sts32(rb + 640u, ckpn);
             const uint32_t ib = idxp0 + (uint32_t)(b & 1) * (uint32_t)(R + 1) * 128u + lane4;
 #pragma unroll
             for (int k = 0; k < R; ++k) sts32(ib + 128u * (uint32_t)k, (uint32_t)ifull[k]);
             if (HG) sts32(ib + 128u * (uint32_t)R, (uint32_t)ifull[NF - 1]);
+            trace(b, 2);
             mbar_arrive(b_tab + 8u * (uint32_t)(b & 1));
         }
         return;
     }
 
-    if (warp == 5 || warp == 6) {
+    if (warp == 5 || warp == 6 || warp == 7 || warp == 9) {
         // =====================================================================================
-        // accountants: the bookkeeping of the batches the consumer has finished.  Accountant p owns the batches b with
-        // b & 1 == p (events, state trace, snapshots) and only follows the indices through the other one's batches
+        // accountants: the bookkeeping of the batches the consumer has finished, split by PARAMETER over four warps (a
+        // single warp runs dependent integer code at ~0.2 instructions per cycle; the parameters are independent).  ONE code
+        // path for the four (the kernel's hot code has to stay small: the instruction caches of 128 SMs refill from L2):
+        // warp a follows the sigma index of restraint a in slot 0; slot 1 is the gamma index (warp 1) or the sigma index of
+        // restraint 4 (warp 2); warp 0 also keeps the conformational state, the state trace and the acceptance totals.
+        // An index and the start of its current run follow from the generator's proposal masks AND the accept bits.
         // =====================================================================================
-        const int ap = warp - 5;
-        const uint32_t evq = evq0 + (uint32_t)ap * (uint32_t)(BL * 64 * 8);
+        const int aw = warp == 9 ? 3 : warp - 5;
+        const bool has0 = aw < R, has1 = (aw == 1 && HG) || (aw == 2 && R > 4);
+        const int q0 = has0 ? aw : 0, q1 = aw == 1 ? R : 4;               // parameter: restraint's sigma, or R = gamma
         const int grp = C.group[c];
         unsigned long long* g_state_counts = C.state_counts + (size_t)grp * T.S;
         unsigned long long* g_param_counts = C.param_counts + (size_t)grp * T.HB;
-        const bool tracing = A.state_trace != nullptr;
+        const bool tracing = aw == 0 && A.state_trace != nullptr;
         const bool traced = tracing && live && c < A.trace_n;
-        const uint32_t lane_lt = (1u << lane) - 1u;
-        const uint32_t bin0 = (uint32_t)grp * (uint32_t)T.HB;
-        int state = C.state[c];
-        int isg[R], since_sg[R];
-        unsigned int acc_r[R];
-        int igm = HG ? C.igm[(size_t)QG * n + c] : 0, since_gm = burn, since_state = burn;
-        unsigned int acc_state = 0, acc_total = 0;
+        // a window of 16 histogram bins per chain and parameter in shared memory ([parameter][bin][chain], private to the
+        // lane: plain read-modify-write): a chain keeps revisiting the same few bins
+        const uint32_t hwdummy = acc0 + (uint32_t)(R + 1) * 16u * 128u + lane4;
+        struct Slot { int idx, since, wb, nn; uint32_t hw; unsigned long long* bins; unsigned int acc; };
+        Slot sl[2];
+        sl[0].nn = T.r[q0].n_sigma; sl[0].bins = g_param_counts + T.r[q0].hist_sigma; sl[0].idx = C.isg[(size_t)q0 * n + c];
+        sl[1].nn = q1 == R ? G : T.r[R > 4 ? 4 : 0].n_sigma;
+        sl[1].bins = g_param_counts + (q1 == R ? T.r[QG].hist_gamma : T.r[R > 4 ? 4 : 0].hist_sigma);
+        sl[1].idx = q1 == R ? (HG ? C.igm[(size_t)QG * n + c] : 0) : C.isg[(size_t)(R > 4 ? 4 : 0) * n + c];
 #pragma unroll
-        for (int k = 0; k < R; ++k) { isg[k] = C.isg[(size_t)k * n + c]; since_sg[k] = burn; acc_r[k] = 0; }
+        for (int u = 0; u < 2; ++u) {
+            sl[u].since = burn; sl[u].acc = 0;
+            sl[u].hw = acc0 + (uint32_t)((u ? q1 : q0) * 16) * 128u + lane4;
+            sl[u].wb = sl[u].idx - 8; sl[u].wb += sl[u].wb < 0 ? sl[u].nn : 0;
+            if (u ? has1 : has0)
+                for (int bq = 0; bq < 16; ++bq) sts32(sl[u].hw + (uint32_t)bq * 128u, 0u);
+        }
+        int state = C.state[c], since_state = burn;
+        unsigned int acc_state = 0, acc_total = 0;
+        // the events of one parameter in a batch, in step order (most lanes have none or one): {bin, run length} into its
+        // window; a walker that has left the window flushes it first
+        auto events = [&](Slot& z, uint32_t m, uint32_t ups, int s0, int pad) {
+            while (__any_sync(SPEC_FULL, m != 0u)) {
+                const int j = __ffs((int)m) - 1;                             // -1 where the lane has no event left
+                const int s = s0 + j - pad;
+                const bool on = m != 0u, rec_on = s > burn;
+                const bool ev = on && rec_on && live && s > z.since;
+                int off = z.idx - z.wb;
+                off += off < 0 ? z.nn : 0;
+                const bool out = ev && (uint32_t)off >= 16u;
+                if (__any_sync(SPEC_FULL, out)) {
+                    if (out) {
+#pragma unroll 1
+                        for (int bq = 0; bq < 16; ++bq) {
+                            const uint32_t a = z.hw + (uint32_t)bq * 128u;
+                            const uint32_t v = lds32(a);
+                            if (v) {
+                                int gi = z.wb + bq;
+                                gi -= gi >= z.nn ? z.nn : 0;
+                                atomicAdd(z.bins + gi, (unsigned long long)v);
+                                sts32(a, 0u);
+                            }
+                        }
+                        z.wb = z.idx - 8;
+                        z.wb += z.wb < 0 ? z.nn : 0;
+                        off = 8;
+                    }
+                }
+                const uint32_t a = ev ? z.hw + (uint32_t)off * 128u : hwdummy;
+                sts32(a, lds32(a) + (uint32_t)(s - z.since));
+                z.idx = on ? wrap1(z.idx + (((ups >> j) & 1u) ? 1 : -1), z.nn) : z.idx;
+                z.since = (on && rec_on) ? s : z.since;
+                m &= m - 1u;
+            }
+        };
 
         for (int b = 0; !it.done(); ++b, it.advance()) {
             const int stage = b % NS, fill = b / NS;
             const uint32_t rs = ring_of(stage);
-            const bool mine = (b & 1) == ap;
             int s0, pad;
             bool snap_last;
             it.get(s0, pad, snap_last);
-            mbar_wait(b_empty + 8u * (uint32_t)stage, (uint32_t)fill & 1u);
-            uint32_t w_dw[BL];
+            trace(b, 0);
+            if (TAB_SPIN >= 2) mbar_spin(b_empty + 8u * (uint32_t)stage, (uint32_t)fill & 1u); else mbar_wait(b_empty + 8u * (uint32_t)stage, (uint32_t)fill & 1u);
+            trace(b, 1);
+            uint4 mk = lds128u(rs + F::O_MK + 16u * (uint32_t)lane);
+            uint32_t mk4 = R > 4 ? lds32(rs + F::O_MK + 512u + lane4) : 0u;
 #pragma unroll
-            for (int j = 0; j < BL; ++j) w_dw[j] = lds32(rs + F::O_DW + 128u * (uint32_t)j + lane4);
-            const uint32_t accb = lds32(rs + F::O_ACC + lane4);
+            for (int gq = 1; gq < 4; ++gq) {
+                const uint4 v = lds128u(rs + F::O_MK + 640u * (uint32_t)gq + 16u * (uint32_t)lane);
+                mk.x |= v.x; mk.y |= v.y; mk.z |= v.z; mk.w |= v.w;
+                if (R > 4) mk4 |= lds32(rs + F::O_MK + 640u * (uint32_t)gq + 512u + lane4);
+            }
+            const uint32_t accb = lds32(rs + F::O_ACC + lane4) & 0xffu;
             const double E_end = lds64(rs + F::O_E + lane8);
-            mbar_arrive(b_free + 8u * (uint32_t)stage);
+            // accepted state moves (rare on large ensembles), the optional state trace: the raw proposal words are needed
+            const uint32_t stm = aw == 0 ? (mk.w >> 16) & accb : 0u;
+            const bool need_dw = aw == 0 && (tracing || __any_sync(SPEC_FULL, stm != 0u));
+            uint32_t w_dw[BL];
+            if (need_dw) {
+#pragma unroll
+                for (int j = 0; j < BL; ++j) w_dw[j] = lds32(rs + F::O_DW + 128u * (uint32_t)j + lane4);
+            }
+            if (!TAB_T_AFREE) mbar_arrive(b_free + 8u * (uint32_t)stage);
             if (TAB_T_NOACC) continue;
-            uint32_t evn = 0;
-            // (1) one pass over the steps: per restraint the steps with an accepted non-null sigma move (8 bits each) and their
-            //     directions, the same for gamma, the accepted state moves, the acceptance counters
-            uint32_t fm = 0, up = 0, fm4 = 0, up4 = 0, fmg = 0, upg = 0, stm = 0, accp = 0, acc4 = 0, acct = 0;
-#pragma unroll
-            for (int j = 0; j < BL; ++j) {
-                const uint32_t dw = w_dw[j];
-                const uint32_t acc = (dw != TAB_PAD) ? (accb >> j) & 1u : 0u;
-                const uint32_t an = acc & (dw >> 31);
-                const uint32_t r = (dw >> 4) & 7u, cs = dw & 3u, cg = (dw >> 2) & 3u;
-                acct += acc;
-                stm |= (acc & ~(dw >> 31) & 1u) << j;
-                const uint32_t es = an & (cs != 1u ? 1u : 0u), us = an & (cs == 2u ? 1u : 0u);
-                if (R <= 4) {
-                    accp += an << (8u * (r & 3u));
-                    fm |= es << (8u * (r & 3u) + (uint32_t)j);
-                    up |= us << (8u * (r & 3u) + (uint32_t)j);
-                } else {
-                    const uint32_t lo4 = r < 4u ? 1u : 0u;
-                    accp += (an & lo4) << (8u * (r & 3u));
-                    fm |= (es & lo4) << (8u * (r & 3u) + (uint32_t)j);
-                    up |= (us & lo4) << (8u * (r & 3u) + (uint32_t)j);
-                    acc4 += an & (lo4 ^ 1u);
-                    fm4 |= (es & (lo4 ^ 1u)) << j;
-                    up4 |= (us & (lo4 ^ 1u)) << j;
-                }
-                if (HG) {
-                    const uint32_t eg = an & (r == (uint32_t)QG ? 1u : 0u);
-                    fmg |= (eg & (cg != 1u ? 1u : 0u)) << j;
-                    upg |= (eg & (cg == 2u ? 1u : 0u)) << j;
+            const uint32_t accrep = accb * 0x01010101u;
+            if (aw == 0) acc_total += (unsigned int)__popc(accb);
+            if (has0) {
+                sl[0].acc += (unsigned int)__popc(((mk.x & accrep) >> (8 * q0)) & 0xffu);
+                events(sl[0], ((mk.y & accrep) >> (8 * q0)) & 0xffu, (mk.z >> (8 * q0)) & 0xffu, s0, pad);
+            }
+            if (has1) {
+                if (q1 == R) events(sl[1], mk.w & accb, (mk.w >> 8) & 0xffu, s0, pad);
+                else {
+                    sl[1].acc += (unsigned int)__popc(mk4 & accb);
+                    events(sl[1], (mk4 >> 8) & accb, (mk4 >> 16) & 0xffu, s0, pad);
                 }
             }
-            if (mine) {
-                acc_total += acct;
-#pragma unroll
-                for (int k = 0; k < R; ++k) acc_r[k] += k < 4 ? (accp >> (8 * k)) & 0xffu : acc4;
-            }
-            // (2) per parameter: its events in step order (most lanes have none or one per batch).  A batch of the other
-            //     accountant only moves the index and the start of the current run.
-            auto events = [&](uint32_t mask, uint32_t ups, int& idx, int& since, int nn, uint32_t binbase) {
-                if (!mine) {
-                    if (mask) {
-                        const int net = 2 * __popc(mask & ups) - __popc(mask);       // |net| <= 8 < grid length
-                        idx = wrap1(idx + net, nn);
-                        const int s = s0 + (31 - __clz((int)mask)) - pad;
-                        since = s > burn ? s : since;
-                    }
-                    return;
-                }
-                while (__any_sync(SPEC_FULL, mask != 0u)) {
-                    const int j = __ffs((int)mask) - 1;                     // -1 where the lane has no event left
-                    const int s = s0 + j - pad;
-                    const bool on = mask != 0u, rec_on = s > burn;
-                    const int cnt = (on && rec_on && live) ? s - since : 0;
-                    const uint32_t bin = binbase + (uint32_t)idx;
-                    if (on) {
-                        idx = wrap1(idx + (((ups >> j) & 1u) ? 1 : -1), nn);
-                        since = rec_on ? s : since;
-                    }
-                    const bool ev = cnt > 0;
-                    const uint32_t m = __ballot_sync(SPEC_FULL, ev);
-                    if (ev) sts64u(evq + 8u * (evn + (uint32_t)__popc(m & lane_lt)), bin, (uint32_t)cnt);
-                    evn += (uint32_t)__popc(m);
-                    mask &= mask - 1u;
-                }
-            };
-#pragma unroll
-            for (int k = 0; k < R; ++k)
-                events(k < 4 ? (fm >> (8 * k)) & 0xffu : fm4, k < 4 ? (up >> (8 * k)) & 0xffu : up4, isg[k], since_sg[k], T.r[k].n_sigma,
-                       bin0 + (uint32_t)T.r[k].hist_sigma);
-            if (HG) events(fmg, upg, igm, since_gm, G, bin0 + (uint32_t)T.r[QG].hist_gamma);
-            // (3) accepted state moves (rare on large ensembles) and the optional state trace, in step order
-            if ((mine && tracing) || __any_sync(SPEC_FULL, stm != 0u)) {
+            // accepted state moves and the optional state trace, in step order
+            if (need_dw) {
 #pragma unroll
                 for (int j = 0; j < BL; ++j) {
                     const uint32_t dw = w_dw[j];
                     const int s = s0 + j - pad;
                     if ((stm >> j) & 1u) {
-                        if (mine) ++acc_state;
+                        ++acc_state;
                         const int i2 = (int)dw;
                         if (i2 != state) {
                             const bool rec_on = s > burn;
-                            if (mine && rec_on && live) atomicAdd(g_state_counts + state, (unsigned long long)(s - since_state));
+                            if (rec_on && live) atomicAdd(g_state_counts + state, (unsigned long long)(s - since_state));
                             if (rec_on) since_state = s;
                             state = i2;
                         }
                     }
-                    if (mine && traced && dw != TAB_PAD && s >= burn) A.state_trace[(size_t)(A.s_begin + s - A.burn) * A.trace_n + c] = state;
+                    if (traced && dw != TAB_PAD && s >= burn) A.state_trace[(size_t)(A.s_begin + s - A.burn) * A.trace_n + c] = state;
                 }
             }
-            if (!mine) { if (snap_last) ++snap_idx; continue; }
-            __syncwarp();
-            for (uint32_t k = (uint32_t)lane; k < evn; k += 32) {
-                const uint2 e = lds64u(evq + 8u * k);
-                atomicAdd(C.param_counts + e.x, (unsigned long long)e.y);
-            }
-            __syncwarp();
+            trace(b, 2);
             if (snap_last) {
-                const size_t o = (size_t)snap_idx * n + c;
                 if (live) {
-                    A.traj_E[o] = E_end;
-                    A.traj_state[o] = state;
-                    A.traj_accept[o] = (unsigned char)((accb >> (BL - 1)) & 1u);
-#pragma unroll
-                    for (int k = 0; k < R; ++k) A.traj_idx[((size_t)snap_idx * T.P + k) * n + c] = isg[k];
-                    if (HG) A.traj_idx[((size_t)snap_idx * T.P + R) * n + c] = igm;
+                    const size_t o = (size_t)snap_idx * n + c;
+                    if (aw == 0) {
+                        A.traj_E[o] = E_end;
+                        A.traj_state[o] = state;
+                        A.traj_accept[o] = (unsigned char)((accb >> (BL - 1)) & 1u);
+                    }
+                    if (has0) A.traj_idx[((size_t)snap_idx * T.P + q0) * n + c] = sl[0].idx;
+                    if (has1) A.traj_idx[((size_t)snap_idx * T.P + q1) * n + c] = sl[1].idx;
                 }
                 ++snap_idx;
             }
         }
-        // ---- acceptance counters of the own batches; accountant 0 flushes the run-length counters and persists the chain
-        //      (E is persisted by the consumer) ----
+        // ---- flush the run-length counters and the windows, persist the own part of the chain (E: the consumer) ----
         if (live) {
-            atomicAdd(C.accepted + c, (unsigned long long)acc_total);
-            atomicAdd(C.sep + (size_t)R * n + c, (unsigned long long)acc_state);
-#pragma unroll
-            for (int k = 0; k < R; ++k) atomicAdd(C.sep + (size_t)k * n + c, (unsigned long long)acc_r[k]);
-        }
-        if (live && ap == 0) {
-            if (s_end > since_state) atomicAdd(g_state_counts + state, (unsigned long long)(s_end - since_state));
-            C.state[c] = state;
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-                if (s_end > since_sg[k]) atomicAdd(g_param_counts + T.r[k].hist_sigma + isg[k], (unsigned long long)(s_end - since_sg[k]));
-                C.isg[(size_t)k * n + c] = isg[k];
+            if (aw == 0) {
+                if (s_end > since_state) atomicAdd(g_state_counts + state, (unsigned long long)(s_end - since_state));
+                C.state[c] = state;
+                C.accepted[c] += acc_total;
+                C.sep[(size_t)R * n + c] += acc_state;
             }
-            if (HG) {
-                if (s_end > since_gm) atomicAdd(g_param_counts + T.r[QG].hist_gamma + igm, (unsigned long long)(s_end - since_gm));
-                C.igm[(size_t)QG * n + c] = igm;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!(u ? has1 : has0)) continue;
+                Slot& z = sl[u];
+                const int q = u ? q1 : q0;
+                if (s_end > z.since) atomicAdd(z.bins + z.idx, (unsigned long long)(s_end - z.since));
+                for (int bq = 0; bq < 16; ++bq) {
+                    const uint32_t v = lds32(z.hw + (uint32_t)bq * 128u);
+                    int gi = z.wb + bq;
+                    gi -= gi >= z.nn ? z.nn : 0;
+                    if (v) atomicAdd(z.bins + gi, (unsigned long long)v);
+                }
+                if (q == R) C.igm[(size_t)QG * n + c] = z.idx;
+                else { C.isg[(size_t)q * n + c] = z.idx; C.sep[(size_t)q * n + c] += z.acc; }
             }
         }
         return;
@@ -707,6 +812,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
 #pragma unroll
     for (int k = 0; k < R; ++k) idx0[k] = C.isg[(size_t)k * n + c];
     const int gi0 = HG ? C.igm[(size_t)QG * n + c] : 0;
+    int cstate = C.state[c];                                 // the chain's conformational state (changes in the careful path only)
     unsigned int n_batches = 0, n_rollbacks = 0;
     const uint32_t tabl = tab0 + lane8;
     constexpr uint32_t MS = 0x7f7f7f7fu, MN = 0x00007f7fu;
@@ -716,6 +822,14 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     uint32_t ov_nls = 0, ov_mgs = 0, ov_nln = 0, ov_mgn = 0;  // windows of the chains the careful path has just rebuilt
     bool ov = false;
 
+    // the Metropolis uniform of local step s (the rare paths only: the ring does not carry it)
+    auto uniform_of = [&](int s) {
+        const unsigned long long chain_id = C.chain_id0 + (unsigned long long)c;
+        const unsigned long long ctr = A.step0 + (unsigned long long)A.s_begin + (unsigned long long)(long long)s;
+        const Philox4 w = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)chain_id, (uint32_t)(chain_id >> 32),
+                                        (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
+        return spec_u2(w.w2, w.w3);
+    };
     // exact terms of proposed state i2 at the chain's indices (restraint 0 carries energy + logZ), reference order
     auto eval_state = [&](int i2, const int* idx, int gi, double* xk) {
         const double C2 = __dadd_rn(energy[i2], logZ);
@@ -737,17 +851,47 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         return En;
     };
 
+    // true indices at packed positions (psj, pnj): the tabulator's checkpoint of parity buffer `par` (the launch's start if
+    // !have) plus the positions' progress since (at most 63 positions: checkpoints are at most 6 batches old)
+    auto true_indices = [&](bool have, int par, uint32_t psj, uint32_t pnj, int* idj, int& gj) {
+        uint32_t psb = 0u, pnb = 0u;
+        int gib = gi0;
+#pragma unroll
+        for (int k = 0; k < R; ++k) idj[k] = idx0[k];
+        if (have) {
+            const uint32_t rb = rect0 + (uint32_t)par * 768u + lane4;
+            const uint32_t ib = idxp0 + (uint32_t)par * (uint32_t)(R + 1) * 128u + lane4;
+            psb = lds32(rb + 512u); pnb = lds32(rb + 640u);
+#pragma unroll
+            for (int k = 0; k < R; ++k) idj[k] = (int)lds32(ib + 128u * (uint32_t)k);
+            if (HG) gib = (int)lds32(ib + 128u * (uint32_t)R);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const uint32_t pm = (HG && k == QG) ? (pnj & 127u) - (pnb & 127u) : ((psj >> (8 * k)) & 127u) - ((psb >> (8 * k)) & 127u);
+            idj[k] = wrap1(idj[k] + ((int)((pm + 64u) & 127u) - 64), T.r[k].n_sigma);
+        }
+        gj = HG ? wrap1(gib + ((int)(((((pnj >> 8) & 127u) - ((pnb >> 8) & 127u)) + 64u) & 127u) - 64), G) : 0;
+    };
+
     mbar_wait(b_tab + 16u, 0u);                               // the initial tables
 #pragma unroll
-    for (int k = 0; k < R; ++k) t[k] = lds64(tabl + (uint32_t)((HG && k == QG) ? 16 * RS : 16 * k) * 256u);
+    for (int k = 0; k < R; ++k) t[k] = lds64(tabl + (uint32_t)((HG && k == QG) ? 32 * RS : 32 * k) * 256u);
 
     for (int b = 0; !it.done(); ++b, it.advance()) {
         const int stage = b % NS, fill = b / NS;
         const uint32_t rs = ring_of(stage);
-        mbar_wait(b_full + 8u * (uint32_t)stage, (uint32_t)fill & 1u);
+        trace(b, 0);
+        if (TAB_SPIN >= 1) mbar_spin(b_full + 8u * (uint32_t)stage, (uint32_t)fill & 1u); else mbar_wait(b_full + 8u * (uint32_t)stage, (uint32_t)fill & 1u);
+        trace(b, 1);
+        int cs0, cpad;                                        // the batch's first real step and front padding (rare paths)
+        {
+            bool snap_last;
+            it.get(cs0, cpad, snap_last);
+        }
         uint32_t nls, mgs, nln, mgn;
         if (b >= 2) {
-            mbar_wait(b_tab + 8u * (uint32_t)(b & 1), (uint32_t)((b - 2) >> 1) & 1u);
+            if (TAB_SPIN >= 1) mbar_spin(b_tab + 8u * (uint32_t)(b & 1), (uint32_t)((b - 2) >> 1) & 1u); else mbar_wait(b_tab + 8u * (uint32_t)(b & 1), (uint32_t)((b - 2) >> 1) & 1u);
             const uint32_t rb = rect0 + (uint32_t)(b & 1) * 768u + lane4;
             nls = lds32(rb); mgs = lds32(rb + 128u); nln = lds32(rb + 256u); mgn = lds32(rb + 384u);
         } else {
@@ -758,6 +902,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         }
         if (ov) { nls = ov_nls; mgs = ov_mgs; nln = ov_nln; mgn = ov_mgn; }
         ov = false;
+        trace(b, 2);
 
         // ---- fast batch ----------------------------------------------------------------------------
         const double sv_E = E;
@@ -765,86 +910,86 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         double sv_t[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) sv_t[k] = t[k];
-        uint32_t accb = 0, why = 0, lbm = 0;
+        uint32_t accb = 0, why = 0;
         bool rare = false;
-        double Eh[BL];                                        // energy / positions BEFORE every step (SSA values kept alive: no instructions)
-        uint32_t Psh[BL], Pnh[BL];
-        uint4 wv[BL];
-        double2 tx[BL];
-#pragma unroll
+        // the lane's first state-move proposal of this batch that the lower bound cannot reject: step, energy and positions then
+        int jf = -1;
+        double Ef = 0.0;
+        uint32_t Psf = 0u, Pnf = 0u;
+        uint4 w = lds128u(rs + F::O_W + 16u * (uint32_t)lane);
+        double2 txv = lds128(rs + F::O_TX + 16u * (uint32_t)lane);
+        constexpr int CU = TAB_CU;
+#pragma unroll CU
         for (int j = 0; j < BL; ++j) {
-            wv[j] = lds128u(rs + F::O_W + 512u * (uint32_t)j + 16u * (uint32_t)lane);
-            tx[j] = lds128(rs + F::O_TX + 512u * (uint32_t)j + 16u * (uint32_t)lane);
-        }
-#pragma unroll
-        for (int j = 0; j < BL; ++j) {
-            const uint4 w = wv[j];
+            // (the next step's words are loaded a step ahead; the last iteration re-reads its own)
+            const uint32_t jn = (uint32_t)(j + 1 < BL ? j + 1 : j);
+            const uint4 wn = lds128u(rs + F::O_W + 512u * jn + 16u * (uint32_t)lane);
+            const double2 txn = lds128(rs + F::O_TX + 512u * jn + 16u * (uint32_t)lane);
             const uint32_t Ps2 = (Ps + w.x) & MS, Pn2 = (Pn + w.y) & MN;
             const uint32_t x = __byte_perm(Ps2, Pn2, w.z);
-            const uint32_t e = (x & 0xfu) | ((x >> 4) & 0xf0u);
-            const double tp = lds64(tabl + w.w + e * 256u);
-            const uint32_t bad = ((((Ps2 + nls) & MS) + mgs) & HS) | ((((Pn2 + nln) & MN) + mgn) & HN);
-            const int r = (int)(w.z >> 16);
+            const uint32_t e = (x & (0xfu | ((w.z >> 16) & 0x10u))) | ((x >> 4) & 0xf0u);
+            double tp = lds64(tabl + w.w + e * 256u);
+            const int r = (int)((w.z >> 16) & 7u);
+            // the proposal's position outside its tabulated window (a walker that outran the tabulator): the term is evaluated
+            // here, exactly like a table entry -- rare, and the batch goes on
+            const uint32_t bs = (((Ps2 + nls) & MS) + mgs) & HS, bn = (((Pn2 + nln) & MN) + mgn) & HN;
+            const bool bad = !TAB_T_NOTAB && (((w.z >> 20) & 1u) ? (((bs >> (8 * (r & 3))) & 0x80u) != 0u || ((TAB_DBG & 16) && r < R)) : (bn != 0u || (TAB_DBG & 8)));
+            if (TAB_INPLACE && __any_sync(SPEC_FULL, bad)) {
+                if (bad) {
+                    int idj[R], gj, ir = 0;
+                    true_indices(b >= 2, b & 1, Ps2, Pn2, idj, gj);
+#pragma unroll
+                    for (int k = 0; k < R; ++k) ir = r == k ? idj[k] : ir;
+                    tp = cell_value(lane, r, ir, gj);
+                }
+                if (TAB_STATS) why |= bad ? 2u : 0u;
+            }
             double xk[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) xk[k] = r == k ? tp : t[k];
             double En = xk[0];
 #pragma unroll
             for (int k = 1; k < R; ++k) En = __dadd_rn(En, xk[k]);
-            const double Ahi = __dsub_rn(E, tx[j].x), Alo = __dadd_rn(Ahi, 2.0 * TAB_MARGIN);
+            const double Ahi = __dsub_rn(E, txv.x), Alo = __dadd_rn(Ahi, 2.0 * TAB_MARGIN);
             const bool acc = En < Ahi;
             const bool unsure = !acc && !(En > Alo);                     // guard band, also NaN
-            rare = rare || unsure || (!TAB_T_NOTAB && bad != 0u);
-            lbm |= !(E < tx[j].y) ? (1u << j) : 0u;                       // a state move the lower bound cannot reject: resolved after the batch
-            Eh[j] = E; Psh[j] = Ps; Pnh[j] = Pn;
-            if (TAB_STATS) { why |= unsure ? 1u : 0u; why |= bad != 0u ? 2u : 0u; }
+            // a state move the lower bound cannot reject: the first one of a lane is resolved after the batch, a second one rolls back
+            const bool lbf = !(E < txv.y), first = lbf && jf < 0;
+            rare = rare || unsure || (lbf && (!first || (TAB_DBG & 4))) || (!TAB_INPLACE && bad);
+            if (TAB_STATS && !TAB_INPLACE) why |= bad ? 2u : 0u;
+            Ef = first ? E : Ef; Psf = first ? Ps : Psf; Pnf = first ? Pn : Pnf; jf = first ? j : jf;
+            if (TAB_STATS) why |= unsure ? 1u : 0u;
             E = acc ? En : E;
 #pragma unroll
             for (int k = 0; k < R; ++k) t[k] = acc ? xk[k] : t[k];
             Ps = acc ? Ps2 : Ps;
             Pn = acc ? Pn2 : Pn;
             accb |= acc ? (1u << j) : 0u;
+            w = wn; txv = txn;
         }
         ++n_batches;
         uint32_t rebw = 0;
-        if (!__any_sync(SPEC_FULL, rare) && __any_sync(SPEC_FULL, lbm != 0u)) {
+        if (!__any_sync(SPEC_FULL, rare) && __any_sync(SPEC_FULL, jf >= 0)) {
             // ---- state-move proposals the lower bound could not reject: evaluated exactly at the chain's indices of that step
-            //      (true indices = the tabulator's last publication + the positions' progress since); almost all are rejected
+            //      (true indices = the tabulator's last checkpoint + the positions' progress since); almost all are rejected
             //      and the batch stands ----
-            int idb[R], gib = gi0;
-            uint32_t psb = 0u, pnb = 0u;
-#pragma unroll
-            for (int k = 0; k < R; ++k) idb[k] = idx0[k];
-            if (b >= 2) {
-                const uint32_t rb = rect0 + (uint32_t)(b & 1) * 768u + lane4;
-                const uint32_t ib = idxp0 + (uint32_t)(b & 1) * (uint32_t)(R + 1) * 128u + lane4;
-                psb = lds32(rb + 512u); pnb = lds32(rb + 640u);
-#pragma unroll
-                for (int k = 0; k < R; ++k) idb[k] = (int)lds32(ib + 128u * (uint32_t)k);
-                if (HG) gib = (int)lds32(ib + 128u * (uint32_t)R);
-            }
-            while (__any_sync(SPEC_FULL, lbm != 0u)) {
-                const int j = __ffs((int)lbm) - 1;
-                if (lbm) {
-                    double Ej = Eh[0];
-                    uint32_t psj = Psh[0], pnj = Pnh[0];
-#pragma unroll
-                    for (int q = 1; q < BL; ++q) { Ej = j == q ? Eh[q] : Ej; psj = j == q ? Psh[q] : psj; pnj = j == q ? Pnh[q] : pnj; }
-                    int idj[R];
-#pragma unroll
-                    for (int k = 0; k < R; ++k) {
-                        const uint32_t pm = (HG && k == QG) ? (pnj & 127u) - (pnb & 127u) : ((psj >> (8 * k)) & 127u) - ((psb >> (8 * k)) & 127u);
-                        idj[k] = wrap1(idb[k] + ((int)((pm + 64u) & 127u) - 64), T.r[k].n_sigma);
-                    }
-                    const int gj = HG ? wrap1(gib + ((int)(((((pnj >> 8) & 127u) - ((pnb >> 8) & 127u)) + 64u) & 127u) - 64), G) : 0;
-                    const uint32_t dw = lds32(rs + F::O_DW + 128u * (uint32_t)j + lane4);
-                    const double u = lds64(rs + F::O_U + 256u * (uint32_t)j + lane8);
-                    double xk[R];
-                    const double En = eval_state((int)dw, idj, gj, xk);
-                    if ((En < Ej) || metropolis_accept(__dsub_rn(Ej, En), u)) rare = true;      // accepted after all: the careful path
-                    if (TAB_STATS) why |= 4u;
+            if (jf >= 0) {
+                int idj[R], gj;
+                true_indices(b >= 2, b & 1, Psf, Pnf, idj, gj);
+                const uint32_t dw = lds32(rs + F::O_DW + 128u * (uint32_t)jf + lane4);
+                const double u = uniform_of(cs0 + jf - cpad);
+                double xk[R];
+                const double En = eval_state((int)dw, idj, gj, xk);
+                const bool accf = (En < Ef) || metropolis_accept(__dsub_rn(Ef, En), u);
+                // the chain's own state proposed (1 / S of the state moves): accepted, and nothing changes but the counters
+                // (unless E is not the energy of the chain's configuration yet: the initial 1e99, an energy set by the caller)
+                if (accf && (int)dw == cstate && __double_as_longlong(En) == __double_as_longlong(Ef) && !(TAB_DBG & 1)) accb |= 1u << jf;
+                else if (accf) rare = true;                                                    // accepted after all: the careful path
+                if (TAB_STATS) {
+                    why |= 4u;
+                    atomicAdd(C.spec_stats + 5, 1ull);                                           // resolutions
+                    if (rare) atomicAdd(C.spec_stats + 6, 1ull);                                 // ... that found an accepted move to another state
                 }
-                lbm &= lbm - 1u;
             }
         }
         if (__any_sync(SPEC_FULL, rare)) {
@@ -862,76 +1007,76 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < R; ++k) t[k] = sv_t[k];
             accb = 0;
-            int idx[R], gi = gi0;
-#pragma unroll
-            for (int k = 0; k < R; ++k) idx[k] = idx0[k];
-            if (b >= 1) {
-                // the tabulator has finished batch b - 1 (and is now idle until this batch is published): its true indices
-                mbar_wait(b_tab + 8u * (uint32_t)((b - 1) & 1), (uint32_t)((b - 1) >> 1) & 1u);
-                const uint32_t ib = idxp0 + (uint32_t)((b - 1) & 1) * (uint32_t)(R + 1) * 128u + lane4;
-#pragma unroll
-                for (int k = 0; k < R; ++k) idx[k] = (int)lds32(ib + 128u * (uint32_t)k);
-                if (HG) gi = (int)lds32(ib + 128u * (uint32_t)R);
-            }
-            bool reb = false;
+            // the tabulator has finished batch b - 1 (and is now idle until this batch is published): the careful path may rebuild tables
+            if (b >= 1) mbar_wait(b_tab + 8u * (uint32_t)((b - 1) & 1), (uint32_t)((b - 1) >> 1) & 1u);
+            // the fast path's step with a vote after each test: whatever it cannot decide is evaluated exactly on the spot, for the
+            // lanes concerned (true indices = the tabulator's checkpoint + the positions' progress since)
+            bool reb = false;                                 // the lane's chain has changed its state in this batch: its tables are stale
 #pragma unroll 1
             for (int j = 0; j < BL; ++j) {
                 const uint32_t dw = lds32(rs + F::O_DW + 128u * (uint32_t)j + lane4);
-                const double u = lds64(rs + F::O_U + 256u * (uint32_t)j + lane8);
                 const uint4 w = lds128u(rs + F::O_W + 512u * (uint32_t)j + 16u * (uint32_t)lane);
                 const double2 txj = lds128(rs + F::O_TX + 512u * (uint32_t)j + 16u * (uint32_t)lane);
-                const bool realj = dw != TAB_PAD;
-                const bool nuis = (int)dw < 0;
-                const int r = (int)((dw >> 4) & 7u), ds = (int)(dw & 3u) - 1, dg = (int)((dw >> 2) & 3u) - 1;
-                double En = E;
-                double xk[R];
-                int inew = 0, gnew = gi;
-                bool acc = false;
-                if (realj && nuis) {
-                    int ik = 0;
+                const uint32_t Ps2 = (Ps + w.x) & MS, Pn2 = (Pn + w.y) & MN;
+                const uint32_t x = __byte_perm(Ps2, Pn2, w.z);
+                const uint32_t e = (x & (0xfu | ((w.z >> 16) & 0x10u))) | ((x >> 4) & 0xf0u);
+                double tp = lds64(tabl + w.w + e * 256u);
+                const int r = (int)((w.z >> 16) & 7u);
+                const uint32_t bs = (((Ps2 + nls) & MS) + mgs) & HS, bn = (((Pn2 + nln) & MN) + mgn) & HN;
+                const bool bad = r < R && ((TAB_DBG & 2) || reb || (((w.z >> 20) & 1u) ? ((bs >> (8 * (r & 3))) & 0x80u) != 0u : bn != 0u));
+                if (__any_sync(SPEC_FULL, bad)) {             // outside the tabulated window (or stale tables): the exact term
+                    if (bad) {
+                        int idj[R], gj, ir = 0;
+                        true_indices(b >= 1, (b - 1) & 1, Ps2, Pn2, idj, gj);
 #pragma unroll
-                    for (int k = 0; k < R; ++k) ik = r == k ? idx[k] : ik;
-                    inew = wrap1(ik + ds, T.r[r].n_sigma);
-                    if (HG && r == QG) gnew = wrap1(gi + dg, G);
-                    const double tp = cell_value(lane, r, inew, gnew);
-#pragma unroll
-                    for (int k = 0; k < R; ++k) xk[k] = r == k ? tp : t[k];
-                    En = xk[0];
-#pragma unroll
-                    for (int k = 1; k < R; ++k) En = __dadd_rn(En, xk[k]);
-                    acc = (En < E) || metropolis_accept(__dsub_rn(E, En), u);
-                }
-                // state moves: the lower bound rejects almost all of them; the others are evaluated exactly
-                const bool st_eval = realj && !nuis && !(E < txj.y);
-                if (__any_sync(SPEC_FULL, st_eval)) {
-                    if (st_eval) {
-                        En = eval_state((int)dw, idx, gi, xk);
-                        acc = (En < E) || metropolis_accept(__dsub_rn(E, En), u);
+                        for (int k = 0; k < R; ++k) ir = r == k ? idj[k] : ir;
+                        tp = cell_value(lane, r, ir, gj);
                     }
-                    // an accepted state move: the chain's record / gamma row in shared memory, its tables after the batch
-                    uint32_t m = __ballot_sync(SPEC_FULL, st_eval && acc);
+                }
+                double xk[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) xk[k] = r == k ? tp : t[k];
+                double En = xk[0];
+#pragma unroll
+                for (int k = 1; k < R; ++k) En = __dadd_rn(En, xk[k]);
+                const double Ahi = __dsub_rn(E, txj.x), Alo = __dadd_rn(Ahi, 2.0 * TAB_MARGIN);
+                bool acc = En < Ahi;
+                const bool unsure = !acc && !(En > Alo);
+                if (__any_sync(SPEC_FULL, unsure)) {          // inside the guard band: the specified exact rule
+                    if (unsure) acc = (En < E) || metropolis_accept(__dsub_rn(E, En), uniform_of(cs0 + j - cpad));
+                }
+                // a state move the lower bound cannot reject: evaluated exactly
+                const bool lbf = !(E < txj.y) && (int)dw >= 0 && dw != TAB_PAD;
+                if (__any_sync(SPEC_FULL, lbf)) {
+                    bool accst = false;
+                    if (lbf) {
+                        int idj[R], gj;
+                        true_indices(b >= 1, (b - 1) & 1, Ps, Pn, idj, gj);
+                        En = eval_state((int)dw, idj, gj, xk);
+                        acc = (En < E) || metropolis_accept(__dsub_rn(E, En), uniform_of(cs0 + j - cpad));
+                        accst = acc && (int)dw != cstate;     // (the chain's own state proposed: accepted, nothing changes)
+                    }
+                    // an accepted state move: the chain's record / gamma row in shared memory now, its tables after the batch
+                    uint32_t m = __ballot_sync(SPEC_FULL, accst);
                     while (m) {
                         const int L = __ffs((int)m) - 1;
                         m &= m - 1;
                         stage_state(L, __shfl_sync(SPEC_FULL, (int)dw, L), __shfl_sync(SPEC_FULL, lam, L));
                     }
-                    if (st_eval && acc) reb = true;
+                    if (accst) { reb = true; cstate = (int)dw; }
                     __syncwarp();
                 }
                 if (acc) {
                     E = En;
 #pragma unroll
                     for (int k = 0; k < R; ++k) t[k] = xk[k];
-                    if (nuis) {
-#pragma unroll
-                        for (int k = 0; k < R; ++k) idx[k] = r == k ? inew : idx[k];
-                        gi = gnew;
-                        Ps = (Ps + w.x) & MS;
-                        Pn = (Pn + w.y) & MN;
-                    }
+                    Ps = lbf ? Ps : Ps2;
+                    Pn = lbf ? Pn : Pn2;
                     accb |= 1u << j;
                 }
             }
+            int idx[R], gi;
+            true_indices(b >= 1, (b - 1) & 1, Ps, Pn, idx, gi);        // (the rebuild below)
             // rebuild the tables of the chains that changed their state, around their positions at the end of the batch
             uint32_t m = __ballot_sync(SPEC_FULL, reb);
             while (m) {
@@ -960,6 +1105,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         sts32(rs + F::O_PN + lane4, Pn);
         sts32(rs + F::O_ACC + lane4, accb | rebw);
         sts64d(rs + F::O_E + lane8, E);
+        trace(b, 3);
         mbar_arrive(b_empty + 8u * (uint32_t)stage);
     }
 
@@ -977,12 +1123,12 @@ static cudaError_t launch_tab_one(const SamplerTables& T, const ChainBuffers& C,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t smem = (size_t)T.sig4_bytes + (size_t)F::NE * 256 + (HG ? (size_t)32 * T.gh4_stride * 8 : 0) + (size_t)R * 512 + 256 +
-                        (size_t)F::NS * F::STAGE + 2 * 6 * 128 + 2 * (size_t)(R + 1) * 128 + 256 + 512 + 2 * (size_t)F::BL * 64 * 8 + 128;
+                        (size_t)F::NS * F::STAGE + 2 * 6 * 128 + 2 * (size_t)(R + 1) * 128 + 256 + 512 + ((size_t)(R + 1) * 16 * 128 + 128) + 128;
     if (smem + 1024 > (size_t)max_optin) return cudaErrorNotSupported;
     cudaError_t e = cudaFuncSetAttribute(mcmc_tab_kernel<R, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)((C.n_chains + 31) / 32);
-    mcmc_tab_kernel<R, HG><<<grid, 256, smem, st>>>(T, C, A);
+    mcmc_tab_kernel<R, HG><<<grid, 384, smem, st>>>(T, C, A);
     return cudaGetLastError();
 }
 

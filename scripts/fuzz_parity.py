@@ -48,6 +48,12 @@ for case in range(n_cases):
     want = cbind.sample(tabs, n, 7 + case, steps, chain_lambda=lam, n_threads=4, **kw)
     want2 = cbind.sample(tabs, n, 7 + case, 50, chain_lambda=lam, n_threads=4, step0=steps + burn, resume=want, traj_every=3)
     T = engine.DeviceTables(tabs)
+    ref3 = None
+    if os.environ.get("FUZZ_ONLY") and int(os.environ["FUZZ_ONLY"]) != case:
+        T.close()
+        continue
+    if os.environ.get("FUZZ_ONLY"):
+        print("case", case, "grids", [(len(r_["sigma"]), len(r_["grids"][0]) if r_["grids"] else 0) for r_ in rest], flush=True)
     for kern in kernels:
         if kern == "auto":
             os.environ.pop("BCP_KERNEL", None)
@@ -60,7 +66,7 @@ for case in range(n_cases):
             got2 = blk.sample(50, traj_every=3)               # second call continues the chains
             if big:                                           # ... and a third one on the kernel under test again
                 got3 = blk.sample(200, traj_every=40)
-                if kern == kernels[0]:
+                if ref3 is None:
                     ref3 = got3
                 else:
                     assert_outputs_equal(got3, ref3)
@@ -68,6 +74,14 @@ for case in range(n_cases):
             blk.close()
         except AssertionError as e:
             bad += 1
+            if os.environ.get("FUZZ_ONLY"):
+                for nm, (g_, w_) in (("call1", (got, want)), ("call2", (locals().get("got2"), want2))):
+                    if g_ is None:
+                        continue
+                    for k in w_:
+                        if not np.array_equal(g_[k], w_[k]):
+                            d = np.argwhere(np.asarray(g_[k]) != np.asarray(w_[k]))
+                            print("  ", kern, nm, k, "differs at", d[:6].tolist(), "got", np.asarray(g_[k])[tuple(d[0])], "want", np.asarray(w_[k])[tuple(d[0])], "n_diff", len(d))
             print("MISMATCH case %d kernel %s R=%d S=%d K=%d hg=%d flat=%d n=%d steps=%d burn=%d te=%d trace=%d: %s" % (
                 case, kern, R, S, K, hg, flat, n, steps, burn, te, trace, str(e)[:80]), flush=True)
     T.close()

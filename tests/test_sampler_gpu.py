@@ -8,10 +8,10 @@ from helpers import cineromycin_tables, stack_lambdas, assert_outputs_equal, loa
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["ws", "spec", "coop", "fast", "generic"], autouse=True)
+@pytest.fixture(params=["tab", "ws", "spec", "coop", "fast", "generic"], autouse=True)
 def kernel(request, monkeypatch):
-    """Every parity case runs through all Metropolis kernels (warp-specialised speculative, speculative cooperative, cooperative lanes-per-chain,
-    thread-per-chain specialised, generic); BCP_KERNEL is read at each launch."""
+    """Every parity case runs through all Metropolis kernels (table-driven, warp-specialised speculative, speculative cooperative,
+    cooperative lanes-per-chain, thread-per-chain specialised, generic); BCP_KERNEL is read at each launch."""
     monkeypatch.setenv("BCP_KERNEL", request.param)
     return request.param
 
