@@ -542,22 +542,27 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             const bool trig_s = reb || ((((ps + tls) & MS) + tgs) & HS) != 0u;
             const bool trig_n = HG && (reb || ((((pn + tln) & MN) + tgn) & HN) != 0u);
             const bool any_s = RS > 0 && __any_sync(SPEC_FULL, trig_s), any_n = HG && __any_sync(SPEC_FULL, trig_n);
-            if (any_s || any_n || (b & 3) == 3) {
+            // the scalar restraints and the gamma restraint are handled separately: with 32-slot windows the scalars rarely trigger
+            const bool per = (b & 3) == 3, do_s = any_s || (RS > 0 && per), do_n = any_n || (HG && per);
+            if (do_s || do_n) {
                 // checkpoint: unwrapped positions and true indices at the end of this batch (at most 4 batches = 32 steps on)
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
+                    if (!(f < RS ? do_s : do_n)) continue;
                     const uint32_t pm = f < RS ? (ps >> (8 * f)) & 127u : (pn >> (8 * (f - RS))) & 127u;
                     const int d = (int)((pm - (uint32_t)pfull[f] + 64u) & 127u) - 64;
                     pfull[f] += d;
                     ifull[f] = wrap1(ifull[f] + d, nf[f]);
                 }
-                ckps = ps; ckpn = pn;
+                if (do_s) ckps = ps;
+                if (do_n) ckpn = pn;
             }
             if (any_s || any_n) {
                 int lo_n[NF > 0 ? NF : 1], hi_n[NF > 0 ? NF : 1];
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
-                    constexpr int dummy = 0; (void)dummy;
+                    lo_n[f] = lo[f]; hi_n[f] = hi[f];
+                    if (!(f < RS ? any_s : any_n)) continue;
                     const int span = f < RS ? 31 : 15, mrg = f < RS ? TAB_MRG_S : TAB_MRG_N;     // slots - 1
                     const int p = pfull[f];
                     int l = lo[f], h = hi[f];
@@ -587,6 +592,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                     }
                     if (n1) process1();
                 }
+                trace(b, 3);
                 // ---- new cells: the gamma restraint (new sigma columns over the new gamma range, new gamma rows over the new
                 //      sigma range; cells in both are filled twice with the same value) ----
                 if (HG && any_n) {
@@ -664,38 +670,45 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         unsigned int acc_state = 0, acc_total = 0;
         // the events of one parameter in a batch, in step order (most lanes have none or one): {bin, run length} into its
         // window; a walker that has left the window flushes it first
-        auto events = [&](Slot& z, uint32_t m, uint32_t ups, int s0, int pad) {
-            while (__any_sync(SPEC_FULL, m != 0u)) {
-                const int j = __ffs((int)m) - 1;                             // -1 where the lane has no event left
-                const int s = s0 + j - pad;
-                const bool on = m != 0u, rec_on = s > burn;
-                const bool ev = on && rec_on && live && s > z.since;
-                int off = z.idx - z.wb;
-                off += off < 0 ? z.nn : 0;
-                const bool out = ev && (uint32_t)off >= 16u;
-                if (__any_sync(SPEC_FULL, out)) {
-                    if (out) {
+        // one event of a parameter: {bin, run length} into its window; a walker that has left the window flushes it first
+        auto event1 = [&](Slot& z, uint32_t& m, uint32_t ups, int s0, int pad) {
+            const int j = __ffs((int)m) - 1;                                 // -1 where the lane has no event left
+            const int s = s0 + j - pad;
+            const bool on = m != 0u, rec_on = s > burn;
+            const bool ev = on && rec_on && live && s > z.since;
+            int off = z.idx - z.wb;
+            off += off < 0 ? z.nn : 0;
+            if (ev && (uint32_t)off >= 16u) {                                // (rare, divergent: no vote)
 #pragma unroll 1
-                        for (int bq = 0; bq < 16; ++bq) {
-                            const uint32_t a = z.hw + (uint32_t)bq * 128u;
-                            const uint32_t v = lds32(a);
-                            if (v) {
-                                int gi = z.wb + bq;
-                                gi -= gi >= z.nn ? z.nn : 0;
-                                atomicAdd(z.bins + gi, (unsigned long long)v);
-                                sts32(a, 0u);
-                            }
-                        }
-                        z.wb = z.idx - 8;
-                        z.wb += z.wb < 0 ? z.nn : 0;
-                        off = 8;
+                for (int bq = 0; bq < 16; ++bq) {
+                    const uint32_t a = z.hw + (uint32_t)bq * 128u;
+                    const uint32_t v = lds32(a);
+                    if (v) {
+                        int gi = z.wb + bq;
+                        gi -= gi >= z.nn ? z.nn : 0;
+                        atomicAdd(z.bins + gi, (unsigned long long)v);
+                        sts32(a, 0u);
                     }
                 }
-                const uint32_t a = ev ? z.hw + (uint32_t)off * 128u : hwdummy;
-                sts32(a, lds32(a) + (uint32_t)(s - z.since));
-                z.idx = on ? wrap1(z.idx + (((ups >> j) & 1u) ? 1 : -1), z.nn) : z.idx;
-                z.since = (on && rec_on) ? s : z.since;
-                m &= m - 1u;
+                z.wb = z.idx - 8;
+                z.wb += z.wb < 0 ? z.nn : 0;
+                off = 8;
+            }
+            const uint32_t a = ev ? z.hw + (uint32_t)off * 128u : hwdummy;
+            sts32(a, lds32(a) + (uint32_t)(s - z.since));
+            z.idx = on ? wrap1(z.idx + (((ups >> j) & 1u) ? 1 : -1), z.nn) : z.idx;
+            z.since = (on && rec_on) ? s : z.since;
+            m &= m - 1u;
+        };
+        // the events of one or two parameters in a batch, in step order per parameter, the two side by side (most lanes have none
+        // or one event per parameter and batch)
+        auto events = [&](Slot& z, uint32_t m, uint32_t ups, int s0, int pad) {
+            while (__any_sync(SPEC_FULL, m != 0u)) event1(z, m, ups, s0, pad);
+        };
+        auto events2 = [&](Slot& za, uint32_t ma, uint32_t ua, Slot& zb, uint32_t mb, uint32_t ub, int s0, int pad) {
+            while (__any_sync(SPEC_FULL, (ma | mb) != 0u)) {
+                event1(za, ma, ua, s0, pad);
+                event1(zb, mb, ub, s0, pad);
             }
         };
 
@@ -730,17 +743,20 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             if (TAB_T_NOACC) continue;
             const uint32_t accrep = accb * 0x01010101u;
             if (aw == 0) acc_total += (unsigned int)__popc(accb);
+            uint32_t m0 = 0, u0 = 0, m1 = 0, u1 = 0;
             if (has0) {
                 sl[0].acc += (unsigned int)__popc(((mk.x & accrep) >> (8 * q0)) & 0xffu);
-                events(sl[0], ((mk.y & accrep) >> (8 * q0)) & 0xffu, (mk.z >> (8 * q0)) & 0xffu, s0, pad);
+                m0 = ((mk.y & accrep) >> (8 * q0)) & 0xffu; u0 = (mk.z >> (8 * q0)) & 0xffu;
             }
             if (has1) {
-                if (q1 == R) events(sl[1], mk.w & accb, (mk.w >> 8) & 0xffu, s0, pad);
+                if (q1 == R) { m1 = mk.w & accb; u1 = (mk.w >> 8) & 0xffu; }
                 else {
                     sl[1].acc += (unsigned int)__popc(mk4 & accb);
-                    events(sl[1], (mk4 >> 8) & accb, (mk4 >> 16) & 0xffu, s0, pad);
+                    m1 = (mk4 >> 8) & accb; u1 = (mk4 >> 16) & 0xffu;
                 }
             }
+            if (has1) events2(sl[0], m0, u0, sl[1], m1, u1, s0, pad);
+            else events(sl[0], m0, u0, s0, pad);
             // accepted state moves and the optional state trace, in step order
             if (need_dw) {
 #pragma unroll
