@@ -264,6 +264,7 @@ def run_ours(args, rank, world, local_rank):
         b.record()
         b.synchronize()
         kern_ms.append(blk.last_kernel_ms()[0])
+    headline_kernel = blk.last_kernel()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -501,14 +502,18 @@ def run_ours(args, rank, world, local_rank):
             traffic = json.load(f).get("dram_bytes_per_launch")
     except Exception:
         pass
+    kernel_names = {"tab": "bcp::tabk::mcmc_tab_kernel<4,true> (table-driven, one thread per chain + helper warps; auto-selected "
+                           "for one wave of 32 chains per SM beyond the warp-specialised kernel's range)",
+                    "spec": "bcp::mcmc_spec_kernel<4,4,true> (speculative, 4 lanes per chain)",
+                    "ws": "bcp::mcmc_ws_kernel<4,4,true> (warp-specialised speculative)",
+                    "fast": "bcp::mcmc_fast_kernel<4,true> (thread per chain)"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "bcp::mcmc_spec_kernel<4,4,true> (auto-selected for <= 8192 chains)", "kernel_ms_per_launch": k_ms,
+                "traffic": traffic, "kernel": kernel_names.get(headline_kernel, headline_kernel), "kernel_ms_per_launch": k_ms,
                 "cycles_per_chain_step": k_ms * 1e-3 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / N_MCMC,
-                "cost_model_cycles_per_chain_step": 4.5 * 41 + 1.5 * 150,
-                "cost_model_note": "fits every Metropolis kernel variant measured (DESIGN.md section 4): one warp issues a "
-                                   "shared-memory / shuffle / cp.async instruction every ~4.5 cycles and any other every ~1.5; "
-                                   "the spec kernel executes 41 + 150 per step (profiles/r02_mcmc_spec_4096.lines.txt); the "
-                                   "dependency cycle alone would allow ~155 cycles (latencies: profiles/r01_microbench.json)",
+                "cost_model_note": "a Metropolis step is one warp's dependent instruction stream (DESIGN.md section 4): a single warp "
+                                   "issues dependent integer / fp64 code at 0.2-0.4 instructions per cycle; the table-driven kernel's "
+                                   "consumer executes ~100 instructions per step (profiles/r02_mcmc_tab_4096.summary.txt), its helper "
+                                   "warps (generators, tabulator, accountants) each need about as long per batch of 8 steps",
                 "algorithmic_bytes_per_chain_step": bps, "peak_source": peak_src,
                 "note": "latency/issue-bound by construction (SURVEY 8d): the useful table words are L2-resident "
                         "gathers (measured L2 random-gather peak 2.9e11 8-B words/s, profiles/r01_microbench.json: "

@@ -195,6 +195,7 @@ _SIGS = {
     "bcp_chains_fetch": (C.c_int, [C.c_void_p, C.POINTER(bcp_sample_out)]),
     "bcp_chains_device_hist": (C.c_int, [C.c_void_p, C.POINTER(c_int64_p), C.POINTER(c_int64_p)]),
     "bcp_chains_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), c_int32_p]),
+    "bcp_chains_last_kernel": (C.c_char_p, [C.c_void_p]),
     "bcp_neglogp": (C.c_int, [C.c_void_p, C.c_int64, c_int32_p, c_int32_p, c_int32_p, c_double_p]),
     "bcp_precompute": (C.c_int, [C.POINTER(bcp_obs), C.c_int32, C.c_int, c_double_p, c_double_p, c_double_p,
                                  c_double_p]),

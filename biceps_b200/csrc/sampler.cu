@@ -407,9 +407,11 @@ struct bcp_chains {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk = nullptr;
     std::vector<int> h_lam;                 // lambda index of every chain (bcp_chains_score)
     int spec_verdict = 0;                   // 0 undecided, 1 keep the speculative kernel, -1 its batches roll back too often
+    int tab_verdict = 0, tab_trials = 0;    // table-driven kernel (its rollback unit is 8 x larger): 0 undecided, 1 keep, -1 not for this ensemble
     cudaStream_t copy_stream = nullptr;     // device -> host copies of finished snapshots (bcp_sample)
     long long snaps_piped = 0;
     int last_launches = 0;
+    const char* last_kernel = "none";      // the Metropolis kernel the last launch of the last sample call ran
     bool sampled = false;
     // reference-stream mode (bcp_chain_cfg.rng_mode == 1): numpy's MT19937 outputs, one chain
     int rng_mode = 0;
@@ -820,6 +822,13 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
         const long long lim = wl ? atoll(wl) : 2;
         if (which == 3 && n * lanes <= lim * sms * 32) which = 4;
     }
+    // one wave of the table-driven kernel (sampler_tab.cu: 32 chains per CTA, one CTA per SM) beyond the warp-specialised
+    // kernel's range: measured on C3 (scripts/profile_target.py, 20 000 steps) 3.8 ms at 704 .. 4096 chains against 4.3 .. 4.6 ms
+    // for spec and 3.3 / 4.7 ms for ws at 704 / 4096 chains; BCP_TAB=0 disables the choice
+    {
+        const char* tb = getenv("BCP_TAB");
+        if (which == 3 && T.lb && n <= 32ll * sms && !(tb && tb[0] == '0')) which = 5;
+    }
     if (kern && T.canonical)
         which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : (!strcmp(kern, "ws") ? 4 : (!strcmp(kern, "tab") ? 5 : 2))));
     if (force && force[0] == '1') which = 0;
@@ -858,47 +867,81 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     const bool spec_auto = (which == 3 || which == 4 || which == 5) && !(kern && T.canonical) && T.pf.q < 0;
     if (spec_auto && c->spec_verdict < 0) which = 1;
     const long long pilot = (spec_auto && c->spec_verdict == 0 && total >= 8192) ? 1024 : 0;
+    // The table-driven kernel redoes 256 chain-steps where spec redoes 32, and an accepted state move rebuilds a chain's tables:
+    // it is kept only where its own rollback fraction is small.  The first steps of a chain are no measure (indices drifting from
+    // the middle of their grids, E = 1e99), so the kernel is tried in launches of 16 384 steps -- the first that rolls back less
+    // than 6 % of its batches keeps it, six that do not hand the block to the spec kernel (also runs shorter than 32 768 steps).
+    const bool tab_auto = spec_auto && which == 5;
+    const long long tab_trial_steps = 16384;
+    if (tab_auto && (c->tab_verdict < 0 || (c->tab_verdict == 0 && total < 2 * tab_trial_steps))) which = 3;
+    if (pilot && which == 5) which = 3;                      // (the pilot itself runs on the spec kernel)
+    unsigned long long tab_stats0[2] = {0, 0};
+    bool tab_trial = false;
     for (long long s0 = 0, s1 = 0; s0 < total; s0 = s1) {
         s1 = (pilot && s0 == 0) ? pilot : s0 + chunk;
-        if (s1 > total) s1 = total;
-        A.s_begin = s0;
-        A.s_end = s1;
         if (pilot && s0 == pilot) {
             unsigned long long stats[2] = {0, 0};
             BCP_CUDA(cudaMemcpyAsync(stats, c->C.spec_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
             BCP_CUDA(cudaStreamSynchronize(st));
-            c->spec_verdict = (stats[0] > 0 && (double)stats[1] > 0.15 * (double)stats[0]) ? -1 : 1;
-            if (c->spec_verdict < 0) which = 1;
+            const double frac = stats[0] > 0 ? (double)stats[1] / (double)stats[0] : 0.0;
+            c->spec_verdict = frac > 0.15 ? -1 : 1;
+            which = c->spec_verdict < 0 ? 1 : ((tab_auto && c->tab_verdict >= 0 && total - s0 >= tab_trial_steps) ? 5 : which);
+            if (getenv("BCP_SPEC_STATS")) fprintf(stderr, "bcp pilot: %llu of %llu spec batches rolled back (%.4f) -> verdict %d\n", stats[1], stats[0], frac, c->spec_verdict);
         }
+        if (tab_trial) {                                     // the trial launch that has just been queued: its rollback fraction
+            unsigned long long stats[2] = {0, 0};
+            BCP_CUDA(cudaMemcpyAsync(stats, c->C.spec_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+            BCP_CUDA(cudaStreamSynchronize(st));
+            const double nb = (double)(stats[0] - tab_stats0[0]), nr = (double)(stats[1] - tab_stats0[1]);
+            if (nb > 0 && nr < 0.06 * nb) c->tab_verdict = 1;
+            else if (++c->tab_trials >= 6) { c->tab_verdict = -1; which = 3; }
+            if (getenv("BCP_SPEC_STATS")) fprintf(stderr, "bcp tab trial: %.0f of %.0f batches rolled back -> verdict %d\n", nr, nb, c->tab_verdict);
+            tab_trial = false;
+        }
+        if (tab_auto && which == 5 && c->tab_verdict == 0 && !(pilot && s0 == 0)) {
+            BCP_CUDA(cudaMemcpyAsync(tab_stats0, c->C.spec_stats, sizeof(tab_stats0), cudaMemcpyDeviceToHost, st));
+            BCP_CUDA(cudaStreamSynchronize(st));
+            if (s1 > s0 + tab_trial_steps) s1 = s0 + tab_trial_steps;
+            tab_trial = true;
+        }
+        if (s1 > total) s1 = total;
+        A.s_begin = s0;
+        A.s_end = s1;
         const bool fast = which == 1;
         cudaError_t e;
+        const char* kname = "generic";
         if (c->rng_mode == 1) {
             const MtStream M{c->d_mt_raw, c->mt_len, c->d_mt_pos, c->d_mt_dry};
             e = launch_mcmc_mt(T, c->C, A, M, st);
+            kname = "mt";
         }
         else if (T.pf.q >= 0) {
             // BCP_PF_KERNEL=generic forces the general warp-per-chain kernel (tests run both)
             const char* pk = getenv("BCP_PF_KERNEL");
             e = (pk && !strcmp(pk, "generic")) ? cudaErrorNotSupported : launch_mcmc_pf2(T, c->C, A, st);
-            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_pf(T, c->C, A, st); }
+            kname = "pf2";
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_pf(T, c->C, A, st); kname = "pf"; }
         }
         else if (which == 5) {
             e = launch_mcmc_tab(T, c->C, A, st);
-            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_ws(T, c->C, A, st, sms); }
-            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_spec(T, c->C, A, st, sms); }
-            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); }
+            kname = "tab";
+            if (e == cudaErrorNotSupported && kern && !strcmp(kern, "tab")) { (void)cudaGetLastError(); e = launch_mcmc_ws(T, c->C, A, st, sms); kname = "ws"; }
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_spec(T, c->C, A, st, sms); kname = "spec"; }
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); kname = "coop"; }
         }
         else if (which == 4) {
             e = launch_mcmc_ws(T, c->C, A, st, sms);
-            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_spec(T, c->C, A, st, sms); }
-            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); }
+            kname = "ws";
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_spec(T, c->C, A, st, sms); kname = "spec"; }
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); kname = "coop"; }
         }
         else if (which == 3) {
             e = launch_mcmc_spec(T, c->C, A, st, sms);
-            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); }
+            kname = "spec";
+            if (e == cudaErrorNotSupported) { (void)cudaGetLastError(); e = launch_mcmc_coop(T, c->C, A, st, sms); kname = "coop"; }
         }
-        else if (which == 2) e = launch_mcmc_coop(T, c->C, A, st, sms);
-        else if (fast) e = launch_mcmc_fast(T, c->C, A, fgrid, fblock, st);
+        else if (which == 2) { e = launch_mcmc_coop(T, c->C, A, st, sms); kname = "coop"; }
+        else if (fast) { e = launch_mcmc_fast(T, c->C, A, fgrid, fblock, st); kname = "fast"; }
         else switch (T.R) {
             case 1: e = launch_mcmc<1>(T, c->C, A, grid, block, st); break;
             case 2: e = launch_mcmc<2>(T, c->C, A, grid, block, st); break;
@@ -910,6 +953,7 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
             default: e = launch_mcmc<8>(T, c->C, A, grid, block, st); break;
         }
         if (e != cudaSuccess) { set_error("mcmc_kernel launch failed: %s", cudaGetErrorString(e)); return BCP_ERR_CUDA; }
+        c->last_kernel = kname;
         ++launches;
         if (pipe) {
             // snapshots m with burn + m * traj_every < s_end are final once this launch has finished
@@ -995,6 +1039,10 @@ extern "C" int bcp_chains_sync(bcp_chains* c) {
         }
     }
     return BCP_OK;
+}
+
+extern "C" const char* bcp_chains_last_kernel(bcp_chains* c) {
+    return c ? c->last_kernel : "none";
 }
 
 extern "C" int bcp_chains_last_kernel_ms(bcp_chains* c, float* ms, int32_t* n_launches) {

@@ -213,6 +213,10 @@ class ChainBlock(object):
         A.check(self._lib.bcp_chains_last_kernel_ms(self._c, C.byref(ms), C.byref(nl)), "bcp_chains_last_kernel_ms")
         return float(ms.value), int(nl.value)
 
+    def last_kernel(self):
+        """Name of the Metropolis kernel the last launch ran (the choice is automatic and invisible in the results)."""
+        return self._lib.bcp_chains_last_kernel(self._c).decode()
+
     def device_hist_ptrs(self):
         a = A.c_int64_p(); b = A.c_int64_p()
         A.check(self._lib.bcp_chains_device_hist(self._c, C.byref(a), C.byref(b)), "bcp_chains_device_hist")

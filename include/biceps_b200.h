@@ -187,6 +187,9 @@ int bcp_chains_set_state(bcp_chains* c, const int32_t* state, const int32_t* ind
 int bcp_chains_device_hist(bcp_chains* c, int64_t** d_state_counts, int64_t** d_param_counts);
 /* elapsed device time (ms, CUDA events on the launch stream) of the last sample launch */
 int bcp_chains_last_kernel_ms(bcp_chains* c, float* ms, int32_t* n_launches);
+/* which Metropolis kernel the last launch ran ("tab", "ws", "spec", "fast", "coop", "generic", "pf2", "pf", "mt"; "none"
+ * before the first launch): the choice is automatic (chain count, layout, acceptance) and invisible in the results */
+const char* bcp_chains_last_kernel(bcp_chains* c);
 
 /* -log P of explicit configurations (PosteriorSampler.neglogP, :233-248): for n
  * configurations, lambda index lam[n], state[n], indices[n][P] -> energy_out[n].         */

@@ -16,4 +16,4 @@ blk = T.chains(n_chains, 1, chain_lambda=lam)
 for _ in range(reps):
     blk.launch(n_steps)
     blk.sync()
-    print("kernel ms", blk.last_kernel_ms())
+    print("kernel", blk.last_kernel(), "ms", blk.last_kernel_ms())
