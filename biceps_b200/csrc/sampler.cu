@@ -688,8 +688,8 @@ extern "C" int bcp_chains_create(bcp_handle* h, const bcp_chain_cfg* cfg, bcp_ch
     // both histograms in ONE block, state counts first: a multi-GPU caller all-reduces them with one collective
     TRY_CUDA(pool_alloc(&C.state_counts, (size_t)n_groups * ((size_t)T.S + T.HB)));
     C.param_counts = C.state_counts + (size_t)n_groups * T.S;
-    TRY_CUDA(pool_alloc(&C.spec_stats, 8 + 40 * 12 * 4));          // (+ the hand-off trace of a diagnostic build of sampler_tab.cu)
-    TRY_CUDA(cudaMemset(C.spec_stats, 0, (8 + 40 * 12 * 4) * sizeof(unsigned long long)));
+    TRY_CUDA(pool_alloc(&C.spec_stats, 8 + 40 * 14 * 4));          // (+ the hand-off trace of a diagnostic build of sampler_tab.cu)
+    TRY_CUDA(cudaMemset(C.spec_stats, 0, (8 + 40 * 14 * 4) * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.accepted, 0, n * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.sep, 0, (size_t)(T.R + 1) * n * sizeof(unsigned long long)));
     TRY_CUDA(cudaMemset(C.state_counts, 0, (size_t)n_groups * T.S * sizeof(unsigned long long)));
@@ -1027,13 +1027,13 @@ extern "C" int bcp_chains_sync(bcp_chains* c) {
         fprintf(stderr, "bcp spec stats: %llu batches, %llu rolled back (guard band %llu, window %llu, state move %llu; %llu lower-bound resolutions, %llu accepted)\n",
                 stats[0], stats[1], stats[2], stats[3], stats[4], stats[5], stats[6]);
         if (getenv("BCP_TAB_TRACE")) {
-            static unsigned long long tr[40 * 12 * 4];
+            static unsigned long long tr[40 * 14 * 4];
             BCP_CUDA(cudaMemcpy(tr, c->C.spec_stats + 8, sizeof(tr), cudaMemcpyDeviceToHost));
             for (int b = 0; b < 40; ++b) {
                 fprintf(stderr, "trace b=%d", 1000 + b);
-                for (int w = 0; w < 12; ++w)
+                for (int w = 0; w < 14; ++w)
                     for (int e = 0; e < 4; ++e)
-                        if (tr[(b * 12 + w) * 4 + e]) fprintf(stderr, " w%d.%d=%llu", w, e, tr[(b * 12 + w) * 4 + e] - tr[0]);
+                        if (tr[(b * 14 + w) * 4 + e]) fprintf(stderr, " w%d.%d=%llu", w, e, tr[(b * 14 + w) * 4 + e] - tr[0]);
                 fprintf(stderr, "\n");
             }
         }

@@ -126,6 +126,18 @@ __device__ __forceinline__ void mbar_spin(uint32_t a, uint32_t parity) {
         "}\n" ::"r"(a), "r"(parity)
         : "memory");
 }
+// one non-blocking test of a phase (acquire when it has completed)
+__device__ __forceinline__ bool mbar_test(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(a), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -210,7 +222,7 @@ struct BatchIter {
 };
 
 template <int R, bool HG>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(448, 1)
 mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                 const __grid_constant__ LaunchArgs A) {
     using F = TabCfg<R, HG>;
@@ -219,7 +231,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t tma_bar;
     __shared__ __align__(8) uint64_t bars[3][NS];            // 0 full, 1 empty, 2 free
-    __shared__ __align__(8) uint64_t bars_tab[3];            // tables valid after batch b (b & 1); 2: initial build done
+    __shared__ __align__(8) uint64_t bars_tab[4];            // tables valid after batch b (b % 3); 3: initial build done
 
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
     if (threadIdx.x == 0) {
@@ -227,23 +239,24 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         for (int k = 0; k < NS; ++k) {
             mbar_init(smem_u32(&bars[0][k]), 128);           // four generator warps
             mbar_init(smem_u32(&bars[1][k]), 32);            // consumer
-            mbar_init(smem_u32(&bars[2][k]), TAB_T_AFREE ? 32 : 160);           // tabulator + four accountants have copied the stage's words
+            mbar_init(smem_u32(&bars[2][k]), TAB_T_AFREE ? 32 : (HG ? 192 : 160));           // tabulator + four / five accountants have copied the stage's words
         }
         mbar_init(smem_u32(&bars_tab[0]), 32);
         mbar_init(smem_u32(&bars_tab[1]), 32);
         mbar_init(smem_u32(&bars_tab[2]), 32);
+        mbar_init(smem_u32(&bars_tab[3]), 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     stage_sigma_table(reinterpret_cast<double*>(smem_raw), T.sig4, T.sig4_bytes, &tma_bar);     // has the block barrier
-    if (warp == 4 || warp == 8) return;                      // (they would share the consumer's SM sub-partition)
+    if (warp == 4 || warp == 8 || warp == 12 || (warp == 13 && !HG)) return;     // (4, 8, 12 would share the consumer's SM sub-partition)
 
     const long long n = C.n_chains;
     long long c = (long long)blockIdx.x * 32 + lane;
     const bool live = c < n;                                 // dead lanes shadow the last chain, no stores
-    // (diagnostics) event e of warp `warp` at batch b: spec_stats[8 + ((b - 1000) * 12 + warp) * 4 + e]
+    // (diagnostics) event e of warp `warp` at batch b: spec_stats[8 + ((b - 1000) * 14 + warp) * 4 + e]
     auto trace = [&](int b, int e) {
         if (TAB_TRACE && blockIdx.x == 0 && lane == 0 && b >= 1000 && b < 1040)
-            C.spec_stats[8 + ((b - 1000) * 12 + warp) * 4 + e] = (unsigned long long)clock64();
+            C.spec_stats[8 + ((b - 1000) * 14 + warp) * 4 + e] = (unsigned long long)clock64();
     };
     if (!live) c = n - 1;
     const int lam = C.lam[c];
@@ -273,9 +286,9 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     const uint32_t rec0 = row0 + (HG ? 32u * (uint32_t)GS * 8u : 0u);        // [R][32] {sse, ref} of the current state
     const uint32_t cst0 = rec0 + (uint32_t)R * 512u;                         // [32] energy + logZ of the current state
     const uint32_t ring0 = cst0 + 256u;
-    const uint32_t rect0 = ring0 + (uint32_t)(NS * F::STAGE);                // [2][6][32] valid windows, positions (tabulator -> consumer)
-    const uint32_t idxp0 = rect0 + 2u * 6u * 128u;                           // [2][R + 1][32] true indices after a batch
-    const uint32_t q10 = idxp0 + 2u * (uint32_t)(R + 1) * 128u;              // 64 scalar cells to fill
+    const uint32_t rect0 = ring0 + (uint32_t)(NS * F::STAGE);                // [3][6][32] valid windows, positions (tabulator -> consumer)
+    const uint32_t idxp0 = rect0 + 3u * 6u * 128u;                           // [3][R + 1][32] true indices at the checkpoint
+    const uint32_t q10 = idxp0 + 3u * (uint32_t)(R + 1) * 128u;              // 64 scalar cells to fill
     const uint32_t q20 = q10 + 256u;                                         // 64 row / column segments to fill
     const uint32_t acc0 = q20 + 512u;                                        // accountants: [R + 1][16][32] histogram windows, 32 dummy words
     const uint32_t lane8 = 8u * (uint32_t)lane, lane4 = 4u * (uint32_t)lane;
@@ -443,12 +456,14 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         // =====================================================================================
         int nf[NF > 0 ? NF : 1];                             // grid length of every field
         int pfull[NF > 0 ? NF : 1], ifull[NF > 0 ? NF : 1], lo[NF > 0 ? NF : 1], hi[NF > 0 ? NF : 1];
+        int lop[NF > 0 ? NF : 1], hip[NF > 0 ? NF : 1], lo_cur[NF > 0 ? NF : 1], hi_cur[NF > 0 ? NF : 1];   // the window one batch ago (and a copy)
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
             const int k = f < R ? f : QG;
             nf[f] = f < R ? T.r[k].n_sigma : G;
             ifull[f] = f < R ? C.isg[(size_t)k * n + c] : C.igm[(size_t)QG * n + c];
             pfull[f] = 0; lo[f] = -TAB_MRG0; hi[f] = TAB_MRG0;
+            lop[f] = lo[f]; hip[f] = hi[f]; lo_cur[f] = lo[f]; hi_cur[f] = hi[f];
         }
         // ---- prologue: stage the chains' current states, build every window around position 0 ----
         {
@@ -464,7 +479,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 build_chain(L, 0u, 0u, idx, gi);
             }
             __syncwarp();
-            mbar_arrive(b_tab + 16u);
+            mbar_arrive(b_tab + 24u);
         }
         const uint32_t lane_lt = (1u << lane) - 1u;
         uint32_t n1 = 0, n2 = 0;
@@ -537,7 +552,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             const uint32_t ps = lds32(rs + F::O_PS + lane4), pn = lds32(rs + F::O_PN + lane4);
             const bool reb = (lds32(rs + F::O_ACC + lane4) >> 16) & 1u;
             mbar_arrive(b_free + 8u * (uint32_t)stage);
-            if (TAB_T_NOTAB) { mbar_arrive(b_tab + 8u * (uint32_t)(b & 1)); continue; }
+            if (TAB_T_NOTAB) { mbar_arrive(b_tab + 8u * (uint32_t)(b % 3)); continue; }
             // walkers that left their trigger window (packed test, like the consumer's), chains rebuilt by the careful path
             const bool trig_s = reb || ((((ps + tls) & MS) + tgs) & HS) != 0u;
             const bool trig_n = HG && (reb || ((((pn + tln) & MN) + tgn) & HN) != 0u);
@@ -566,12 +581,12 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                     const int span = f < RS ? 31 : 15, mrg = f < RS ? TAB_MRG_S : TAB_MRG_N;     // slots - 1
                     const int p = pfull[f];
                     int l = lo[f], h = hi[f];
-                    if (reb) { l = p - TAB_MRG0; h = p + TAB_MRG0; lo[f] = l; hi[f] = h; }        // rebuilt by the consumer's careful path
+                    if (reb) { l = p - TAB_MRG0; h = p + TAB_MRG0; lo[f] = l; hi[f] = h; lop[f] = l; hip[f] = h; }   // rebuilt by the consumer's careful path
                     else {
-                        // extend towards the walker; old and new window together span at most `slots` positions, so a slot that the
-                        // consumer may still read (it works with the previous window) is never rewritten
-                        if (hi[f] - p < TAB_MRGMIN) h = imax(hi[f], imin(p + mrg, lo[f] + span));
-                        if (p - lo[f] < TAB_MRGMIN) l = imin(lo[f], imax(p - mrg, hi[f] - span));
+                        // extend towards the walker; the new window and the two before it together span at most `slots` positions, so
+                        // a slot that the consumer may still read (it works with one of the two previous windows) is never rewritten
+                        if (hi[f] - p < TAB_MRGMIN) h = imax(hi[f], imin(p + mrg, imin(lo[f], lop[f]) + span));
+                        if (p - lo[f] < TAB_MRGMIN) l = imin(lo[f], imax(p - mrg, imax(hi[f], hip[f]) - span));
                         if (h - l > span - 1) { if (p - l > h - p) l = h - (span - 1); else h = l + (span - 1); }
                     }
                     lo_n[f] = l; hi_n[f] = h;
@@ -618,32 +633,35 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 for (int f = 0; f < NF; ++f) { lo[f] = lo_n[f]; hi[f] = hi_n[f]; }
                 pack();
             }
+            // (the window of the batch before: a batch that changes nothing ages the older one out as well)
+#pragma unroll
+            for (int f = 0; f < NF; ++f) { lop[f] = lo_cur[f]; hip[f] = hi_cur[f]; lo_cur[f] = lo[f]; hi_cur[f] = hi[f]; }
             // ---- publish: the windows (valid two batches on), the checkpoint {positions, true indices} ----
-            const uint32_t rb = rect0 + (uint32_t)(b & 1) * 768u + lane4;
+            const uint32_t rb = rect0 + (uint32_t)(b % 3) * 768u + lane4;
             sts32(rb, nls); sts32(rb + 128u, mgs); sts32(rb + 256u, nln); sts32(rb + 384u, mgn);
             sts32(rb + 512u, ckps); sts32(rb + 640u, ckpn);
-            const uint32_t ib = idxp0 + (uint32_t)(b & 1) * (uint32_t)(R + 1) * 128u + lane4;
+            const uint32_t ib = idxp0 + (uint32_t)(b % 3) * (uint32_t)(R + 1) * 128u + lane4;
 #pragma unroll
             for (int k = 0; k < R; ++k) sts32(ib + 128u * (uint32_t)k, (uint32_t)ifull[k]);
             if (HG) sts32(ib + 128u * (uint32_t)R, (uint32_t)ifull[NF - 1]);
             trace(b, 2);
-            mbar_arrive(b_tab + 8u * (uint32_t)(b & 1));
+            mbar_arrive(b_tab + 8u * (uint32_t)(b % 3));
         }
         return;
     }
 
-    if (warp == 5 || warp == 6 || warp == 7 || warp == 9) {
+    if (warp == 5 || warp == 6 || warp == 7 || warp == 9 || warp == 13) {
         // =====================================================================================
         // accountants: the bookkeeping of the batches the consumer has finished, split by PARAMETER over four warps (a
         // single warp runs dependent integer code at ~0.2 instructions per cycle; the parameters are independent).  ONE code
         // path for the four (the kernel's hot code has to stay small: the instruction caches of 128 SMs refill from L2):
-        // warp a follows the sigma index of restraint a in slot 0; slot 1 is the gamma index (warp 1) or the sigma index of
-        // restraint 4 (warp 2); warp 0 also keeps the conformational state, the state trace and the acceptance totals.
+        // accountant a < 4 follows the sigma index of restraint a in slot 0 (accountant 2 that of restraint 4 in slot 1), accountant
+        // 4 (warp 13) the gamma index; accountant 0 also keeps the conformational state, the state trace and the acceptance totals.
         // An index and the start of its current run follow from the generator's proposal masks AND the accept bits.
         // =====================================================================================
-        const int aw = warp == 9 ? 3 : warp - 5;
-        const bool has0 = aw < R, has1 = (aw == 1 && HG) || (aw == 2 && R > 4);
-        const int q0 = has0 ? aw : 0, q1 = aw == 1 ? R : 4;               // parameter: restraint's sigma, or R = gamma
+        const int aw = warp == 9 ? 3 : (warp == 13 ? 4 : warp - 5);
+        const bool has0 = aw < R && aw < 4, has1 = (aw == 4 && HG) || (aw == 2 && R > 4);
+        const int q0 = has0 ? aw : 0, q1 = aw == 4 ? R : 4;               // parameter: restraint's sigma, or R = gamma
         const int grp = C.group[c];
         unsigned long long* g_state_counts = C.state_counts + (size_t)grp * T.S;
         unsigned long long* g_param_counts = C.param_counts + (size_t)grp * T.HB;
@@ -836,7 +854,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     // windows: valid where ((P + neglo) & mask) + marg has no bit 7 set in any field
     constexpr uint32_t NL0 = (uint32_t)TAB_MRG0 * 0x01010101u, MG0 = (uint32_t)(127 - 2 * TAB_MRG0) * 0x01010101u;
     uint32_t ov_nls = 0, ov_mgs = 0, ov_nln = 0, ov_mgn = 0;  // windows of the chains the careful path has just rebuilt
-    bool ov = false;
+    int rebat = -1;                                           // the batch of the chain's last rebuild
 
     // the Metropolis uniform of local step s (the rare paths only: the ring does not carry it)
     auto uniform_of = [&](int s) {
@@ -890,15 +908,16 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         gj = HG ? wrap1(gib + ((int)(((((pnj >> 8) & 127u) - ((pnb >> 8) & 127u)) + 64u) & 127u) - 64), G) : 0;
     };
 
-    mbar_wait(b_tab + 16u, 0u);                               // the initial tables
+    mbar_wait(b_tab + 24u, 0u);                               // the initial tables
 #pragma unroll
     for (int k = 0; k < R; ++k) t[k] = lds64(tabl + (uint32_t)((HG && k == QG) ? 32 * RS : 32 * k) * 256u);
 
+    bool ok_full = false, ok_tab = false;                     // the batch's barriers have been seen completed already
     for (int b = 0; !it.done(); ++b, it.advance()) {
         const int stage = b % NS, fill = b / NS;
         const uint32_t rs = ring_of(stage);
         trace(b, 0);
-        if (TAB_SPIN >= 1) mbar_spin(b_full + 8u * (uint32_t)stage, (uint32_t)fill & 1u); else mbar_wait(b_full + 8u * (uint32_t)stage, (uint32_t)fill & 1u);
+        if (!ok_full) mbar_wait(b_full + 8u * (uint32_t)stage, (uint32_t)fill & 1u);
         trace(b, 1);
         int cs0, cpad;                                        // the batch's first real step and front padding (rare paths)
         {
@@ -906,9 +925,16 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             it.get(cs0, cpad, snap_last);
         }
         uint32_t nls, mgs, nln, mgn;
+        int xw = -1;                                          // the tabulator batch whose windows / checkpoint this batch works with
         if (b >= 2) {
-            if (TAB_SPIN >= 1) mbar_spin(b_tab + 8u * (uint32_t)(b & 1), (uint32_t)((b - 2) >> 1) & 1u); else mbar_wait(b_tab + 8u * (uint32_t)(b & 1), (uint32_t)((b - 2) >> 1) & 1u);
-            const uint32_t rb = rect0 + (uint32_t)(b & 1) * 768u + lane4;
+            // the windows after batch b - 2 if the tabulator has got that far, else those after batch b - 3 (it never rewrites a
+            // slot of the two windows before the one it is building)
+            xw = b - 2;
+            if (!ok_tab && !mbar_test(b_tab + 8u * (uint32_t)(xw % 3), (uint32_t)(xw / 3) & 1u)) {
+                if (b >= 3) --xw;
+                mbar_wait(b_tab + 8u * (uint32_t)(xw % 3), (uint32_t)(xw / 3) & 1u);
+            }
+            const uint32_t rb = rect0 + (uint32_t)(xw % 3) * 768u + lane4;
             nls = lds32(rb); mgs = lds32(rb + 128u); nln = lds32(rb + 256u); mgn = lds32(rb + 384u);
         } else {
             nls = NL0; mgs = MG0; nln = NL0 & MN; mgn = MG0 & 0xffffu;
@@ -916,8 +942,8 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             for (int f = RS; f < 4; ++f) { nls &= ~(0xffu << (8 * f)); mgs |= 127u << (8 * f); }
             if (!HG) { nln = 0u; mgn = 127u | (127u << 8); }
         }
-        if (ov) { nls = ov_nls; mgs = ov_mgs; nln = ov_nln; mgn = ov_mgn; }
-        ov = false;
+        // a chain the careful path has rebuilt keeps its own window until the tabulator's windows include that batch
+        if (xw < rebat) { nls = ov_nls; mgs = ov_mgs; nln = ov_nln; mgn = ov_mgn; }
         trace(b, 2);
 
         // ---- fast batch ----------------------------------------------------------------------------
@@ -953,7 +979,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             if (TAB_INPLACE && __any_sync(SPEC_FULL, bad)) {
                 if (bad) {
                     int idj[R], gj, ir = 0;
-                    true_indices(b >= 2, b & 1, Ps2, Pn2, idj, gj);
+                    true_indices(xw >= 0, xw >= 0 ? xw % 3 : 0, Ps2, Pn2, idj, gj);
 #pragma unroll
                     for (int k = 0; k < R; ++k) ir = r == k ? idj[k] : ir;
                     tp = cell_value(lane, r, ir, gj);
@@ -984,6 +1010,13 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             w = wn; txv = txn;
         }
         ++n_batches;
+        // the next batch's barriers are tested here, a barrier query's latency ahead of their use (a phase that has completed
+        // stays completed until this warp has moved on: the next batch then starts without a wait)
+        {
+            const int bn = b + 1, stn = bn % NS, fn = bn / NS;
+            ok_full = mbar_test(b_full + 8u * (uint32_t)stn, (uint32_t)fn & 1u);
+            ok_tab = bn >= 2 ? mbar_test(b_tab + 8u * (uint32_t)((bn - 2) % 3), (uint32_t)((bn - 2) / 3) & 1u) : true;
+        }
         uint32_t rebw = 0;
         if (!__any_sync(SPEC_FULL, rare) && __any_sync(SPEC_FULL, jf >= 0)) {
             // ---- state-move proposals the lower bound could not reject: evaluated exactly at the chain's indices of that step
@@ -991,7 +1024,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             //      and the batch stands ----
             if (jf >= 0) {
                 int idj[R], gj;
-                true_indices(b >= 2, b & 1, Psf, Pnf, idj, gj);
+                true_indices(xw >= 0, xw >= 0 ? xw % 3 : 0, Psf, Pnf, idj, gj);
                 const uint32_t dw = lds32(rs + F::O_DW + 128u * (uint32_t)jf + lane4);
                 const double u = uniform_of(cs0 + jf - cpad);
                 double xk[R];
@@ -1024,7 +1057,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             for (int k = 0; k < R; ++k) t[k] = sv_t[k];
             accb = 0;
             // the tabulator has finished batch b - 1 (and is now idle until this batch is published): the careful path may rebuild tables
-            if (b >= 1) mbar_wait(b_tab + 8u * (uint32_t)((b - 1) & 1), (uint32_t)((b - 1) >> 1) & 1u);
+            if (b >= 1) mbar_wait(b_tab + 8u * (uint32_t)((b - 1) % 3), (uint32_t)((b - 1) / 3) & 1u);
             // the fast path's step with a vote after each test: whatever it cannot decide is evaluated exactly on the spot, for the
             // lanes concerned (true indices = the tabulator's checkpoint + the positions' progress since)
             bool reb = false;                                 // the lane's chain has changed its state in this batch: its tables are stale
@@ -1043,7 +1076,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 if (__any_sync(SPEC_FULL, bad)) {             // outside the tabulated window (or stale tables): the exact term
                     if (bad) {
                         int idj[R], gj, ir = 0;
-                        true_indices(b >= 1, (b - 1) & 1, Ps2, Pn2, idj, gj);
+                        true_indices(b >= 1, b >= 1 ? (b - 1) % 3 : 0, Ps2, Pn2, idj, gj);
 #pragma unroll
                         for (int k = 0; k < R; ++k) ir = r == k ? idj[k] : ir;
                         tp = cell_value(lane, r, ir, gj);
@@ -1067,7 +1100,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                     bool accst = false;
                     if (lbf) {
                         int idj[R], gj;
-                        true_indices(b >= 1, (b - 1) & 1, Ps, Pn, idj, gj);
+                        true_indices(b >= 1, b >= 1 ? (b - 1) % 3 : 0, Ps, Pn, idj, gj);
                         En = eval_state((int)dw, idj, gj, xk);
                         acc = (En < E) || metropolis_accept(__dsub_rn(E, En), uniform_of(cs0 + j - cpad));
                         accst = acc && (int)dw != cstate;     // (the chain's own state proposed: accepted, nothing changes)
@@ -1092,7 +1125,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 }
             }
             int idx[R], gi;
-            true_indices(b >= 1, (b - 1) & 1, Ps, Pn, idx, gi);        // (the rebuild below)
+            true_indices(b >= 1, b >= 1 ? (b - 1) % 3 : 0, Ps, Pn, idx, gi);        // (the rebuild below)
             // rebuild the tables of the chains that changed their state, around their positions at the end of the batch
             uint32_t m = __ballot_sync(SPEC_FULL, reb);
             while (m) {
@@ -1106,7 +1139,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             __syncwarp();
             if (reb) {
                 rebw = 1u << 16;
-                ov = true;
+                rebat = b;
                 // window [P - MRG0, P + MRG0] in every field
                 ov_nls = ((((MS - Ps) + 0x01010101u) & MS) + (NL0 & MS)) & MS;
                 ov_nln = ((((MN - Pn) + 0x00000101u) & MN) + (NL0 & MN)) & MN;
@@ -1139,12 +1172,12 @@ static cudaError_t launch_tab_one(const SamplerTables& T, const ChainBuffers& C,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t smem = (size_t)T.sig4_bytes + (size_t)F::NE * 256 + (HG ? (size_t)32 * T.gh4_stride * 8 : 0) + (size_t)R * 512 + 256 +
-                        (size_t)F::NS * F::STAGE + 2 * 6 * 128 + 2 * (size_t)(R + 1) * 128 + 256 + 512 + ((size_t)(R + 1) * 16 * 128 + 128) + 128;
+                        (size_t)F::NS * F::STAGE + 3 * 6 * 128 + 3 * (size_t)(R + 1) * 128 + 256 + 512 + ((size_t)(R + 1) * 16 * 128 + 128) + 128;
     if (smem + 1024 > (size_t)max_optin) return cudaErrorNotSupported;
     cudaError_t e = cudaFuncSetAttribute(mcmc_tab_kernel<R, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)((C.n_chains + 31) / 32);
-    mcmc_tab_kernel<R, HG><<<grid, 384, smem, st>>>(T, C, A);
+    mcmc_tab_kernel<R, HG><<<grid, 448, smem, st>>>(T, C, A);
     return cudaGetLastError();
 }
 
