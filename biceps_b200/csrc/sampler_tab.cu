@@ -74,6 +74,9 @@ namespace tabk {
 #ifndef TAB_TRACE
 #define TAB_TRACE 0                // 1: CTA 0 records clock values of its warps' hand-offs for batches 1000 .. 1039 into spec_stats[8 ...]
 #endif
+#ifndef TAB_TRACE_B0
+#define TAB_TRACE_B0 1000
+#endif
 #ifndef TAB_T_AFREE
 #define TAB_T_AFREE 0              // the accountants do not hold the ring's stages (they may read overwritten words)
 #endif
@@ -253,10 +256,14 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     const long long n = C.n_chains;
     long long c = (long long)blockIdx.x * 32 + lane;
     const bool live = c < n;                                 // dead lanes shadow the last chain, no stores
-    // (diagnostics) event e of warp `warp` at batch b: spec_stats[8 + ((b - 1000) * 14 + warp) * 4 + e]
+    // (diagnostics) event e of warp `warp` at batch b: spec_stats[8 + ((b - TAB_TRACE_B0) * 14 + warp) * 4 + e]
     auto trace = [&](int b, int e) {
-        if (TAB_TRACE && blockIdx.x == 0 && lane == 0 && b >= 1000 && b < 1040)
-            C.spec_stats[8 + ((b - 1000) * 14 + warp) * 4 + e] = (unsigned long long)clock64();
+        if (TAB_TRACE && blockIdx.x == 0 && lane == 0 && b >= TAB_TRACE_B0 && b < TAB_TRACE_B0 + 40)
+            C.spec_stats[8 + ((b - TAB_TRACE_B0) * 14 + warp) * 4 + e] = (unsigned long long)clock64();
+    };
+    auto trace_t = [&](int b, int k) {                      // (the tabulator's finer points go into the slots of the idle warps 4, 8, 12)
+        if (TAB_TRACE && blockIdx.x == 0 && lane == 0 && b >= TAB_TRACE_B0 && b < TAB_TRACE_B0 + 40)
+            C.spec_stats[8 + ((b - TAB_TRACE_B0) * 14 + 4 + 4 * (k >> 2)) * 4 + (k & 3)] = (unsigned long long)clock64();
     };
     if (!live) c = n - 1;
     const int lam = C.lam[c];
@@ -558,6 +565,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             const bool trig_n = HG && (reb || ((((pn + tln) & MN) + tgn) & HN) != 0u);
             const bool any_s = RS > 0 && __any_sync(SPEC_FULL, trig_s), any_n = HG && __any_sync(SPEC_FULL, trig_n);
             // the scalar restraints and the gamma restraint are handled separately: with 32-slot windows the scalars rarely trigger
+            trace_t(b, 0);
             const bool per = (b & 3) == 3, do_s = any_s || (RS > 0 && per), do_n = any_n || (HG && per);
             if (do_s || do_n) {
                 // checkpoint: unwrapped positions and true indices at the end of this batch (at most 4 batches = 32 steps on)
@@ -572,6 +580,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 if (do_s) ckps = ps;
                 if (do_n) ckpn = pn;
             }
+            trace_t(b, 1);
             if (any_s || any_n) {
                 int lo_n[NF > 0 ? NF : 1], hi_n[NF > 0 ? NF : 1];
 #pragma unroll
@@ -591,6 +600,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                     }
                     lo_n[f] = l; hi_n[f] = h;
                 }
+                trace_t(b, 2);
                 // ---- new cells: scalars ----
                 if (any_s) {
 #pragma unroll
@@ -627,11 +637,14 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                                   (uint32_t)(lo_n[fv] & 15) | ((uint32_t)vidx0 << 4));
                         }
                     }
+                    trace_t(b, 4);
                     if (n2) process2();
                 }
+                trace_t(b, 5);
 #pragma unroll
                 for (int f = 0; f < NF; ++f) { lo[f] = lo_n[f]; hi[f] = hi_n[f]; }
                 pack();
+                trace_t(b, 6);
             }
             // (the window of the batch before: a batch that changes nothing ages the older one out as well)
 #pragma unroll
@@ -974,8 +987,11 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             const int r = (int)((w.z >> 16) & 7u);
             // the proposal's position outside its tabulated window (a walker that outran the tabulator): the term is evaluated
             // here, exactly like a table entry -- rare, and the batch goes on
+            // (branch-free: the scalar word's flag of restraint r, or the gamma restraint's two flags)
             const uint32_t bs = (((Ps2 + nls) & MS) + mgs) & HS, bn = (((Pn2 + nln) & MN) + mgn) & HN;
-            const bool bad = !TAB_T_NOTAB && (((w.z >> 20) & 1u) ? (((bs >> (8 * (r & 3))) & 0x80u) != 0u || ((TAB_DBG & 16) && r < R)) : (bn != 0u || (TAB_DBG & 8)));
+            const uint32_t scal = (w.z >> 20) & 1u;
+            const uint32_t bsel = (scal ? (bs >> (8 * (r & 3))) & 0x80u : bn) | (((TAB_DBG & 16) && scal && r < R) ? 1u : 0u) | (((TAB_DBG & 8) && !scal) ? 1u : 0u);
+            const bool bad = !TAB_T_NOTAB && bsel != 0u;
             if (TAB_INPLACE && __any_sync(SPEC_FULL, bad)) {
                 if (bad) {
                     int idj[R], gj, ir = 0;
