@@ -822,12 +822,14 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
         const long long lim = wl ? atoll(wl) : 2;
         if (which == 3 && n * lanes <= lim * sms * 32) which = 4;
     }
-    // one wave of the table-driven kernel (sampler_tab.cu: 32 chains per CTA, one CTA per SM) beyond the warp-specialised
-    // kernel's range: measured on C3 (scripts/profile_target.py, 20 000 steps) 3.8 ms at 704 .. 4096 chains against 4.3 .. 4.6 ms
-    // for spec and 3.3 / 4.7 ms for ws at 704 / 4096 chains; BCP_TAB=0 disables the choice
+    // one wave of the table-driven kernel (sampler_tab.cu: 32 chains per CTA, one CTA per SM), long runs: measured on C3 in the
+    // steady state (scripts/gpu/r02_tab22.sh, third launch of 100 000 steps) 14.1 ms at 704 .. 4736 chains against 16.5 / 17.6 ms
+    // for ws at 704 / 2368 chains (23.4 ms beyond) and 21.2 .. 22.7 ms for spec; BCP_TAB=0 disables the choice.  The kernel
+    // has to earn its place per chain block (trial launches below); the kernel chosen here otherwise takes over.
+    const int which_no_tab = which;
     {
         const char* tb = getenv("BCP_TAB");
-        if (which == 3 && T.lb && n <= 32ll * sms && !(tb && tb[0] == '0')) which = 5;
+        if ((which == 3 || which == 4) && T.lb && n <= 32ll * sms && !(tb && tb[0] == '0')) which = 5;
     }
     if (kern && T.canonical)
         which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : (!strcmp(kern, "ws") ? 4 : (!strcmp(kern, "tab") ? 5 : 2))));
@@ -873,7 +875,7 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     // than 6 % of its batches keeps it, six that do not hand the block to the spec kernel (also runs shorter than 32 768 steps).
     const bool tab_auto = spec_auto && which == 5;
     const long long tab_trial_steps = 16384;
-    if (tab_auto && (c->tab_verdict < 0 || (c->tab_verdict == 0 && total < 2 * tab_trial_steps))) which = 3;
+    if (tab_auto && (c->tab_verdict < 0 || (c->tab_verdict == 0 && total < 2 * tab_trial_steps))) which = which_no_tab;
     if (pilot && which == 5) which = 3;                      // (the pilot itself runs on the spec kernel)
     unsigned long long tab_stats0[2] = {0, 0};
     bool tab_trial = false;
@@ -885,7 +887,7 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
             BCP_CUDA(cudaStreamSynchronize(st));
             const double frac = stats[0] > 0 ? (double)stats[1] / (double)stats[0] : 0.0;
             c->spec_verdict = frac > 0.15 ? -1 : 1;
-            which = c->spec_verdict < 0 ? 1 : ((tab_auto && c->tab_verdict >= 0 && total - s0 >= tab_trial_steps) ? 5 : which);
+            which = c->spec_verdict < 0 ? 1 : ((tab_auto && c->tab_verdict >= 0 && total - s0 >= tab_trial_steps) ? 5 : which_no_tab);
             if (getenv("BCP_SPEC_STATS")) fprintf(stderr, "bcp pilot: %llu of %llu spec batches rolled back (%.4f) -> verdict %d\n", stats[1], stats[0], frac, c->spec_verdict);
         }
         if (tab_trial) {                                     // the trial launch that has just been queued: its rollback fraction
@@ -894,7 +896,7 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
             BCP_CUDA(cudaStreamSynchronize(st));
             const double nb = (double)(stats[0] - tab_stats0[0]), nr = (double)(stats[1] - tab_stats0[1]);
             if (nb > 0 && nr < 0.06 * nb) c->tab_verdict = 1;
-            else if (++c->tab_trials >= 6) { c->tab_verdict = -1; which = 3; }
+            else if (++c->tab_trials >= 6) { c->tab_verdict = -1; which = which_no_tab; }
             if (getenv("BCP_SPEC_STATS")) fprintf(stderr, "bcp tab trial: %.0f of %.0f batches rolled back -> verdict %d\n", nr, nb, c->tab_verdict);
             tab_trial = false;
         }

@@ -1034,7 +1034,9 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             ok_tab = bn >= 2 ? mbar_test(b_tab + 8u * (uint32_t)((bn - 2) % 3), (uint32_t)((bn - 2) / 3) & 1u) : true;
         }
         uint32_t rebw = 0;
-        if (!__any_sync(SPEC_FULL, rare) && __any_sync(SPEC_FULL, jf >= 0)) {
+        // (one vote decides whether anything at all needs a second look: almost always nothing does)
+        const bool second_look = __any_sync(SPEC_FULL, rare || jf >= 0);
+        if (second_look && !__any_sync(SPEC_FULL, rare)) {
             // ---- state-move proposals the lower bound could not reject: evaluated exactly at the chain's indices of that step
             //      (true indices = the tabulator's last checkpoint + the positions' progress since); almost all are rejected
             //      and the batch stands ----
@@ -1057,7 +1059,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 }
             }
         }
-        if (__any_sync(SPEC_FULL, rare)) {
+        if (second_look && __any_sync(SPEC_FULL, rare)) {
             // ---- careful batch: step by step from the raw proposal words, every rare case handled exactly ----
             ++n_rollbacks;
             if (TAB_STATS) {
