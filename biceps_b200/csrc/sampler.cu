@@ -868,11 +868,15 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     // sticks to the chain block.  Every kernel produces the same bits, so this is invisible in the results.
     const bool spec_auto = (which == 3 || which == 4 || which == 5) && !(kern && T.canonical) && T.pf.q < 0;
     if (spec_auto && c->spec_verdict < 0) which = 1;
-    const long long pilot = (spec_auto && c->spec_verdict == 0 && total >= 8192) ? 1024 : 0;
+    // (a block that is a candidate for the table-driven kernel goes straight to its trial launches: the pilot only follows if
+    // those hand the block back)
+    const bool tab_first = spec_auto && which == 5 && c->tab_verdict >= 0 && c->spec_verdict == 0 && total >= 2 * 16384;
+    const long long pilot = (spec_auto && c->spec_verdict == 0 && total >= 8192 && !tab_first) ? 1024 : 0;
     // The table-driven kernel redoes 256 chain-steps where spec redoes 32, and an accepted state move rebuilds a chain's tables:
     // it is kept only where its own rollback fraction is small.  The first steps of a chain are no measure (indices drifting from
     // the middle of their grids, E = 1e99), so the kernel is tried in launches of 16 384 steps -- the first that rolls back less
-    // than 6 % of its batches keeps it, six that do not hand the block to the spec kernel (also runs shorter than 32 768 steps).
+    // than 6 % of its batches keeps it; six that do not, or one beyond 25 %, hand the block to the other kernels (as do runs
+    // shorter than 32 768 steps).
     const bool tab_auto = spec_auto && which == 5;
     const long long tab_trial_steps = 16384;
     if (tab_auto && (c->tab_verdict < 0 || (c->tab_verdict == 0 && total < 2 * tab_trial_steps))) which = which_no_tab;
@@ -896,7 +900,7 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
             BCP_CUDA(cudaStreamSynchronize(st));
             const double nb = (double)(stats[0] - tab_stats0[0]), nr = (double)(stats[1] - tab_stats0[1]);
             if (nb > 0 && nr < 0.06 * nb) c->tab_verdict = 1;
-            else if (++c->tab_trials >= 6) { c->tab_verdict = -1; which = which_no_tab; }
+            else if (++c->tab_trials >= 6 || nr > 0.25 * nb) { c->tab_verdict = -1; which = which_no_tab; }     // (far off: no second trial)
             if (getenv("BCP_SPEC_STATS")) fprintf(stderr, "bcp tab trial: %.0f of %.0f batches rolled back -> verdict %d\n", nr, nb, c->tab_verdict);
             tab_trial = false;
         }
