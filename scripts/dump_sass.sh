@@ -7,9 +7,10 @@ dump() { obj=$1; pat=$2; out=$3
   fn=$(cuobjdump -elf $L/$obj 2>/dev/null | grep -o "\.text\.[A-Za-z0-9_]*" | sed 's/^\.text\.//' | sort -u | grep -E "$pat" | head -1)
   [ -n "$fn" ] || { echo "no kernel matching $pat in $obj"; return; }
   cuobjdump -sass -fun "$fn" $L/$obj | sed 's/ *\/\* 0x[0-9a-f]* \*\/$//' > $O/$out
-  echo "$out  <- $fn  ($(grep -c '^ *\/\*[0-9a-f]\{4\}\*\/' $O/$out) instructions)"; }
+  echo "$out  <- $fn  ($(grep -c '^ *\/\*[0-9a-f]\{4,6\}\*\/' $O/$out) instructions)"; }
 dump sampler_spec.o 'mcmc_spec_kernelILi4ELi4ELb1ELb0' mcmc_spec_kernel_4_4_gamma.sass
-dump sampler_ws.o 'mcmc_ws_kernelILi4ELi4ELb1ELi256' mcmc_ws_kernel_4_4_gamma.sass
+dump sampler_tab.o 'mcmc_tab_kernelILi4ELb1' mcmc_tab_kernel_4_gamma.sass
+dump sampler_ws.o 'mcmc_ws_kernelILi4ELi4ELb1ELi' mcmc_ws_kernel_4_4_gamma.sass
 dump sampler_fast.o 'mcmc_fast_kernelILi4ELb1ELb1' mcmc_fast_kernel_4_gamma_mk.sass
 dump sampler_pf2.o 'mcmc_pf2_kernelILi1ELi4' mcmc_pf2_kernel_1_4.sass
 dump sampler_pf2.o 'mcmc_pf2_kernelILi3ELi4' mcmc_pf2_kernel_3_4.sass
