@@ -829,7 +829,11 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     const int which_no_tab = which;
     {
         const char* tb = getenv("BCP_TAB");
-        if ((which == 3 || which == 4) && T.lb && n <= 32ll * sms && !(tb && tb[0] == '0')) which = 5;
+        const char* tw = getenv("BCP_TAB_WAVES");            // (tuning: waves of 32 chains per SM the kernel is considered for)
+        // (measured on C3, 50 000 steps: 14.4 / 21.7 / 28.8 ms at two / three / four waves against 32.7 / 32.7 / 49.0 ms for spec and
+        // 34-35 ms for the thread-per-chain kernel: four waves still pay)
+        const long long waves = tw ? atoll(tw) : 4;
+        if ((which == 3 || which == 4 || (which == 1 && waves > 1)) && T.lb && n <= waves * 32ll * sms && !(tb && tb[0] == '0')) which = 5;
     }
     if (kern && T.canonical)
         which = !strcmp(kern, "generic") ? 0 : (!strcmp(kern, "fast") ? 1 : (!strcmp(kern, "spec") ? 3 : (!strcmp(kern, "ws") ? 4 : (!strcmp(kern, "tab") ? 5 : 2))));

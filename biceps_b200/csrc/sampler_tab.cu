@@ -15,21 +15,31 @@
 // entries are the exact terms ((Ndof ln sigma + sse / 2 sigma^2) + cnorm) - ref in the reference's operation order
 // (Markstein division == IEEE division, spec_common.cuh), so the chain is bit-identical to every other kernel.
 //
-// Warps of a CTA (one consumer warp = 32 chains per CTA, one CTA per SM):
-//   0  consumer    the critical path above, 8 steps per batch on registers; anything rare only raises a flag and the
-//                  batch is redone by a careful step-by-step path: an accept decision inside the guard band of the
-//                  threshold test, a position outside its tabulated window, a state-move proposal that a per-state lower
-//                  bound of the energy cannot reject (lb[state] = min over all nuisance parameters, built by bcp_create:
-//                  on large ensembles a state move is almost never accepted, and then E_new >= lb > E - ln u proves it
-//                  without evaluating anything), and an accepted state move (the careful path rebuilds the chain's tables).
-//   1,2 generators Philox4x32-10, decode into pre-digested step words {packed deltas, byte selector, table offset},
-//                  thresholds ln u + margin, lb + ln u for state moves; one batch each in turn, a ring of NS stages.
-//   3  tabulator   follows the positions the consumer publishes per batch, keeps every window around its walker
-//                  (extends it ahead of the walk, at most 15 entries per dimension so that a slot is never rewritten
-//                  while the consumer may still read it) and publishes the valid rectangles two batches ahead.
-//   5  accountant  replays {proposal word, accept bit} into the run-length histograms, acceptance counters, state trace and
-//                  snapshots (the batches are cut so that a snapshot is the last step of its batch).
-//   (warp 4 exits: it would share the consumer's SM sub-partition.)
+// Warps of a CTA (448 threads; one consumer warp = 32 chains per CTA, one CTA per SM).  A single warp issues dependent integer /
+// fp64 code at 0.2-0.4 instructions per cycle, so every role is sized by the length of its dependent chains, the loops of the
+// helpers are ROLLED (six code paths share an SM's instruction caches, 128 SMs refill them from L2), and the work that does not
+// have to be serial is spread over more warps:
+//   0            consumer    the critical path above, 8 steps per batch, registers only; anything rare only raises a flag: a
+//                            state-move proposal that a per-state lower bound of the energy cannot reject (lb[state] = min over
+//                            all nuisance parameters, built by bcp_create: on large ensembles a state move is almost never
+//                            accepted, and then E_new >= lb > E - ln u proves it without evaluating anything) is evaluated
+//                            exactly after the batch, and the batch stands unless the move is accepted to another state; an
+//                            accept decision inside the guard band of the threshold test, a position outside its tabulated
+//                            window, an accepted state move redo the batch with the same step, a vote after each test and the
+//                            exact evaluation in place for the lanes concerned (an accepted state move rebuilds the chain's tables).
+//   1, 2, 3, 11  generators  Philox4x32-10, decode into pre-digested step words {packed deltas, byte selector, table offset},
+//                            thresholds ln u + margin, lb + ln u for state moves, the batch's proposals as bit masks for the
+//                            accountants; every batch by all four, two steps each (the ring has to cover a batch's latency).
+//   10           tabulator   follows the positions the consumer publishes per batch, keeps every window around its walker
+//                            (extends it ahead of the walk; old and new windows of three consecutive batches span at most the
+//                            slots of a table, so a slot is never rewritten while the consumer may still read it), publishes the
+//                            windows and a checkpoint {positions, true indices}, triple-buffered.
+//   5, 6, 7, 9, 13  accountants, one parameter each: accepted non-null moves = proposal masks AND accept bits; run-length
+//                            histogram events into a lane-private 16-bin window in shared memory (plain read-modify-write; one
+//                            RED per event from every chain of a lambda to the same hot bins is a global rate limit), acceptance
+//                            counters, state trace and snapshots (the batches are cut so that a snapshot is the last step of
+//                            its batch).
+//   4, 8, 12     exit at once: they would share the consumer's SM sub-partition.
 // Same RNG stream, same fp64 operation order, same outputs as every other Metropolis kernel (bit for bit).
 #include <type_traits>
 #include "spec_common.cuh"
@@ -174,9 +184,9 @@ __device__ __forceinline__ int wrap1(int v, int n) {           // v in [-n, 2n)
 __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
 __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
 
-template <int R, bool HG>
+template <int R, bool HG, int NSV = TAB_NS>
 struct TabCfg {
-    static constexpr int BL = TAB_BL, NS = TAB_NS;
+    static constexpr int BL = TAB_BL, NS = NSV;
     static constexpr int RS = HG ? R - 1 : R;               // scalar restraints
     static constexpr int NF = RS + (HG ? 2 : 0);            // position fields: sigma of every restraint, then gamma
     static constexpr int NE = RS * 32 + (HG ? 256 : 0);     // table entries per chain, stored [entry][chain]
@@ -224,11 +234,11 @@ struct BatchIter {
     }
 };
 
-template <int R, bool HG>
+template <int R, bool HG, int NSV>
 __global__ void __launch_bounds__(448, 1)
 mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
                 const __grid_constant__ LaunchArgs A) {
-    using F = TabCfg<R, HG>;
+    using F = TabCfg<R, HG, NSV>;
     constexpr int BL = F::BL, NS = F::NS, RS = F::RS, NF = F::NF, EB = SPEC_ENT_BYTES;
     constexpr int QG = R - 1;                                // the gamma restraint (if HG)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1183,20 +1193,28 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     if (live) C.E[c] = E;
 }
 
-template <int R, bool HG>
-static cudaError_t launch_tab_one(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st) {
-    using F = TabCfg<R, HG>;
+template <int R, bool HG, int NSV>
+static cudaError_t launch_tab_ns(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st) {
+    using F = TabCfg<R, HG, NSV>;
     int dev = 0, max_optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t smem = (size_t)T.sig4_bytes + (size_t)F::NE * 256 + (HG ? (size_t)32 * T.gh4_stride * 8 : 0) + (size_t)R * 512 + 256 +
                         (size_t)F::NS * F::STAGE + 3 * 6 * 128 + 3 * (size_t)(R + 1) * 128 + 256 + 512 + ((size_t)(R + 1) * 16 * 128 + 128) + 128;
     if (smem + 1024 > (size_t)max_optin) return cudaErrorNotSupported;
-    cudaError_t e = cudaFuncSetAttribute(mcmc_tab_kernel<R, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mcmc_tab_kernel<R, HG, NSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)((C.n_chains + 31) / 32);
-    mcmc_tab_kernel<R, HG><<<grid, 448, smem, st>>>(T, C, A);
+    mcmc_tab_kernel<R, HG, NSV><<<grid, 448, smem, st>>>(T, C, A);
     return cudaGetLastError();
+}
+// a ring of four stages where the tables leave room for it, else three or two (five restraints, long sigma grids)
+template <int R, bool HG>
+static cudaError_t launch_tab_one(const SamplerTables& T, const ChainBuffers& C, const LaunchArgs& A, cudaStream_t st) {
+    cudaError_t e = launch_tab_ns<R, HG, TAB_NS>(T, C, A, st);
+    if (e == cudaErrorNotSupported) e = launch_tab_ns<R, HG, 3>(T, C, A, st);
+    if (e == cudaErrorNotSupported) e = launch_tab_ns<R, HG, 2>(T, C, A, st);
+    return e;
 }
 
 }  // namespace tabk
