@@ -388,13 +388,14 @@ def run_ours(args, rank, world, local_rank):
             b2c.launch(steps2, stream=stream)
             b2c.sync()
             ms2.append(b2c.last_kernel_ms()[0])
+        c2_kernel = b2c.last_kernel()
         b2c.close(); T2c.close()
         rate2 = n2 * steps2 / (min(ms2) * 1e-3)
         bps2 = bytes_per_chain_step(tabs2)
         peak2, _ = measured_peak_hbm()
         c2 = {"workload": "C2: 1000 states, R=5 (cs_H, cs_Ca, cs_N, J, NOE), 8 lambdas x 1024 chains, 20000 steps",
               "value": rate2, "unit": "chain-steps/s",
-              "kernel": "auto-selected (speculative 8-lane kernel, two waves of 8-warp CTAs)",
+              "kernel": "auto-selected: " + c2_kernel + " (spec = speculative 8-lane kernel, two waves of 8-warp CTAs)",
               "roofline": {"bound": "hbm", "achieved": rate2 * bps2 / 1e9, "peak": peak2, "unit": "GB/s",
                            "frac": rate2 * bps2 / 1e9 / peak2, "algorithmic_bytes_per_chain_step": bps2, "traffic": None,
                            "cycles_per_chain_step_per_warp": min(ms2) * 1e-3 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / steps2,

@@ -85,6 +85,29 @@ def test_c3_trajectories_do_not_depend_on_launch_block_or_kernel_split(c3, monke
         assert np.array_equal(f[k], ref[k]), k
 
 
+def test_c3_long_run_automatic_choice_is_the_table_driven_kernel_and_changes_nothing(c3, monkeypatch):
+    """A long run of the named configuration goes to the table-driven kernel (trial launches of 16 384 steps, then the rest):
+    same chains, histograms, counters and snapshots as the speculative kernel, bit for bit."""
+    ens, tabs, T, lam = c3
+    monkeypatch.delenv("BCP_KERNEL", raising=False)
+    b = T.chains(N_CHAINS, 11, chain_lambda=lam)
+    a = b.sample(70000, burn=1000, traj_every=1000)
+    assert b.last_kernel() == "tab"
+    c = b.sample(40000, traj_every=800)                       # the verdict sticks to the block: no trial, one launch
+    assert b.last_kernel() == "tab"
+    b.close()
+    monkeypatch.setenv("BCP_KERNEL", "spec")
+    b2 = T.chains(N_CHAINS, 11, chain_lambda=lam)
+    a2 = b2.sample(70000, burn=1000, traj_every=1000)
+    c2 = b2.sample(40000, traj_every=800)
+    assert b2.last_kernel() == "spec"
+    b2.close()
+    for got, want in ((a, a2), (c, c2)):
+        for k in want:
+            assert np.array_equal(got[k], want[k]), k
+    assert a["state_counts"].sum() == N_CHAINS * 70000
+
+
 def test_c5_mbar_properties_at_full_size():
     """K = 11 runs x 6.4e5 samples (N = 7.04e6): f_0 = 0, gauge invariance, populations sum to one, and the
     solution satisfies the MBAR fixed-point equations to 1e-10."""
