@@ -53,8 +53,11 @@ namespace tabk {
 #ifndef TAB_NS
 #define TAB_NS 4                   // ring stages
 #endif
+#ifndef TAB_MRG0S
+#define TAB_MRG0S 15               // half-width of a freshly built window of a scalar restraint (32 slots: up to 15)
+#endif
 #ifndef TAB_MRG0
-#define TAB_MRG0 4                 // half-width of a freshly built window
+#define TAB_MRG0 6                 // half-width of a freshly built window (gamma restraint: both dimensions)
 #endif
 #ifndef TAB_MRGMIN
 #define TAB_MRGMIN 4               // the tabulator extends a window when the walker is closer than this to its edge ...
@@ -206,7 +209,7 @@ struct TabCfg {
     static constexpr int O_ACC = O_PN + 128;                // [32] accept bits | rebuilt << 16          (consumer -> helpers)
     static constexpr int O_E = O_ACC + 128;                 // [32] energy after the batch               (consumer -> accountant)
     static constexpr int STAGE = O_E + 256;
-    static_assert(BL == 8 && NS >= 2 && RS <= 4 && TAB_MRGMIN <= TAB_MRG0, "batch / ring / field shape");
+    static_assert(BL == 8 && NS >= 2 && RS <= 4 && TAB_MRGMIN <= TAB_MRG0 && TAB_MRGMIN <= TAB_MRG0S && TAB_MRG0S <= 15, "batch / ring / field shape");
 };
 // raw proposal word: bit 31 nuisance move {bits 1:0 dsigma + 1, 3:2 dgamma + 1, 6:4 restraint}, else the proposed state;
 // packed positions: 7-bit fields in bytes (mod 128; a table slot is position & 31 for a scalar restraint, & 15 in either
@@ -339,18 +342,18 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     };
     // the windows of chain L around positions (ps, pn) whose true indices are idx[] / gi: all lanes of the warp
     auto build_chain = [&](int L, uint32_t ps, uint32_t pn, const int* idx, int gi) {
-        constexpr int W0 = 2 * TAB_MRG0 + 1;
-        constexpr int NC = RS * W0 + (HG ? W0 * W0 : 0);
+        constexpr int W0 = 2 * TAB_MRG0 + 1, W0S = 2 * TAB_MRG0S + 1;
+        constexpr int NC = RS * W0S + (HG ? W0 * W0 : 0);
         for (int e = lane; e < NC; e += 32) {
-            if (e < RS * W0) {
-                const int k = e / W0, d = e - k * W0 - TAB_MRG0;
+            if (e < RS * W0S) {
+                const int k = e / W0S, d = e - k * W0S - TAB_MRG0S;
                 const int p = (int)((ps >> (8 * k)) & 127u);
                 int ik = 0;
 #pragma unroll
                 for (int q = 0; q < RS; ++q) ik = q == k ? idx[q] : ik;
                 sts64d(cell_addr(L, k, (p + d) & 31), cell_value(L, k, wrap1(ik + d, T.r[k].n_sigma), 0));
             } else if (HG) {
-                const int e2 = e - RS * W0;
+                const int e2 = e - RS * W0S;
                 const int dg = e2 / W0 - TAB_MRG0, dp = e2 - (e2 / W0) * W0 - TAB_MRG0;
                 const int p = (int)(pn & 127u), g = (int)((pn >> 8) & 127u);
                 sts64d(cell_addr(L, QG, ((p + dp) & 15) | (((g + dg) & 15) << 4)),
@@ -485,7 +488,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             const int k = f < R ? f : QG;
             nf[f] = f < R ? T.r[k].n_sigma : G;
             ifull[f] = f < R ? C.isg[(size_t)k * n + c] : C.igm[(size_t)QG * n + c];
-            pfull[f] = 0; lo[f] = -TAB_MRG0; hi[f] = TAB_MRG0;
+            pfull[f] = 0; lo[f] = f < RS ? -TAB_MRG0S : -TAB_MRG0; hi[f] = -lo[f];
             lop[f] = lo[f]; hip[f] = hi[f]; lo_cur[f] = lo[f]; hi_cur[f] = hi[f];
         }
         // ---- prologue: stage the chains' current states, build every window around position 0 ----
@@ -606,7 +609,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                     const int span = f < RS ? 31 : 15, mrg = f < RS ? TAB_MRG_S : TAB_MRG_N;     // slots - 1
                     const int p = pfull[f];
                     int l = lo[f], h = hi[f];
-                    if (reb) { l = p - TAB_MRG0; h = p + TAB_MRG0; lo[f] = l; hi[f] = h; lop[f] = l; hip[f] = h; }   // rebuilt by the consumer's careful path
+                    if (reb) { l = p - (f < RS ? TAB_MRG0S : TAB_MRG0); h = p + (f < RS ? TAB_MRG0S : TAB_MRG0); lo[f] = l; hi[f] = h; lop[f] = l; hip[f] = h; }   // rebuilt by the consumer's careful path
                     else {
                         // extend towards the walker; the new window and the two before it together span at most `slots` positions, so
                         // a slot that the consumer may still read (it works with one of the two previous windows) is never rewritten
@@ -882,6 +885,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
     constexpr uint32_t HS = 0x80808080u, HN = 0x00008080u;
     // windows: valid where ((P + neglo) & mask) + marg has no bit 7 set in any field
     constexpr uint32_t NL0 = (uint32_t)TAB_MRG0 * 0x01010101u, MG0 = (uint32_t)(127 - 2 * TAB_MRG0) * 0x01010101u;
+    constexpr uint32_t NL0S = (uint32_t)TAB_MRG0S * 0x01010101u, MG0S = (uint32_t)(127 - 2 * TAB_MRG0S) * 0x01010101u;
     uint32_t ov_nls = 0, ov_mgs = 0, ov_nln = 0, ov_mgn = 0;  // windows of the chains the careful path has just rebuilt
     int rebat = -1;                                           // the batch of the chain's last rebuild
 
@@ -966,7 +970,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             const uint32_t rb = rect0 + (uint32_t)(xw % 3) * 768u + lane4;
             nls = lds32(rb); mgs = lds32(rb + 128u); nln = lds32(rb + 256u); mgn = lds32(rb + 384u);
         } else {
-            nls = NL0; mgs = MG0; nln = NL0 & MN; mgn = MG0 & 0xffffu;
+            nls = NL0S; mgs = MG0S; nln = NL0 & MN; mgn = MG0 & 0xffffu;
 #pragma unroll
             for (int f = RS; f < 4; ++f) { nls &= ~(0xffu << (8 * f)); mgs |= 127u << (8 * f); }
             if (!HG) { nln = 0u; mgn = 127u | (127u << 8); }
@@ -1235,9 +1239,9 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 rebw = 1u << 16;
                 rebat = b;
                 // window [P - MRG0, P + MRG0] in every field
-                ov_nls = ((((MS - Ps) + 0x01010101u) & MS) + (NL0 & MS)) & MS;
+                ov_nls = ((((MS - Ps) + 0x01010101u) & MS) + (NL0S & MS)) & MS;
                 ov_nln = ((((MN - Pn) + 0x00000101u) & MN) + (NL0 & MN)) & MN;
-                ov_mgs = MG0; ov_mgn = MG0 & 0xffffu;
+                ov_mgs = MG0S; ov_mgn = MG0 & 0xffffu;
 #pragma unroll
                 for (int f = RS; f < 4; ++f) { ov_nls &= ~(0xffu << (8 * f)); ov_mgs |= 127u << (8 * f); }
                 if (!HG) { ov_nln = 0u; ov_mgn = 127u | (127u << 8); }
