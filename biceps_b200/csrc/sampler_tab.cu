@@ -370,6 +370,24 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             for (int k = lane; k < GS; k += 32) sts64d(row0 + ((uint32_t)L * (uint32_t)GS + (uint32_t)k) * 8u, gh4[(size_t)st * GS + k]);
     };
 
+    // ---- prologue, all working warps: the chains' current states into shared memory, every window built around position 0
+    //      (262 cells per chain at C3: a warp takes every 11th chain) ----
+    {
+        constexpr int NPW = HG ? 11 : 10;
+        const int pw = warp < 4 ? warp : (warp < 8 ? warp - 1 : (warp < 12 ? warp - 2 : warp - 3));
+        for (int L = pw; L < 32; L += NPW) {
+            long long cL = (long long)blockIdx.x * 32 + L;
+            if (cL >= n) cL = n - 1;
+            stage_state(L, C.state[cL], C.lam[cL]);
+            __syncwarp();
+            int idx[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) idx[k] = C.isg[(size_t)k * n + cL];
+            build_chain(L, 0u, 0u, idx, HG ? C.igm[(size_t)QG * n + cL] : 0);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");
+    }
+
     if ((warp >= 1 && warp <= 3) || warp == 11) {
         // =====================================================================================
         // generators: Philox + decode.  EVERY batch is generated by all four warps, two steps each: what the ring's depth has to
@@ -490,22 +508,6 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             ifull[f] = f < R ? C.isg[(size_t)k * n + c] : C.igm[(size_t)QG * n + c];
             pfull[f] = 0; lo[f] = f < RS ? -TAB_MRG0S : -TAB_MRG0; hi[f] = -lo[f];
             lop[f] = lo[f]; hip[f] = hi[f]; lo_cur[f] = lo[f]; hi_cur[f] = hi[f];
-        }
-        // ---- prologue: stage the chains' current states, build every window around position 0 ----
-        {
-            const int st_mine = C.state[c];
-            for (int L = 0; L < 32; ++L)
-                stage_state(L, __shfl_sync(SPEC_FULL, st_mine, L), __shfl_sync(SPEC_FULL, lam, L));
-            __syncwarp();
-            for (int L = 0; L < 32; ++L) {
-                int idx[R];
-#pragma unroll
-                for (int k = 0; k < R; ++k) idx[k] = __shfl_sync(SPEC_FULL, ifull[k], L);
-                const int gi = HG ? __shfl_sync(SPEC_FULL, ifull[NF - 1], L) : 0;
-                build_chain(L, 0u, 0u, idx, gi);
-            }
-            __syncwarp();
-            mbar_arrive(b_tab + 24u);
         }
         const uint32_t lane_lt = (1u << lane) - 1u;
         uint32_t n1 = 0, n2 = 0;
@@ -941,7 +943,6 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         gj = HG ? wrap1(gib + ((int)(((((pnj >> 8) & 127u) - ((pnb >> 8) & 127u)) + 64u) & 127u) - 64), G) : 0;
     };
 
-    mbar_wait(b_tab + 24u, 0u);                               // the initial tables
 #pragma unroll
     for (int k = 0; k < R; ++k) t[k] = lds64(tabl + (uint32_t)((HG && k == QG) ? 32 * RS : 32 * k) * 256u);
 
