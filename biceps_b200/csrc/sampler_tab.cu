@@ -1056,10 +1056,10 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         constexpr int CU = TAB_CU;
 #pragma unroll CU
         for (int j = 0; j < BL; ++j) {
-            // (the next step's words are loaded a step ahead; the last iteration re-reads its own)
-            const uint32_t jn = (uint32_t)(j + 1 < BL ? j + 1 : j);
-            const uint4 wn = lds128u(rs + F::O_W + 512u * jn + 16u * (uint32_t)lane);
-            const double2 txn = lds128(rs + F::O_TX + 512u * jn + 16u * (uint32_t)lane);
+            // (the next step's words are loaded a step ahead; the last iteration reads the 512 bytes after its array -- the next
+            // array of the stage -- and drops them)
+            const uint4 wn = lds128u(rs + F::O_W + 512u * (uint32_t)(j + 1) + 16u * (uint32_t)lane);
+            const double2 txn = lds128(rs + F::O_TX + 512u * (uint32_t)(j + 1) + 16u * (uint32_t)lane);
             const uint32_t Ps2 = (Ps + w.x) & MS, Pn2 = (Pn + w.y) & MN;
             const uint32_t x = __byte_perm(Ps2, Pn2, w.z);
             const uint32_t e = (x & (0xfu | ((w.z >> 16) & 0x10u))) | ((x >> 4) & 0xf0u);
