@@ -408,6 +408,8 @@ struct bcp_chains {
     std::vector<int> h_lam;                 // lambda index of every chain (bcp_chains_score)
     int spec_verdict = 0;                   // 0 undecided, 1 keep the speculative kernel, -1 its batches roll back too often
     int tab_verdict = 0, tab_trials = 0;    // table-driven kernel (its rollback unit is 8 x larger): 0 undecided, 1 keep, -1 not for this ensemble
+    double tab_ms_step = 0.0, alt_ms_step = 0.0;   // measured time per step of the last trial launch of the table-driven kernel / of the other choice
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaStream_t copy_stream = nullptr;     // device -> host copies of finished snapshots (bcp_sample)
     long long snaps_piped = 0;
     int last_launches = 0;
@@ -726,6 +728,8 @@ extern "C" void bcp_chains_destroy(bcp_chains* c) {
     pool_free(c->d_trace);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_chunk) cudaEventDestroy(c->ev_chunk);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     bcp_handle* h = c->h;
@@ -875,20 +879,35 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
     // (a block that is a candidate for the table-driven kernel goes straight to its trial launches: the pilot only follows if
     // those hand the block back)
     const bool tab_first = spec_auto && which == 5 && c->tab_verdict >= 0 && c->spec_verdict == 0 && total >= 2 * 16384;
-    const long long pilot = (spec_auto && c->spec_verdict == 0 && total >= 8192 && !tab_first) ? 1024 : 0;
+    const bool tab_kept = spec_auto && which == 5 && c->tab_verdict == 1;     // (its trials are behind it: no pilot either)
+    const long long pilot = (spec_auto && c->spec_verdict == 0 && total >= 8192 && !tab_first && !tab_kept) ? 1024 : 0;
     // The table-driven kernel redoes 256 chain-steps where spec redoes 32, and an accepted state move rebuilds a chain's tables:
-    // it is kept only where its own rollback fraction is small.  The first steps of a chain are no measure (indices drifting from
-    // the middle of their grids, E = 1e99), so the kernel is tried in launches of 16 384 steps -- the first that rolls back less
-    // than 6 % of its batches keeps it; six that do not, or one beyond 25 %, hand the block to the other kernels (as do runs
-    // shorter than 32 768 steps).
+    // it is kept where its own rollback fraction is small, or where the clock says so.  The first steps of a chain are no measure
+    // (indices drifting from the middle of their grids, E = 1e99), so the kernel is tried in launches of 16 384 steps: the first
+    // that rolls back less than 6 % of its batches keeps it, one beyond 50 % drops it.  In between a block's first trial is
+    // repeated, and from the second on the trial's measured time per step decides, against a timed launch of 4096 steps of the
+    // kernel that would run otherwise (every kernel writes the same bits: a trial costs nothing but its own slowness); four lost
+    // comparisons hand the block to the other kernels, as do runs shorter than 32 768 steps.
     const bool tab_auto = spec_auto && which == 5;
     const long long tab_trial_steps = 16384;
     if (tab_auto && (c->tab_verdict < 0 || (c->tab_verdict == 0 && total < 2 * tab_trial_steps))) which = which_no_tab;
     if (pilot && which == 5) which = 3;                      // (the pilot itself runs on the spec kernel)
     unsigned long long tab_stats0[2] = {0, 0};
-    bool tab_trial = false;
+    bool tab_trial = false, alt_trial = false, timing = false;
+    long long trial_steps = 0;
     for (long long s0 = 0, s1 = 0; s0 < total; s0 = s1) {
         s1 = (pilot && s0 == 0) ? pilot : s0 + chunk;
+        if (alt_trial) {                                     // the timed launch of the other kernel that has just been queued
+            float ms = 0.f;
+            BCP_CUDA(cudaEventSynchronize(c->ev_t1));
+            BCP_CUDA(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+            c->alt_ms_step = (double)ms / (double)trial_steps;
+            alt_trial = false;
+            if (c->tab_ms_step < c->alt_ms_step) c->tab_verdict = 1;
+            else if (++c->tab_trials >= 5) c->tab_verdict = -1;
+            which = c->tab_verdict >= 0 && total - s0 >= tab_trial_steps ? 5 : which_no_tab;
+            if (getenv("BCP_SPEC_STATS")) fprintf(stderr, "bcp tab trial: %.3f us per step against %.3f us -> verdict %d\n", 1e3 * c->tab_ms_step, 1e3 * c->alt_ms_step, c->tab_verdict);
+        }
         if (pilot && s0 == pilot) {
             unsigned long long stats[2] = {0, 0};
             BCP_CUDA(cudaMemcpyAsync(stats, c->C.spec_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
@@ -903,18 +922,35 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
             BCP_CUDA(cudaMemcpyAsync(stats, c->C.spec_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
             BCP_CUDA(cudaStreamSynchronize(st));
             const double nb = (double)(stats[0] - tab_stats0[0]), nr = (double)(stats[1] - tab_stats0[1]);
-            if (nb > 0 && nr < 0.06 * nb) c->tab_verdict = 1;
-            else if (++c->tab_trials >= 6 || nr > 0.25 * nb) { c->tab_verdict = -1; which = which_no_tab; }     // (far off: no second trial)
-            if (getenv("BCP_SPEC_STATS")) fprintf(stderr, "bcp tab trial: %.0f of %.0f batches rolled back -> verdict %d\n", nr, nb, c->tab_verdict);
+            float ms = 0.f;
+            BCP_CUDA(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+            c->tab_ms_step = (double)ms / (double)trial_steps;
             tab_trial = false;
+            if (nb > 0 && nr < 0.06 * nb) c->tab_verdict = 1;
+            else if (nr > 0.5 * nb) c->tab_verdict = -1;                                     // (far off: no second trial)
+            else if (c->tab_trials++ == 0) {}                                                // (a block's first trial: its chains' first steps)
+            else if (c->alt_ms_step <= 0.0) alt_trial = true;                                // the other kernel's time first
+            else if (c->tab_ms_step < c->alt_ms_step) c->tab_verdict = 1;
+            else if (++c->tab_trials >= 5) c->tab_verdict = -1;
+            if (c->tab_verdict < 0 || alt_trial) which = which_no_tab;
+            if (getenv("BCP_SPEC_STATS")) fprintf(stderr, "bcp tab trial: %.0f of %.0f batches rolled back, %.3f us per step -> verdict %d\n", nr, nb, 1e3 * c->tab_ms_step, c->tab_verdict);
         }
-        if (tab_auto && which == 5 && c->tab_verdict == 0 && !(pilot && s0 == 0)) {
+        if (alt_trial) {
+            if (s1 > s0 + 4096) s1 = s0 + 4096;
+            timing = true;
+        } else if (tab_auto && which == 5 && c->tab_verdict == 0 && !(pilot && s0 == 0)) {
             BCP_CUDA(cudaMemcpyAsync(tab_stats0, c->C.spec_stats, sizeof(tab_stats0), cudaMemcpyDeviceToHost, st));
             BCP_CUDA(cudaStreamSynchronize(st));
             if (s1 > s0 + tab_trial_steps) s1 = s0 + tab_trial_steps;
             tab_trial = true;
+            timing = true;
         }
         if (s1 > total) s1 = total;
+        if (timing) {
+            if (!c->ev_t0) { BCP_CUDA(cudaEventCreate(&c->ev_t0)); BCP_CUDA(cudaEventCreate(&c->ev_t1)); }
+            BCP_CUDA(cudaEventRecord(c->ev_t0, st));
+            trial_steps = s1 - s0;
+        }
         A.s_begin = s0;
         A.s_end = s1;
         const bool fast = which == 1;
@@ -965,6 +1001,7 @@ static int sample_launch_impl(bcp_chains* c, const bcp_sample_cfg* cfg, void* st
         if (e != cudaSuccess) { set_error("mcmc_kernel launch failed: %s", cudaGetErrorString(e)); return BCP_ERR_CUDA; }
         c->last_kernel = kname;
         ++launches;
+        if (timing) { BCP_CUDA(cudaEventRecord(c->ev_t1, st)); timing = false; }
         if (pipe) {
             // snapshots m with burn + m * traj_every < s_end are final once this launch has finished
             long long done = A.s_end <= cfg->burn ? 0 : (A.s_end - cfg->burn + cfg->traj_every - 1) / cfg->traj_every;

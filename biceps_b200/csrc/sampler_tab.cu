@@ -1155,8 +1155,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < R; ++k) t[k] = sv_t[k];
             accb = 0;
-            // the tabulator has finished batch b - 1 (and is now idle until this batch is published): the careful path may rebuild tables
-            if (b >= 1) mbar_wait(b_tab + 8u * (uint32_t)((b - 1) % 3), (uint32_t)((b - 1) / 3) & 1u);
+            trace_t(b, 8);
             // the fast path's step with a vote after each test: whatever it cannot decide is evaluated exactly on the spot, for the
             // lanes concerned (true indices = the tabulator's checkpoint + the positions' progress since)
             bool reb = false;                                 // the lane's chain has changed its state in this batch: its tables are stale
@@ -1175,7 +1174,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 if (__any_sync(SPEC_FULL, bad)) {             // outside the tabulated window (or stale tables): the exact term
                     if (bad) {
                         int idj[R], gj, ir = 0;
-                        true_indices(b >= 1, b >= 1 ? (b - 1) % 3 : 0, Ps2, Pn2, idj, gj);
+                        true_indices(xw >= 0, xw >= 0 ? xw % 3 : 0, Ps2, Pn2, idj, gj);
 #pragma unroll
                         for (int k = 0; k < R; ++k) ir = r == k ? idj[k] : ir;
                         tp = cell_value(lane, r, ir, gj);
@@ -1199,7 +1198,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                     bool accst = false;
                     if (lbf) {
                         int idj[R], gj;
-                        true_indices(b >= 1, b >= 1 ? (b - 1) % 3 : 0, Ps, Pn, idj, gj);
+                        true_indices(xw >= 0, xw >= 0 ? xw % 3 : 0, Ps, Pn, idj, gj);
                         En = eval_state((int)dw, idj, gj, xk);
                         acc = (En < E) || metropolis_accept(__dsub_rn(E, En), uniform_of(cs0 + j - cpad));
                         accst = acc && (int)dw != cstate;     // (the chain's own state proposed: accepted, nothing changes)
@@ -1223,10 +1222,14 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                     accb |= 1u << j;
                 }
             }
+            trace_t(b, 10);
             int idx[R], gi;
-            true_indices(b >= 1, b >= 1 ? (b - 1) % 3 : 0, Ps, Pn, idx, gi);        // (the rebuild below)
-            // rebuild the tables of the chains that changed their state, around their positions at the end of the batch
+            true_indices(xw >= 0, xw >= 0 ? xw % 3 : 0, Ps, Pn, idx, gi);           // (the rebuild below)
+            // rebuild the tables of the chains that changed their state, around their positions at the end of the batch -- once
+            // the tabulator has finished batch b - 1 (it is then idle until this batch is published, and nobody else writes tables)
             uint32_t m = __ballot_sync(SPEC_FULL, reb);
+            trace_t(b, 9);
+            if (m && b >= 1) mbar_wait(b_tab + 8u * (uint32_t)((b - 1) % 3), (uint32_t)((b - 1) / 3) & 1u);
             while (m) {
                 const int L = __ffs((int)m) - 1;
                 m &= m - 1;
