@@ -102,6 +102,9 @@ namespace tabk {
 #ifndef TAB_NG
 #define TAB_NG 3                   // generator warps (3 or 4: warp 11 joins)
 #endif
+#ifndef TAB_CELLPAR
+#define TAB_CELLPAR 1    // the tabulator's new scalar cells: one (chain, restraint) at a time across the lanes (0: a queue of cells)
+#endif
 #ifndef TAB_SPEC2
 #define TAB_SPEC2 0                // 1: the consumer looks the next step's proposal up under both outcomes of the current step (the address
                                    // computation and the load leave the dependent chain).  Bit-identical, measured: 14.28 ms against 14.16 ms per
@@ -582,9 +585,10 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             mbar_arrive(b_free + 8u * (uint32_t)stage);
             if (TAB_T_NOTAB) { mbar_arrive(b_tab + 8u * (uint32_t)(b % 3)); continue; }
             // walkers that left their trigger window (packed test, like the consumer's), chains rebuilt by the careful path
-            const bool trig_s = reb || ((((ps + tls) & MS) + tgs) & HS) != 0u;
+            // (per scalar restraint: bit 8 f + 7 of the warp's OR -- the window policy and the cell loops skip the others)
+            const uint32_t any_fs = RS > 0 ? __reduce_or_sync(SPEC_FULL, reb ? HS : (((ps + tls) & MS) + tgs) & HS) : 0u;
             const bool trig_n = HG && (reb || ((((pn + tln) & MN) + tgn) & HN) != 0u);
-            const bool any_s = RS > 0 && __any_sync(SPEC_FULL, trig_s), any_n = HG && __any_sync(SPEC_FULL, trig_n);
+            const bool any_s = any_fs != 0u, any_n = HG && __any_sync(SPEC_FULL, trig_n);
             // the scalar restraints and the gamma restraint are handled separately: with 32-slot windows the scalars rarely trigger
             trace_t(b, 0);
             const bool per = (b & 3) == 3, do_s = any_s || (RS > 0 && per), do_n = any_n || (HG && per);
@@ -607,7 +611,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
                     lo_n[f] = lo[f]; hi_n[f] = hi[f];
-                    if (!(f < RS ? any_s : any_n)) continue;
+                    if (!(f < RS ? (any_fs >> (8 * f + 7)) & 1u : (uint32_t)any_n)) continue;
                     const int span = f < RS ? 31 : 15, mrg = f < RS ? TAB_MRG_S : TAB_MRG_N;     // slots - 1
                     const int p = pfull[f];
                     int l = lo[f], h = hi[f];
@@ -626,17 +630,36 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 if (any_s) {
 #pragma unroll
                     for (int f = 0; f < RS; ++f) {
+                        if (!((any_fs >> (8 * f + 7)) & 1u)) continue;
                         // positions hi+1 .. hi_n, then lo_n .. lo-1 (either range may be empty)
                         const int up0 = imax(hi[f] + 1, lo_n[f]), nup = imax(hi_n[f] - up0 + 1, 0);
                         const int dn1 = imin(lo[f] - 1, hi_n[f]), ndn = imax(dn1 - lo_n[f] + 1, 0);
                         const int cnt = nup + ndn;
+#if TAB_CELLPAR
+                        // one (chain, restraint) at a time, its new cells (at most 31) across the lanes: few chains move a window
+                        // in a batch, and a loop over cells with a vote per cell is what a single warp is slowest at
+                        uint32_t m = __ballot_sync(SPEC_FULL, cnt > 0);
+                        while (m) {
+                            const int L = __ffs((int)m) - 1;
+                            m &= m - 1;
+                            const int up0L = __shfl_sync(SPEC_FULL, up0, L), nupL = __shfl_sync(SPEC_FULL, nup, L);
+                            const int loL = __shfl_sync(SPEC_FULL, lo_n[f], L), cntL = __shfl_sync(SPEC_FULL, cnt, L);
+                            const int baseL = __shfl_sync(SPEC_FULL, ifull[f] - pfull[f], L);
+                            if (lane < cntL) {
+                                const int q = lane < nupL ? up0L + lane : loL + (lane - nupL);
+                                sts64d(cell_addr(L, f, q & 31), cell_value(L, f, wrap1(baseL + q, T.r[f].n_sigma), 0));
+                            }
+                        }
+#else
                         for (int i = 0; __any_sync(SPEC_FULL, i < cnt); ++i) {
                             const int q = i < nup ? up0 + i : lo_n[f] + (i - nup);
                             const int ii = wrap1(ifull[f] + (q - pfull[f]), nf[f]);
                             emit1(i < cnt, (uint32_t)lane | ((uint32_t)f << 5) | ((uint32_t)(q & 31) << 8) | ((uint32_t)ii << 13));
                         }
+#endif
                     }
-                    if (n1) process1();
+                    if (!TAB_CELLPAR && n1) process1();
+                    __syncwarp();
                 }
                 trace(b, 3);
                 // ---- new cells: the gamma restraint (new sigma columns over the new gamma range, new gamma rows over the new
