@@ -246,6 +246,26 @@ struct BatchIter {
     }
 };
 
+// an accountant's 16-bin histogram window of one chain into the global histogram (a walker has left the window): rare, and
+// kept out of line -- the accountants' loop has to stay small for the instruction cache
+__device__ __noinline__ void flush_window(uint32_t hw, int wb, int nn, unsigned long long* bins) {
+#pragma unroll 1
+    for (int b4 = 0; b4 < 16; b4 += 4) {                                     // (four loads in flight: the walk is latency, not work)
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = lds32(hw + (uint32_t)(b4 + u) * 128u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (v[u]) {
+                int gi = wb + b4 + u;
+                gi -= gi >= nn ? nn : 0;
+                atomicAdd(bins + gi, (unsigned long long)v[u]);
+                sts32(hw + (uint32_t)(b4 + u) * 128u, 0u);
+            }
+        }
+    }
+}
+
 template <int R, bool HG, int NSV>
 __global__ void __launch_bounds__(448, 1)
 mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__ ChainBuffers C,
@@ -754,17 +774,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             int off = z.idx - z.wb;
             off += off < 0 ? z.nn : 0;
             if (ev && (uint32_t)off >= 16u) {                                // (rare, divergent: no vote)
-#pragma unroll 1
-                for (int bq = 0; bq < 16; ++bq) {
-                    const uint32_t a = z.hw + (uint32_t)bq * 128u;
-                    const uint32_t v = lds32(a);
-                    if (v) {
-                        int gi = z.wb + bq;
-                        gi -= gi >= z.nn ? z.nn : 0;
-                        atomicAdd(z.bins + gi, (unsigned long long)v);
-                        sts32(a, 0u);
-                    }
-                }
+                flush_window(z.hw, z.wb, z.nn, z.bins);
                 z.wb = z.idx - 8;
                 z.wb += z.wb < 0 ? z.nn : 0;
                 off = 8;
