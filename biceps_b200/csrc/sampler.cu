@@ -1073,6 +1073,11 @@ extern "C" int bcp_chains_sync(bcp_chains* c) {
         BCP_CUDA(cudaMemcpy(stats, c->C.spec_stats, sizeof(stats), cudaMemcpyDeviceToHost));
         fprintf(stderr, "bcp spec stats: %llu batches, %llu rolled back (guard band %llu, window %llu, state move %llu; %llu lower-bound resolutions, %llu accepted)\n",
                 stats[0], stats[1], stats[2], stats[3], stats[4], stats[5], stats[6]);
+        if (getenv("BCP_TAB_STATS")) {    // (a TAB_STATS build of the table-driven kernel: cycles and counts of lane 0's second looks, by outcome)
+            unsigned long long x[6] = {0};
+            BCP_CUDA(cudaMemcpy(x, c->C.spec_stats + 7, sizeof(x), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "bcp tab second looks: resolved %llu (%llu cycles), replayed %llu (%llu cycles), careful %llu (%llu cycles)\n", x[3], x[0], x[4], x[1], x[5], x[2]);
+        }
         if (getenv("BCP_TAB_TRACE")) {
             static unsigned long long tr[40 * 14 * 4];
             BCP_CUDA(cudaMemcpy(tr, c->C.spec_stats + 8, sizeof(tr), cudaMemcpyDeviceToHost));

@@ -105,6 +105,19 @@ namespace tabk {
 #ifndef TAB_CELLPAR
 #define TAB_CELLPAR 1    // the tabulator's new scalar cells: one (chain, restraint) at a time across the lanes (0: a queue of cells)
 #endif
+#ifndef TAB_REPLAY
+#define TAB_REPLAY 0     // 1: an accepted state move found after a fast batch: that chain's remaining steps replayed by its lane alone
+                         // instead of a careful batch.  Built, bit-identical (90 fuzz cases), 6 x fewer careful batches on C3 (8 300
+                         // cycles per replay against 14 500 per careful batch) -- and no faster: C3 13.85 against 13.57 ms per 100 000
+                         // steps, C2 1.64e10 against 1.58e10, end-to-end kernels 16.93 against 16.89 ms.  What the rare paths cost is
+                         // less their own cycles than the instruction-cache lines they evict for the 14 warps' loops
+#endif
+#ifndef TAB_NI_U
+#define TAB_NI_U 0       // 1: the rare paths' Philox redraw out of line (C3 +-1 %, C2 -6 %: the careful path pays the calls)
+#endif
+#ifndef TAB_NI_A
+#define TAB_NI_A 0       // 1: the rare paths' exact acceptance rule out of line (as above)
+#endif
 #ifndef TAB_SPEC2
 #define TAB_SPEC2 0                // 1: the consumer looks the next step's proposal up under both outcomes of the current step (the address
                                    // computation and the load leave the dependent chain).  Bit-identical, measured: 14.28 ms against 14.16 ms per
@@ -245,6 +258,15 @@ struct BatchIter {
         }
     }
 };
+
+// the consumer's rare paths draw a step's uniform again and apply the exact acceptance rule: out of line, one copy each (the
+// rare paths' code is fetched through the same instruction caches as the 14 warps' loops)
+__device__ __noinline__ double step_uniform(unsigned long long ctr, unsigned long long chain_id, unsigned long long seed) {
+    const Philox4 w = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)chain_id, (uint32_t)(chain_id >> 32),
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+    return spec_u2(w.w2, w.w3);
+}
+__device__ __noinline__ bool accept_exact(double d, double u) { return bcp::metropolis_accept(d, u); }
 
 // an accountant's 16-bin histogram window of one chain into the global histogram (a walker has left the window): rare, and
 // kept out of line -- the accountants' loop has to stay small for the instruction cache
@@ -926,12 +948,14 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
 
     // the Metropolis uniform of local step s (the rare paths only: the ring does not carry it)
     auto uniform_of = [&](int s) {
-        const unsigned long long chain_id = C.chain_id0 + (unsigned long long)c;
         const unsigned long long ctr = A.step0 + (unsigned long long)A.s_begin + (unsigned long long)(long long)s;
+        const unsigned long long chain_id = C.chain_id0 + (unsigned long long)c;
+        if (TAB_NI_U) return step_uniform(ctr, chain_id, C.seed);
         const Philox4 w = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)chain_id, (uint32_t)(chain_id >> 32),
                                         (uint32_t)C.seed, (uint32_t)(C.seed >> 32));
         return spec_u2(w.w2, w.w3);
     };
+    auto metropolis_accept = [&](double d, double u) { return TAB_NI_A ? accept_exact(d, u) : bcp::metropolis_accept(d, u); };
     // exact terms of proposed state i2 at the chain's indices (restraint 0 carries energy + logZ), reference order
     auto eval_state = [&](int i2, const int* idx, int gi, double* xk) {
         const double C2 = __dadd_rn(energy[i2], logZ);
@@ -1150,10 +1174,18 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         uint32_t rebw = 0;
         // (one vote decides whether anything at all needs a second look: almost always nothing does)
         const bool second_look = __any_sync(SPEC_FULL, rare || jf >= 0);
+        const long long t_sl0 = TAB_STATS ? clock64() : 0ll;
+        bool did_careful = false;
+        bool reb = false;                                     // the lane's chain has changed its state in this batch: its tables are stale
         if (second_look && !__any_sync(SPEC_FULL, rare)) {
             // ---- state-move proposals the lower bound could not reject: evaluated exactly at the chain's indices of that step
             //      (true indices = the tabulator's last checkpoint + the positions' progress since); almost all are rejected
             //      and the batch stands ----
+            bool moved = false;                               // ... accepted, to another state
+            int st_new = cstate;
+            double E_mv = 0.0, t_mv[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) t_mv[k] = 0.0;
             if (jf >= 0) {
                 int idj[R], gj;
                 true_indices(xw >= 0, xw >= 0 ? xw % 3 : 0, Psf, Pnf, idj, gj);
@@ -1165,17 +1197,84 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 // the chain's own state proposed (1 / S of the state moves): accepted, and nothing changes but the counters
                 // (unless E is not the energy of the chain's configuration yet: the initial 1e99, an energy set by the caller)
                 if (accf && (int)dw == cstate && __double_as_longlong(En) == __double_as_longlong(Ef) && !(TAB_DBG & 1)) accb |= 1u << jf;
+                else if (accf && TAB_REPLAY) {
+                    moved = true; st_new = (int)dw; E_mv = En;
+#pragma unroll
+                    for (int k = 0; k < R; ++k) t_mv[k] = xk[k];
+                }
                 else if (accf) rare = true;                                                    // accepted after all: the careful path
                 if (TAB_STATS) {
                     why |= 4u;
                     atomicAdd(C.spec_stats + 5, 1ull);                                           // resolutions
-                    if (rare) atomicAdd(C.spec_stats + 6, 1ull);                                 // ... that found an accepted move to another state
+                    if (rare || moved) atomicAdd(C.spec_stats + 6, 1ull);                        // ... that found an accepted move to another state
+                }
+            }
+            // ---- an accepted move to another state: the other chains of the warp keep their batch; this chain's remaining steps
+            //      are replayed by its lane alone, every term evaluated exactly from the new state's rows (its tables are stale).
+            //      Anything undecidable in the replay -- a second state move the lower bound cannot reject -- and the whole
+            //      batch takes the careful path after all ----
+            const uint32_t mvm = TAB_REPLAY ? __ballot_sync(SPEC_FULL, moved) : 0u;
+            if (mvm) {
+                for (uint32_t m = mvm; m; m &= m - 1) {
+                    const int L = __ffs((int)m) - 1;
+                    stage_state(L, __shfl_sync(SPEC_FULL, st_new, L), __shfl_sync(SPEC_FULL, lam, L));
+                }
+                __syncwarp();
+                bool fb = false;
+                uint32_t ab = 0u, Prs = Psf, Prn = Pnf;
+                if (moved) {
+                    ab = (accb & ((1u << jf) - 1u)) | (1u << jf);
+#pragma unroll 1
+                    for (int j = jf + 1; j < BL; ++j) {
+                        const uint32_t dwj = lds32(rs + F::O_DW + 128u * (uint32_t)j + lane4);
+                        const uint4 w = lds128u(rs + F::O_W + 512u * (uint32_t)j + 16u * (uint32_t)lane);
+                        const double2 txj = lds128(rs + F::O_TX + 512u * (uint32_t)j + 16u * (uint32_t)lane);
+                        if (!(E_mv < txj.y) && (int)dwj >= 0 && dwj != TAB_PAD) { fb = true; break; }
+                        const int r = (int)((w.z >> 16) & 7u);
+                        if (r >= R) continue;                        // (a state move the lower bound rejects, padding)
+                        const uint32_t Ps2 = (Prs + w.x) & MS, Pn2 = (Prn + w.y) & MN;
+                        int idj[R], gj, ir = 0;
+                        true_indices(xw >= 0, xw >= 0 ? xw % 3 : 0, Ps2, Pn2, idj, gj);
+#pragma unroll
+                        for (int k = 0; k < R; ++k) ir = r == k ? idj[k] : ir;
+                        const double tp = cell_value(lane, r, ir, gj);
+                        double xk[R];
+#pragma unroll
+                        for (int k = 0; k < R; ++k) xk[k] = r == k ? tp : t_mv[k];
+                        double En = xk[0];
+#pragma unroll
+                        for (int k = 1; k < R; ++k) En = __dadd_rn(En, xk[k]);
+                        const double Ahi = __dsub_rn(E_mv, txj.x), Alo = __dadd_rn(Ahi, 2.0 * TAB_MARGIN);
+                        bool acc = En < Ahi;
+                        if (!acc && !(En > Alo)) acc = (En < E_mv) || metropolis_accept(__dsub_rn(E_mv, En), uniform_of(cs0 + j - cpad));
+                        if (acc) {
+                            E_mv = En;
+#pragma unroll
+                            for (int k = 0; k < R; ++k) t_mv[k] = xk[k];
+                            Prs = Ps2; Prn = Pn2;
+                            ab |= 1u << j;
+                        }
+                    }
+                }
+                if (__any_sync(SPEC_FULL, fb)) {
+                    // (the careful path starts from the batch's first step: the chains' old states back into shared memory)
+                    for (uint32_t m = mvm; m; m &= m - 1) {
+                        const int L = __ffs((int)m) - 1;
+                        stage_state(L, __shfl_sync(SPEC_FULL, cstate, L), __shfl_sync(SPEC_FULL, lam, L));
+                    }
+                    __syncwarp();
+                    rare = true;
+                } else if (moved) {
+                    E = E_mv; Ps = Prs; Pn = Prn; accb = ab; cstate = st_new; reb = true;
+#pragma unroll
+                    for (int k = 0; k < R; ++k) t[k] = t_mv[k];
                 }
             }
         }
         if (second_look && __any_sync(SPEC_FULL, rare)) {
             // ---- careful batch: step by step from the raw proposal words, every rare case handled exactly ----
             ++n_rollbacks;
+            did_careful = true;
             if (TAB_STATS) {
                 const uint32_t w1 = __ballot_sync(SPEC_FULL, why & 1u), w2 = __ballot_sync(SPEC_FULL, why & 2u), w4 = __ballot_sync(SPEC_FULL, why & 4u);
                 if (lane == 0) {
@@ -1191,7 +1290,6 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             trace_t(b, 8);
             // the fast path's step with a vote after each test: whatever it cannot decide is evaluated exactly on the spot, for the
             // lanes concerned (true indices = the tabulator's checkpoint + the positions' progress since)
-            bool reb = false;                                 // the lane's chain has changed its state in this batch: its tables are stale
 #pragma unroll 1
             for (int j = 0; j < BL; ++j) {
                 const uint32_t dw = lds32(rs + F::O_DW + 128u * (uint32_t)j + lane4);
@@ -1256,8 +1354,10 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 }
             }
             trace_t(b, 10);
+        }
+        if (second_look && __any_sync(SPEC_FULL, reb)) {
             int idx[R], gi;
-            true_indices(xw >= 0, xw >= 0 ? xw % 3 : 0, Ps, Pn, idx, gi);           // (the rebuild below)
+            true_indices(xw >= 0, xw >= 0 ? xw % 3 : 0, Ps, Pn, idx, gi);
             // rebuild the tables of the chains that changed their state, around their positions at the end of the batch -- once
             // the tabulator has finished batch b - 1 (it is then idle until this batch is published, and nobody else writes tables)
             uint32_t m = __ballot_sync(SPEC_FULL, reb);
@@ -1283,6 +1383,10 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                 for (int f = RS; f < 4; ++f) { ov_nls &= ~(0xffu << (8 * f)); ov_mgs |= 127u << (8 * f); }
                 if (!HG) { ov_nln = 0u; ov_mgn = 127u | (127u << 8); }
             }
+        }
+        if (TAB_STATS && second_look && lane == 0) {             // cycles spent on second looks, by outcome (7: resolved only, 8: replay, 9: careful)
+            atomicAdd(C.spec_stats + (did_careful ? 9 : (rebw ? 8 : 7)), (unsigned long long)(clock64() - t_sl0));
+            atomicAdd(C.spec_stats + (did_careful ? 12 : (rebw ? 11 : 10)), 1ull);
         }
         // ---- publish the batch, release the stage ----------------------------------------------------
         sts32(rs + F::O_PS + lane4, Ps);
