@@ -108,6 +108,30 @@ def test_c3_long_run_automatic_choice_is_the_table_driven_kernel_and_changes_not
     assert a["state_counts"].sum() == N_CHAINS * 70000
 
 
+def test_c2_long_run_five_restraints_on_the_table_driven_kernel_changes_nothing(monkeypatch):
+    """BASELINE configs[1] (1000 states, cs_H / cs_Ca / cs_N / J / NOE, 8 lambdas x 1024 chains): five restraints leave room for a
+    two-stage ring only and a quarter of the first batches are redone -- the trial launches still keep the table-driven kernel
+    (rollback fraction, then the clock), and the results are those of the speculative kernel, bit for bit."""
+    from biceps_b200 import engine, precompute, synthetic
+    ens = synthetic.make_ensemble("C2", seed=0, n_lambda=8)
+    tabs = precompute.build_tables(ens["energies"], ens["lambdas"], ens["restraints"])
+    T = engine.DeviceTables(tabs)
+    n = 8192
+    lam = (np.arange(n) % 8).astype(np.int32)
+    monkeypatch.delenv("BCP_KERNEL", raising=False)
+    b = T.chains(n, 5, chain_lambda=lam)
+    a = b.sample(60000, burn=500, traj_every=2000)
+    assert b.last_kernel() == "tab"
+    b.close()
+    monkeypatch.setenv("BCP_KERNEL", "spec")
+    b2 = T.chains(n, 5, chain_lambda=lam)
+    a2 = b2.sample(60000, burn=500, traj_every=2000)
+    assert b2.last_kernel() == "spec"
+    b2.close(); T.close()
+    for k in a2:
+        assert np.array_equal(a[k], a2[k]), k
+
+
 def test_c5_mbar_properties_at_full_size():
     """K = 11 runs x 6.4e5 samples (N = 7.04e6): f_0 = 0, gauge invariance, populations sum to one, and the
     solution satisfies the MBAR fixed-point equations to 1e-10."""
