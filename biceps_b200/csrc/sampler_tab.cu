@@ -121,6 +121,9 @@ namespace tabk {
 #ifndef TAB_NI_A
 #define TAB_NI_A 0       // 1: the rare paths' exact acceptance rule out of line (as above)
 #endif
+#ifndef TAB_SLIDE
+#define TAB_SLIDE 1       // accountants: a sliding 16-bin histogram window (one bin emptied per move at its edge) instead of a re-centred one (all 16 flushed)
+#endif
 #ifndef TAB_SPEC2
 #define TAB_SPEC2 0                // 1: the consumer looks the next step's proposal up under both outcomes of the current step (the address
                                    // computation and the load leave the dependent chain).  Bit-identical, measured: 14.28 ms against 14.16 ms per
@@ -772,7 +775,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
         // a window of 16 histogram bins per chain and parameter in shared memory ([parameter][bin][chain], private to the
         // lane: plain read-modify-write): a chain keeps revisiting the same few bins
         const uint32_t hwdummy = acc0 + (uint32_t)(R + 1) * 16u * 128u + lane4;
-        struct Slot { int idx, since, wb, nn; uint32_t hw; unsigned long long* bins; unsigned int acc; };
+        struct Slot { int idx, since, wb, nn; uint32_t hw; unsigned long long* bins; unsigned int acc; int pos, wlo; };
         Slot sl[2];
         sl[0].nn = T.r[q0].n_sigma; sl[0].bins = g_param_counts + T.r[q0].hist_sigma; sl[0].idx = C.isg[(size_t)q0 * n + c];
         sl[1].nn = q1 == R ? G : T.r[R > 4 ? 4 : 0].n_sigma;
@@ -783,6 +786,7 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             sl[u].since = burn; sl[u].acc = 0;
             sl[u].hw = acc0 + (uint32_t)((u ? q1 : q0) * 16) * 128u + lane4;
             sl[u].wb = sl[u].idx - 8; sl[u].wb += sl[u].wb < 0 ? sl[u].nn : 0;
+            sl[u].pos = 0; sl[u].wlo = -8;
             if (u ? has1 : has0)
                 for (int bq = 0; bq < 16; ++bq) sts32(sl[u].hw + (uint32_t)bq * 128u, 0u);
         }
@@ -796,6 +800,34 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
             const int s = s0 + j - pad;
             const bool on = m != 0u, rec_on = s > burn;
             const bool ev = on && rec_on && live && s > z.since;
+#if TAB_SLIDE
+            // a SLIDING window of 16 bins, slot = position & 15, that always holds the walker: the run goes to the walker's bin, then
+            // the walker moves; a move that pushes the window's edge first empties the one slot the walker is about to take
+            {
+                const uint32_t a = ev ? z.hw + (uint32_t)(z.pos & 15) * 128u : hwdummy;
+                sts32(a, lds32(a) + (uint32_t)(s - z.since));
+                if (on) {
+                    const int d = ((ups >> j) & 1u) ? 1 : -1;
+                    z.idx = wrap1(z.idx + d, z.nn);
+                    z.pos += d;
+                    if ((uint32_t)(z.pos - z.wlo) >= 16u) {
+                        const uint32_t av = z.hw + (uint32_t)(z.pos & 15) * 128u;
+                        const uint32_t v = lds32(av);
+                        if (v) {
+                            int gi = z.idx - 16 * d;                  // the grid index of the position that leaves the window
+                            gi += gi < 0 ? z.nn : 0;
+                            gi -= gi >= z.nn ? z.nn : 0;
+                            atomicAdd(z.bins + gi, (unsigned long long)v);
+                            sts32(av, 0u);
+                        }
+                        z.wlo += d;
+                    }
+                }
+                z.since = (on && rec_on) ? s : z.since;
+                m &= m - 1u;
+                return;
+            }
+#endif
             int off = z.idx - z.wb;
             off += off < 0 ? z.nn : 0;
             if (ev && (uint32_t)off >= 16u) {                                // (rare, divergent: no vote)
@@ -919,6 +951,12 @@ mcmc_tab_kernel(const __grid_constant__ SamplerTables T, const __grid_constant__
                     const uint32_t v = lds32(z.hw + (uint32_t)bq * 128u);
                     int gi = z.wb + bq;
                     gi -= gi >= z.nn ? z.nn : 0;
+                    if (TAB_SLIDE) {                                 // slot bq holds the window's position p with p & 15 == bq
+                        const int pp = z.wlo + ((bq - z.wlo) & 15);
+                        gi = z.idx + (pp - z.pos);
+                        gi += gi < 0 ? z.nn : 0;
+                        gi -= gi >= z.nn ? z.nn : 0;
+                    }
                     if (v) atomicAdd(z.bins + gi, (unsigned long long)v);
                 }
                 if (q == R) C.igm[(size_t)QG * n + c] = z.idx;
